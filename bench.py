@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- decoded edges/sec (greedy) of the FaceFormer pointer-decode path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU arm (oracle port), rank 0 only
+
+A "step" is one pass of the hot path (model(batch): embedding + encoder + cross-K/V + the whole
+greedy loop) over one batch of synthetic wireframes.  Workload (BASELINE.json configs[1]):
+configs/ours.yml geometry (E=512, H=8, FF=1024, 6+6 layers, num_lines=216, T=37), batch=32
+wireframes per GPU, n_edges ~ U[24,216], greedy decode.  Metric: decoded edges/s = B*S / time, with
+B = N*F sequences the reference decodes per batch and S the executed decode steps.
+
+Keys beyond the base contract:
+  value     device-resident inputs/outputs, CUDA-event timed on the launching stream, max over ranks
+  e2e       same metric through the C ABI with HOST buffers (pinned): H2D of inputs and D2H of
+            `predict` inside the timed region
+  roofline  the dominant kernel (linear_kernel): algorithmic FLOPs per launch / event-timed duration,
+            measured on one extra (untimed) step with an event pair around every launch
+  cpu_baseline  the numpy oracle port timed on this box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from faceformer_b200 import synth  # noqa: E402
+from faceformer_b200.config import MODE_PARALLEL, OURS  # noqa: E402
+
+METRIC = "decoded_edges_per_sec"
+UNIT = "edges/s"
+WORKLOAD = "configs/ours.yml greedy decode, batch=32 wireframes/GPU, num_lines=216, T=37, n_edges~U[24,216]"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_burst=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+def cpu_sample(seed):
+    """Bounded sample of the workload for the CPU arm: ONE wireframe with 24 edges (the distribution's
+    smallest), full ours.yml model, all 36 decode steps -> 24*S decoded edges."""
+    cfg = OURS
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 1, seed=seed, num_edges=np.array([24], np.int64))
+    return cfg, batch
+
+
+def time_oracle(sd, seed, repeats=1):
+    from oracle import faceformer_oracle as orc
+    cfg, batch = cpu_sample(seed)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = orc.forward_eval(sd, cfg.to_dict(), MODE_PARALLEL, batch)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    edges = int(batch["num_input"].max()) * 1 * out["steps"]
+    return edges / best, best, edges
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (numpy restatement of the reference as written) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        import torch
+        torch.set_num_threads(os.cpu_count())
+    except Exception:
+        pass
+    sd = synth.synth_state_dict(OURS, MODE_PARALLEL, args.seed, "diverse")
+    times, edges = [], 0
+    for i in range(args.warmup + args.steps):
+        v, dt, edges = time_oracle(sd, args.seed)
+        if i >= args.warmup:
+            times.append(dt)
+    dt = float(np.mean(times))
+    value = edges / dt
+    sample = ("numpy/OpenBLAS port of forward_eval as written (oracle/faceformer_oracle.py), 1 wireframe x 24 edges, "
+              "full ours.yml model, 36 steps per step; the unmodified torch reference ran the same sample ~2.7x faster "
+              "in the build container (see DESIGN.md)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "1 wireframe x 24 edges per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from faceformer_b200.engine import Engine, pack_state_dict
+    from faceformer_b200.lib import FFB_OPT_PROFILE
+    from faceformer_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: faceformer_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, mode = OURS, MODE_PARALLEL
+    T = cfg.max_face_length
+
+    # weights: rank 0 builds the blob, NCCL broadcast over NVLink
+    eng = Engine(cfg, mode, local)
+    nw = eng.weight_count()
+    if rank == 0:
+        sd = synth.synth_state_dict(cfg, mode, args.seed, "diverse")
+        blob = torch.from_numpy(pack_state_dict(sd, cfg, mode)).to(dev)
+    else:
+        sd, blob = None, torch.empty(nw, dtype=torch.float32, device=dev)
+    sharding.broadcast_weights(blob, 0)
+    eng.load_blob(blob)
+
+    # one batch per rank (weak scaling: fixed work per GPU)
+    batch = synth.synth_batch(cfg, mode, args.batch, seed=args.seed + 1000 * rank)
+    N = args.batch
+    coords_h = torch.from_numpy(batch["input"].reshape(N, cfg.num_lines, -1)).pin_memory()
+    mask_h = torch.from_numpy(batch["input_mask"].astype(np.uint8)).pin_memory()
+    ni_h = torch.from_numpy(batch["num_input"]).pin_memory()
+    coords_d, mask_d, ni_d = coords_h.to(dev), mask_h.to(dev), ni_h.to(dev)
+    F = int(batch["num_input"].max())
+    pred_d = torch.empty((N, F, T), dtype=torch.int64, device=dev)
+    pred_h = torch.empty((N, F, T), dtype=torch.int64).pin_memory()
+    gather_in = torch.full((N, cfg.num_lines, T), -1, dtype=torch.int32, device=dev)
+    gather_out = torch.empty((world, N, cfg.num_lines, T), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def gather():
+        if world > 1:       # all-gather of the predicted face loops (fixed shape, int32)
+            gather_in[:, :F] = pred_d.to(torch.int32)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+
+    def step_device():
+        _, s = eng.forward_eval(coords_d, mask_d, ni_d, want_steps=True, out=pred_d)
+        gather()
+        return s
+
+    def step_host():
+        _, s = eng.forward_eval(coords_h.numpy(), mask_h.numpy(), ni_h.numpy(), want_steps=True, out=pred_h.numpy())
+        if world > 1:
+            pred_d.copy_(pred_h, non_blocking=True)
+            gather()
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s = 0
+        for _ in range(k):
+            s = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), s
+
+    for _ in range(args.warmup):
+        S = step_device()
+    info = eng.batch_info()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = eng.kernel_launches()
+    ms, S = timed(step_device, args.steps)
+    launches = eng.kernel_launches() - l0
+    clocks = sampler.stop() if sampler else None
+
+    edges_local = torch.tensor([float(info["B"] * S)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(edges_local)
+    edges_per_step = float(edges_local.item())
+    value = edges_per_step * args.steps / (ms / 1e3)
+
+    # end to end through the C ABI with host buffers
+    step_host()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e, _ = timed(step_host, e2e_steps)
+    e2e_value = edges_per_step * e2e_steps / (ms_e / 1e3)
+    h2d = coords_h.numel() * 4 + mask_h.numel() + ni_h.numel() * 8
+    d2h = pred_h.numel() * 8
+
+    # per-kernel-class breakdown and roofline of the dominant kernel, on one extra untimed step
+    eng.set_option(FFB_OPT_PROFILE, 1)
+    step_device()
+    prof = eng.profile_read()
+    eng.set_option(FFB_OPT_PROFILE, 0)
+    if rank == 0:
+        peaks = load_peaks()
+        tot_ms = sum(v["ms"] for v in prof.values())
+        lin = prof["linear"]
+        ach = lin["flops"] / (lin["ms"] * 1e-3) / 1e12 if lin["ms"] > 0 else 0.0
+        passes = 1                      # MMA passes of the precision mode: fp32 SIMT today (no tensor pipe yet)
+        peak = peaks["bf16_sustained"] / passes
+        roofline = {"bound": "tensor", "kernel": "linear_kernel (fp32 SIMT FFMA)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                    "avg_launch_ms": lin["ms"] / max(1, lin["launches"]), "launches_per_step": lin["launches"],
+                    "share_of_step": lin["ms"] / tot_ms if tot_ms else None,
+                    "fp32_ffma_peak_tflops": 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
+                    "breakdown_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+                    "breakdown_tflops": {k: (round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 3) if v["ms"] > 0 else 0.0) for k, v in prof.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, edges = time_oracle(sd, args.seed)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"oracle/faceformer_oracle.py (numpy), 1 wireframe x 24 edges, 36 steps = {edges} edges in {dt:.1f} s"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "wireframes_per_step_per_gpu": N, "sequences_per_step_per_gpu": info["B"],
+                       "sequences_decoded_per_gpu": info["B_eff"], "decode_steps": S, "memory_rows": info["R"],
+                       "weights": f"synthetic seed {args.seed} recipe diverse (32.3 M params, fp32)",
+                       "l2": "no explicit flush: per-step activations + cross-K/V cache are GBs, far larger than the 126 MB L2",
+                       "parallelism": f"dp{world} (whole batches per rank; NCCL weight broadcast + all-gather of predictions)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,839 @@
+// ffb200.cu -- host side of libffb200.so: handle, weight layout, batch planning, launch sequences
+// and the extern "C" entry points declared in include/ffb200.h.
+//
+// Data layout in HBM (all fp32 unless noted):
+//   weights   one blob in reference state_dict order (+ per-decoder-layer cross K/V weights re-packed
+//             as [Ld*E, E] so that all layers' cross-attention K (and V) come from ONE GEMM each)
+//   mem       packed edge memory [R, E], R = sum_i (n_valid_i + 4): only un-masked rows exist, so the
+//             key-padding mask of the reference (transformer.py:170,250) is realised structurally
+//   Kc, Vc    cross-attention K/V cache [R, Ld*E]: computed ONCE per wireframe (the reference
+//             re-projects them every step for every sequence, transformer.py:248-251)
+//   tok       int32 [T, B_eff] step-major token buffer (== `predicts`, model_para.py:207,229)
+//   x, x2, qkv, att, h   activations of the current step, rows ordered (sequence, position)
+#include "../../include/ffb200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ffb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct AttnW { const float *in_w, *in_b, *out_w, *out_b; };
+struct EncLayerW { AttnW sa; const float *l1w, *l1b, *l2w, *l2b, *n1w, *n1b, *n2w, *n2b; };
+struct DecLayerW { AttnW sa, ca; const float *l1w, *l1b, *l2w, *l2b, *n1w, *n1b, *n2w, *n2b, *n3w, *n3b; };
+
+struct Weights {
+    const float *tok_table, *e0w, *e0b, *e2w, *e2b, *pos, *qpos;
+    std::vector<EncLayerW> enc;
+    const float *enc_nw, *enc_nb;
+    std::vector<DecLayerW> dec;
+    const float *dec_nw, *dec_nb, *proj_w, *proj_b;
+    const float *ckw, *ckb, *cvw, *cvb;      // packed cross K / V weights of all decoder layers
+};
+
+}  // namespace
+
+struct ffb_handle {
+    ffb_config cfg;
+    int E, H, FF, L, T, Le, Ld;
+    std::string err;
+    bool weights_loaded = false, encoded = false, decoded = false;
+    int opt_dedup = 1, opt_prune = 1, opt_timing = 0;
+    int64_t launches = 0;
+
+    DevBuf wblob, wcross;
+    Weights w;
+
+    // batch plan (host)
+    int N = 0, F = 0;
+    long long B_full = 0, B = 0, R = 0, Re = 0;
+    int max_vlen = 0, max_seq_per_wf = 0;
+    std::vector<int> h_row_off, h_vlen, h_seq_off;
+    // batch plan (device)
+    DevBuf d_row_off, d_vlen, d_pos_idx, d_edge_src, d_edge_dst, d_seq_wf, d_seq_first, d_seq_off, d_slot_seq, d_seq_slot;
+    // staging for host-located inputs/outputs
+    DevBuf d_coords, d_predict, d_out_stage, d_mask_stage, d_prefix;
+    // persistent per batch
+    DevBuf mem, Kc, Vc, tok, logits, state;     // state: int[4] = stop, steps_run, nonstop_count, eos_count
+    // activations
+    DevBuf x, x2, qkv, att, hb, xl;
+    int last_P = 0;                               // P of the last executed pointer projection (seq2seq 'pointer')
+    // per-kernel-class profiling (FFB_OPT_PROFILE): event pairs around every launch
+    int opt_profile = 0;
+    std::vector<cudaEvent_t> prof_pool;
+    struct ProfRec { int cls; double flops; };
+    std::vector<ProfRec> prof_recs;
+    double sum_seq_vlen = 0, sum_vlen2 = 0;       // sum_i seqs_i*vlen_i and sum_i vlen_i^2 (attention FLOP accounting)
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    std::vector<uint8_t> h_mask;
+    std::vector<int64_t> h_num_input;
+};
+
+namespace {
+
+int fail(ffb_handle* h, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+    return fail((h), FFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+#define FFB_TRY(expr) do { int _r = (expr); if (_r != FFB_OK) return _r; } while (0)
+
+enum { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_ROWS, PC_ATTN_TILED, PC_POINTER, PC_OTHER, PC_COUNT };
+
+inline void prof_begin(ffb_handle* h, int cls, double flops, cudaStream_t s) {
+    if (!h->opt_profile) return;
+    const size_t i = h->prof_recs.size();
+    while (h->prof_pool.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); h->prof_pool.push_back(e); }
+    h->prof_recs.push_back({cls, flops});
+    cudaEventRecord(h->prof_pool[2 * i], s);
+}
+inline void prof_end(ffb_handle* h, cudaStream_t s) {
+    if (!h->opt_profile) return;
+    cudaEventRecord(h->prof_pool[2 * (h->prof_recs.size() - 1) + 1], s);
+}
+
+const char* validate_config(const ffb_config* c) {
+    if (!c) return "config is NULL";
+    if (c->abi_version != FFB_ABI_VERSION) return "abi_version mismatch";
+    if (c->mode != FFB_MODE_PARALLEL && c->mode != FFB_MODE_SEQ2SEQ) return "mode must be FFB_MODE_PARALLEL or FFB_MODE_SEQ2SEQ";
+    if (c->num_model <= 0 || c->num_model % 128 != 0 || c->num_model > 1024) return "num_model must be a multiple of 128, <= 1024";
+    if (c->num_head <= 0 || c->num_model != c->num_head * 64) return "head dim (num_model / num_head) must be 64";
+    if (c->num_feedforward <= 0 || c->num_feedforward % 4 != 0) return "num_feedforward must be a positive multiple of 4";
+    if (c->num_encoder_layers < 1 || c->num_decoder_layers < 1) return "need >= 1 encoder and decoder layer";
+    if (c->in_dim <= 0 || c->in_dim % 4 != 0) return "in_dim must be a positive multiple of 4";
+    if (c->num_lines < 1) return "num_lines must be >= 1";
+    if (c->num_token != 4) return "num_token must be 4 (PAD,SOS,SEP,EOS)";
+    if (c->seq_len < 2) return "seq_len must be >= 2";
+    if (c->device < 0) return "device must be >= 0";
+    return nullptr;
+}
+
+size_t weight_count(const ffb_config* c) {
+    const size_t E = c->num_model, FF = c->num_feedforward, L = c->num_lines + c->num_token, T = c->seq_len;
+    const size_t attn = 3 * E * E + 3 * E + E * E + E;
+    const size_t ffn = FF * E + FF + E * FF + E;
+    size_t n = c->num_token * E + E * c->in_dim + E + E * E + E + L * E + T * E;
+    n += (size_t)c->num_encoder_layers * (attn + ffn + 4 * E) + 2 * E;
+    n += (size_t)c->num_decoder_layers * (2 * attn + ffn + 6 * E) + 2 * E;
+    n += E * E + E;
+    return n;
+}
+
+void bind_weights(ffb_handle* h) {
+    const float* p = h->wblob.as<float>();
+    const size_t E = h->E, FF = h->FF, L = h->L, T = h->T, in = h->cfg.in_dim;
+    auto take = [&](size_t n) { const float* r = p; p += n; return r; };
+    Weights& w = h->w;
+    w.tok_table = take(h->cfg.num_token * E);
+    w.e0w = take(E * in); w.e0b = take(E); w.e2w = take(E * E); w.e2b = take(E);
+    w.pos = take(L * E); w.qpos = take(T * E);
+    auto attn = [&]() { AttnW a; a.in_w = take(3 * E * E); a.in_b = take(3 * E); a.out_w = take(E * E); a.out_b = take(E); return a; };
+    w.enc.resize(h->Le);
+    for (auto& l : w.enc) {
+        l.sa = attn();
+        l.l1w = take(FF * E); l.l1b = take(FF); l.l2w = take(E * FF); l.l2b = take(E);
+        l.n1w = take(E); l.n1b = take(E); l.n2w = take(E); l.n2b = take(E);
+    }
+    w.enc_nw = take(E); w.enc_nb = take(E);
+    w.dec.resize(h->Ld);
+    for (auto& l : w.dec) {
+        l.sa = attn(); l.ca = attn();
+        l.l1w = take(FF * E); l.l1b = take(FF); l.l2w = take(E * FF); l.l2b = take(E);
+        l.n1w = take(E); l.n1b = take(E); l.n2w = take(E); l.n2b = take(E); l.n3w = take(E); l.n3b = take(E);
+    }
+    w.dec_nw = take(E); w.dec_nb = take(E);
+    w.proj_w = take(E * E); w.proj_b = take(E);
+}
+
+inline int grid1d(long long total, int block = 256) {
+    long long g = (total + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, 148LL * 32));
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------
+struct Lin {
+    const float* A = nullptr; int lda = 0; const int* a_rows = nullptr;
+    const float* W = nullptr; int ldw = 0; const float* bias = nullptr;
+    float* C = nullptr; int ldc = 0; const int* c_rows = nullptr;
+    const float* R = nullptr; int ldr = 0;
+    const float* pos = nullptr; int ldpos = 0; const int* pos_idx = nullptr; int pos_mod = 0; int pos_cols = 0;
+    int M = 0, N = 0, K = 0, relu = 0;
+};
+
+int launch_linear(ffb_handle* h, const Lin& l, const int* stop, cudaStream_t s) {
+    if (l.M <= 0) return FFB_OK;
+    LinearArgs a;
+    a.A = l.A; a.lda = l.lda; a.a_rows = l.a_rows; a.W = l.W; a.ldw = l.ldw; a.bias = l.bias;
+    a.C = l.C; a.ldc = l.ldc; a.c_rows = l.c_rows; a.R = l.R; a.ldr = l.ldr;
+    a.pos = l.pos; a.ldpos = l.ldpos; a.pos_idx = l.pos_idx; a.pos_mod = l.pos_mod; a.pos_cols = l.pos_cols;
+    a.M = l.M; a.N = l.N; a.K = l.K; a.relu = l.relu; a.stop = stop;
+    if (l.pos && l.pos_cols < l.N && (l.pos_cols % LBN) != 0)
+        return fail(h, FFB_ERR_ARG, "linear: pos_cols (%d) must be a multiple of %d", l.pos_cols, LBN);
+    if (l.K % 4 != 0 || l.N % 4 != 0) return fail(h, FFB_ERR_ARG, "linear: K and N must be multiples of 4");
+    dim3 grid((l.M + LBM - 1) / LBM, (l.N + LBN - 1) / LBN);
+    prof_begin(h, PC_LINEAR, 2.0 * l.M * (double)l.N * l.K, s);
+    linear_kernel<<<grid, 256, 0, s>>>(a);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_ln(ffb_handle* h, const float* x, const float* g, const float* b, float* y, int M, int E, const int* stop, cudaStream_t s) {
+    if (M <= 0) return FFB_OK;
+    prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
+    layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, y, M, E, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
+                     int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s) {
+    if (G <= 0 || nq <= 0) return FFB_OK;
+    AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
+    dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
+    prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * (double)G * h->H * nq * nk, s);
+    attn_rows_kernel<<<grid, 128, 0, s>>>(Q, ldq, K, V, ldk, O, ldo, g, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
+                      const AttnGroups& g, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s) {
+    if (G <= 0 || max_q_rows <= 0) return FFB_OK;
+    if (G > 65535) return fail(h, FFB_ERR_ARG, "attention: more than 65535 groups");
+    dim3 grid((max_q_rows + AT_BQ - 1) / AT_BQ, h->H, G);
+    prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * qk_pairs, s);
+    attn_tiled_kernel<<<grid, 128, AT_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, g, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int set_device(ffb_handle* h) {
+    CU(h, cudaSetDevice(h->cfg.device));
+    return FFB_OK;
+}
+
+template <class T>
+int upload(ffb_handle* h, DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    CU(h, b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CU(h, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return FFB_OK;
+}
+
+// ---- encode ---------------------------------------------------------------------------------------
+int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int N, cudaStream_t s) {
+    const int nl = h->cfg.num_lines, nt = h->cfg.num_token;
+    h->N = N;
+    h->h_row_off.assign(N + 1, 0); h->h_vlen.assign(N, 0);
+    std::vector<int> nvalid(N), pos_idx, edge_src, edge_dst;
+    long long R = 0, Re = 0; int max_vlen = 0;
+    for (int i = 0; i < N; ++i) {
+        const uint8_t* m = mask + (size_t)i * nl;
+        int nv = 0;
+        while (nv < nl && m[nv] == 0) ++nv;
+        for (int j = nv; j < nl; ++j)
+            if (m[j] == 0)
+                return fail(h, FFB_ERR_UNSUPPORTED, "input_mask of wireframe %d is not of prefix form (valid edge at %d after padding at %d); "
+                            "only masks built like data_para.py:67-68 are supported", i, j, nv);
+        nvalid[i] = nv;
+        h->h_vlen[i] = nv + nt;
+        h->h_row_off[i] = (int)R;
+        max_vlen = std::max(max_vlen, nv + nt);
+        R += nv + nt; Re += nv;
+    }
+    if (R > 0x7fffffffLL / std::max(h->E * 3, h->Ld * h->E)) return fail(h, FFB_ERR_ARG, "batch too large (memory rows)");
+    h->h_row_off[N] = (int)R;
+    h->R = R; h->Re = Re; h->max_vlen = max_vlen;
+    pos_idx.resize(R); edge_src.resize(Re); edge_dst.resize(Re);
+    long long e = 0;
+    for (int i = 0; i < N; ++i) {
+        for (int j = 0; j < h->h_vlen[i]; ++j) pos_idx[h->h_row_off[i] + j] = j;
+        for (int j = 0; j < nvalid[i]; ++j, ++e) { edge_src[e] = i * nl + j; edge_dst[e] = h->h_row_off[i] + nt + j; }
+    }
+
+    std::vector<int> seq_wf, seq_first, slot_seq, seq_slot;
+    h->h_seq_off.assign(N + 1, 0);
+    int max_spw = 0;
+    if (h->cfg.mode == FFB_MODE_PARALLEL) {
+        if (!num_input) return fail(h, FFB_ERR_ARG, "num_input is required in parallel mode");
+        int64_t F = 0;
+        for (int i = 0; i < N; ++i) {
+            if (num_input[i] < 0) return fail(h, FFB_ERR_ARG, "num_input[%d] < 0", i);
+            if (num_input[i] > h->h_vlen[i])
+                return fail(h, FFB_ERR_UNSUPPORTED, "num_input[%d]=%lld exceeds the %d un-masked memory rows: anchors would gather padded rows",
+                            i, (long long)num_input[i], h->h_vlen[i]);
+            F = std::max<int64_t>(F, num_input[i]);
+        }
+        if (F < 1) return fail(h, FFB_ERR_ARG, "max(num_input) must be >= 1");
+        h->F = (int)F;
+        slot_seq.assign((size_t)N * F, 0);
+        for (int i = 0; i < N; ++i) {
+            const int ni = (int)num_input[i];
+            h->h_seq_off[i] = (int)seq_wf.size();
+            for (int a = 0; a < ni; ++a) {                         // anchors = arange(F): rows 0..n_i-1, NOT +4 (model_para.py:201)
+                slot_seq[(size_t)i * F + a] = (int)seq_wf.size();
+                seq_slot.push_back((int)((size_t)i * F + a));
+                seq_wf.push_back(i); seq_first.push_back(a);
+            }
+            if (ni < F) {                                           // padded anchors = token.len-1 (model_para.py:204-205)
+                if (h->opt_dedup) {
+                    int sid;
+                    if (ni >= nt) sid = h->h_seq_off[i] + (nt - 1);  // identical to the real sequence anchored at row 3
+                    else { sid = (int)seq_wf.size(); seq_slot.push_back((int)((size_t)i * F + ni)); seq_wf.push_back(i); seq_first.push_back(nt - 1); }
+                    for (int a = ni; a < F; ++a) slot_seq[(size_t)i * F + a] = sid;
+                } else {
+                    for (int a = ni; a < F; ++a) {
+                        slot_seq[(size_t)i * F + a] = (int)seq_wf.size();
+                        seq_slot.push_back((int)((size_t)i * F + a));
+                        seq_wf.push_back(i); seq_first.push_back(nt - 1);
+                    }
+                }
+            }
+            max_spw = std::max(max_spw, (int)seq_wf.size() - h->h_seq_off[i]);
+        }
+        h->B_full = (long long)N * F;
+    } else {
+        h->F = 1;
+        slot_seq.resize(N);
+        for (int i = 0; i < N; ++i) {
+            h->h_seq_off[i] = i; slot_seq[i] = i; seq_slot.push_back(i);
+            seq_wf.push_back(i); seq_first.push_back(1);           // token.SOS (model.py:190)
+        }
+        max_spw = 1;
+        h->B_full = N;
+    }
+    h->h_seq_off[N] = (int)seq_wf.size();
+    h->B = (long long)seq_wf.size();
+    h->sum_seq_vlen = 0; h->sum_vlen2 = 0;
+    for (int i = 0; i < N; ++i) {
+        h->sum_seq_vlen += (double)(h->h_seq_off[i + 1] - h->h_seq_off[i]) * h->h_vlen[i];
+        h->sum_vlen2 += (double)h->h_vlen[i] * h->h_vlen[i];
+    }
+    h->max_seq_per_wf = max_spw;
+    const long long Mmax = h->B * (long long)(h->T - 1);
+    if (Mmax * (long long)std::max(3 * h->E, h->FF) > 0x7fffffffffLL) return fail(h, FFB_ERR_ARG, "batch too large");
+    if (Mmax > 0x7fffffffLL / 4) return fail(h, FFB_ERR_ARG, "batch too large (decode rows)");
+
+    FFB_TRY(upload(h, h->d_row_off, h->h_row_off, s));
+    FFB_TRY(upload(h, h->d_vlen, h->h_vlen, s));
+    FFB_TRY(upload(h, h->d_pos_idx, pos_idx, s));
+    FFB_TRY(upload(h, h->d_edge_src, edge_src, s));
+    FFB_TRY(upload(h, h->d_edge_dst, edge_dst, s));
+    FFB_TRY(upload(h, h->d_seq_wf, seq_wf, s));
+    FFB_TRY(upload(h, h->d_seq_first, seq_first, s));
+    FFB_TRY(upload(h, h->d_seq_off, h->h_seq_off, s));
+    FFB_TRY(upload(h, h->d_slot_seq, slot_seq, s));
+    FFB_TRY(upload(h, h->d_seq_slot, seq_slot, s));
+    // the std::vectors above are pageable: make sure the copies are done before they go out of scope
+    CU(h, cudaStreamSynchronize(s));
+
+    // workspaces
+    const size_t E = h->E, FF = h->FF, f4 = sizeof(float);
+    const size_t rows = (size_t)std::max<long long>(std::max<long long>(R, Mmax), 1);
+    CU(h, h->mem.ensure((size_t)R * E * f4));
+    CU(h, h->Kc.ensure((size_t)R * h->Ld * E * f4));
+    CU(h, h->Vc.ensure((size_t)R * h->Ld * E * f4));
+    CU(h, h->tok.ensure((size_t)h->T * h->B * sizeof(int)));
+    CU(h, h->logits.ensure((size_t)h->B * h->L * f4));
+    CU(h, h->state.ensure(4 * sizeof(int)));
+    CU(h, h->x.ensure(rows * E * f4));
+    CU(h, h->x2.ensure(rows * E * f4));
+    CU(h, h->qkv.ensure(rows * 3 * E * f4));
+    CU(h, h->att.ensure(rows * E * f4));
+    CU(h, h->hb.ensure(std::max(rows, (size_t)Re) * std::max(FF, E) * f4));
+    CU(h, h->xl.ensure((size_t)std::max<long long>(h->B, 1) * E * f4));
+    return FFB_OK;
+}
+
+int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
+    const int E = h->E, FF = h->FF, R = (int)h->R, Re = (int)h->Re, N = h->N;
+    const Weights& w = h->w;
+    float* x = h->x.as<float>(); float* x2 = h->x2.as<float>(); float* qkv = h->qkv.as<float>();
+    float* att = h->att.as<float>(); float* hb = h->hb.as<float>(); float* mem = h->mem.as<float>();
+    const int* row_off = h->d_row_off.as<int>(); const int* vlen = h->d_vlen.as<int>();
+    const int* pos_idx = h->d_pos_idx.as<int>();
+
+    // value embedding (embedding.py:34): relu(coords W0^T + b0) W2^T + b2 on the valid edges only
+    { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
+      l.C = hb; l.ldc = E; l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    { Lin l; l.A = hb; l.lda = E; l.W = w.e2w; l.ldw = E; l.bias = w.e2b; l.C = x; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>();
+      l.M = Re; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    token_rows_kernel<<<grid1d((long long)N * h->cfg.num_token * (E / 4)), 256, 0, s>>>(w.tok_table, row_off, x, N, h->cfg.num_token, E);
+    h->launches++; CU(h, cudaGetLastError());
+
+    AttnGroups g{}; g.ragged = 1; g.q_begin = row_off; g.q_mul = 1; g.k_begin = row_off; g.k_len = vlen;
+    for (int li = 0; li < h->Le; ++li) {                                  // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
+        const EncLayerW& L = w.enc[li];
+        FFB_TRY(launch_ln(h, x, L.n1w, L.n1b, x2, R, E, nullptr, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = L.sa.in_w; l.ldw = E; l.bias = L.sa.in_b; l.C = qkv; l.ldc = 3 * E;
+          l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = 2 * E; l.M = R; l.N = 3 * E; l.K = E;
+          FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        FFB_TRY(launch_attn_tiled(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, g, N, h->max_vlen, h->sum_vlen2, nullptr, s));
+        { Lin l; l.A = att; l.lda = E; l.W = L.sa.out_w; l.ldw = E; l.bias = L.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+          l.M = R; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        FFB_TRY(launch_ln(h, x, L.n2w, L.n2b, x2, R, E, nullptr, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = L.l1w; l.ldw = E; l.bias = L.l1b; l.C = hb; l.ldc = FF; l.M = R; l.N = FF; l.K = E; l.relu = 1;
+          FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        { Lin l; l.A = hb; l.lda = FF; l.W = L.l2w; l.ldw = FF; l.bias = L.l2b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+          l.M = R; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    }
+    FFB_TRY(launch_ln(h, x, w.enc_nw, w.enc_nb, mem, R, E, nullptr, s));   // encoder.norm (transformer.py:80-81)
+
+    // cross-attention K/V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
+    // (transformer.py:248-251; torch functional.py:5866-5873)
+    const int LdE = h->Ld * E;
+    { Lin l; l.A = mem; l.lda = E; l.W = w.ckw; l.ldw = E; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE;
+      l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = LdE; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    { Lin l; l.A = mem; l.lda = E; l.W = w.cvw; l.ldw = E; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
+      l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    return FFB_OK;
+}
+
+// ---- one decode step --------------------------------------------------------------------------------
+// Runs the loop body for prefix length P on tok[0..P) and (if tok_out) appends tok[P].
+int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
+    const int E = h->E, FF = h->FF, B = (int)h->B, N = h->N, Ld = h->Ld;
+    const int M = B * P;
+    const Weights& w = h->w;
+    float* x = h->x.as<float>(); float* x2 = h->x2.as<float>(); float* qkv = h->qkv.as<float>();
+    float* att = h->att.as<float>(); float* hb = h->hb.as<float>(); float* xl = h->xl.as<float>();
+    int* st = h->state.as<int>();
+    const int* stop = st;            // state[0]
+    const int* row_off = h->d_row_off.as<int>(); const int* vlen = h->d_vlen.as<int>();
+    const int* seq_off = h->d_seq_off.as<int>();
+    const int LdE = Ld * E;
+
+    prof_begin(h, PC_OTHER, 0.0, s);
+    gather_tgt_kernel<<<grid1d((long long)M * (E / 4)), 256, 0, s>>>(h->mem.as<float>(), row_off, h->d_seq_wf.as<int>(),
+                                                                     h->tok.as<int>(), x, B, P, E, stop);
+    prof_end(h, s);
+    h->launches++; CU(h, cudaGetLastError());
+
+    float* cur = x; int rows = M; int Pq = P;            // rows carried through the rest of the layer
+    for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
+        const DecLayerW& Lw = w.dec[li];
+        const bool last = h->opt_prune && (li == Ld - 1);
+        // self-attention over the whole prefix, NO causal mask (model_para.py:222-223)
+        FFB_TRY(launch_ln(h, x, Lw.n1w, Lw.n1b, x2, M, E, stop, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = Lw.sa.in_w; l.ldw = E; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E;
+          l.pos = w.qpos; l.ldpos = E; l.pos_mod = P; l.pos_cols = 2 * E; l.M = M; l.N = 3 * E; l.K = E;
+          FFB_TRY(launch_linear(h, l, stop, s)); }
+        if (!last) {
+            FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s));
+            { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+              l.M = M; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+        } else {
+            // only pointer[-1] is consumed (model_para.py:176): carry just the last position from here on
+            FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s));
+            copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
+            h->launches++; CU(h, cudaGetLastError());
+            { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
+              l.M = B; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+            cur = xl; rows = B; Pq = 1;
+        }
+        // cross-attention over the cached K/V of the owning wireframe
+        FFB_TRY(launch_ln(h, cur, Lw.n2w, Lw.n2b, x2, rows, E, stop, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = Lw.ca.in_w; l.ldw = E; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E;
+          l.pos = last ? w.qpos + (size_t)(P - 1) * E : w.qpos; l.ldpos = E;
+          l.pos_mod = last ? 1 : P; l.pos_cols = E; l.M = rows; l.N = E; l.K = E;
+          FFB_TRY(launch_linear(h, l, stop, s)); }
+        { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
+          FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
+                                    att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s)); }
+        { Lin l; l.A = att; l.lda = E; l.W = Lw.ca.out_w; l.ldw = E; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+          l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+        // feed-forward
+        FFB_TRY(launch_ln(h, cur, Lw.n3w, Lw.n3b, x2, rows, E, stop, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = Lw.l1w; l.ldw = E; l.bias = Lw.l1b; l.C = hb; l.ldc = FF; l.M = rows; l.N = FF; l.K = E; l.relu = 1;
+          FFB_TRY(launch_linear(h, l, stop, s)); }
+        { Lin l; l.A = hb; l.lda = FF; l.W = Lw.l2w; l.ldw = FF; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+          l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, stop, s)); }
+    }
+    // decoder.norm (transformer.py:115-116) + project (model_para.py:225) + select_next (model_para.py:173-179)
+    FFB_TRY(launch_ln(h, cur, w.dec_nw, w.dec_nb, x2, rows, E, stop, s));
+    { Lin l; l.A = x2; l.lda = E; l.W = w.proj_w; l.ldw = E; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+      FFB_TRY(launch_linear(h, l, stop, s)); }
+    PointerArgs pa{};
+    pa.mem = h->mem.as<float>(); pa.ptr = att; pa.ptr_stride_rows = Pq; pa.ptr_off = Pq - 1;
+    pa.row_off = row_off; pa.v_len = vlen; pa.seq_wf = h->d_seq_wf.as<int>();
+    pa.logits = h->logits.as<float>(); pa.L = h->L;
+    pa.tok_out = append ? h->tok.as<int>() + (size_t)P * B : nullptr;
+    pa.B = B; pa.E = E; pa.num_token = h->cfg.num_token;
+    pa.nonstop_count = (h->cfg.mode == FFB_MODE_PARALLEL) ? st + 2 : nullptr;
+    pa.eos_count = (h->cfg.mode == FFB_MODE_SEQ2SEQ) ? st + 3 : nullptr;
+    pa.stop = stop;
+    prof_begin(h, PC_POINTER, 2.0 * E * h->sum_seq_vlen, s);
+    pointer_kernel<<<B, 256, 0, s>>>(pa);
+    prof_end(h, s);
+    h->launches++; CU(h, cudaGetLastError());
+    if (append) {
+        step_end_kernel<<<1, 1, 0, s>>>(h->cfg.mode, B, st + 2, st + 3, st, st + 1);
+        h->launches++; CU(h, cudaGetLastError());
+    }
+    h->last_P = P;
+    return FFB_OK;
+}
+
+int copy_out(ffb_handle* h, const void* dev_src, void* dst, size_t bytes, int loc, cudaStream_t s) {
+    CU(h, cudaMemcpyAsync(dst, dev_src, bytes, loc == FFB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    if (loc == FFB_HOST) CU(h, cudaStreamSynchronize(s));
+    return FFB_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+size_t ffb_weight_count(const ffb_config* cfg) { return validate_config(cfg) ? 0 : weight_count(cfg); }
+
+const char* ffb_last_error(const ffb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ffb_create(const ffb_config* cfg, ffb_handle** out) {
+    if (!out) return fail(nullptr, FFB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (const char* why = validate_config(cfg)) return fail(nullptr, FFB_ERR_ARG, "invalid config: %s", why);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, FFB_ERR_CUDA, "no CUDA device available (%s): libffb200 has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device >= ndev) return fail(nullptr, FFB_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, FFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libffb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    e = cudaFuncSetAttribute(attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
+    ffb_handle* h = new (std::nothrow) ffb_handle();
+    if (!h) return fail(nullptr, FFB_ERR_ARG, "out of host memory");
+    h->cfg = *cfg;
+    h->E = cfg->num_model; h->H = cfg->num_head; h->FF = cfg->num_feedforward;
+    h->L = cfg->num_lines + cfg->num_token; h->T = cfg->seq_len;
+    h->Le = cfg->num_encoder_layers; h->Ld = cfg->num_decoder_layers;
+    h->opt_prune = (cfg->mode == FFB_MODE_PARALLEL) ? 1 : 0;
+    for (auto& ev : h->ev) cudaEventCreate(&ev);
+    *out = h;
+    return FFB_OK;
+}
+
+int ffb_destroy(ffb_handle* h) {
+    if (!h) return FFB_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
+                      &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
+                      &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
+                      &h->att, &h->hb, &h->xl};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
+    delete h;
+    return FFB_OK;
+}
+
+int ffb_set_option(ffb_handle* h, int option, int value) {
+    if (!h) return FFB_ERR_ARG;
+    switch (option) {
+        case FFB_OPT_DEDUP_PAD: h->opt_dedup = value ? 1 : 0; h->encoded = false; return FFB_OK;
+        case FFB_OPT_PRUNE_LAST: h->opt_prune = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_TIMING: h->opt_timing = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; h->prof_recs.clear(); return FFB_OK;
+        default: return fail(h, FFB_ERR_ARG, "unknown option %d", option);
+    }
+}
+
+int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!blob) return fail(h, FFB_ERR_ARG, "blob is NULL");
+    const size_t want = weight_count(&h->cfg);
+    if (count != want) return fail(h, FFB_ERR_ARG, "weight blob has %zu floats, config needs %zu (strict state_dict layout)", count, want);
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, h->wblob.ensure(want * sizeof(float)));
+    CU(h, cudaMemcpyAsync(h->wblob.p, blob, want * sizeof(float), loc == FFB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    bind_weights(h);
+    // pack cross-attention K / V projection weights of all decoder layers: [Ld*E, E] (+ biases [Ld*E])
+    const size_t E = h->E, Ld = h->Ld;
+    CU(h, h->wcross.ensure((2 * Ld * E * E + 2 * Ld * E) * sizeof(float)));
+    float* ckw = h->wcross.as<float>(); float* cvw = ckw + Ld * E * E; float* ckb = cvw + Ld * E * E; float* cvb = ckb + Ld * E;
+    for (size_t l = 0; l < Ld; ++l) {
+        const AttnW& ca = h->w.dec[l].ca;       // in_proj rows: [0,E) q, [E,2E) k, [2E,3E) v (torch functional.py:5866-5873)
+        CU(h, cudaMemcpyAsync(ckw + l * E * E, ca.in_w + E * E, E * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        CU(h, cudaMemcpyAsync(cvw + l * E * E, ca.in_w + 2 * E * E, E * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        CU(h, cudaMemcpyAsync(ckb + l * E, ca.in_b + E, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        CU(h, cudaMemcpyAsync(cvb + l * E, ca.in_b + 2 * E, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    h->w.ckw = ckw; h->w.cvw = cvw; h->w.ckb = ckb; h->w.cvb = cvb;
+    CU(h, cudaStreamSynchronize(s));
+    h->weights_loaded = true;
+    return FFB_OK;
+}
+
+int ffb_encode(ffb_handle* h, const float* coords, const uint8_t* pad_mask, const int64_t* num_input,
+               int32_t N, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    h->encoded = false; h->decoded = false;
+    if (!h->weights_loaded) return fail(h, FFB_ERR_STATE, "ffb_encode before ffb_load_weights");
+    if (!coords || !pad_mask) return fail(h, FFB_ERR_ARG, "coords / pad_mask is NULL");
+    if (N < 1) return fail(h, FFB_ERR_ARG, "n_wireframes must be >= 1");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nl = h->cfg.num_lines;
+    const uint8_t* mask_h = pad_mask; const int64_t* ni_h = num_input;
+    if (loc == FFB_DEVICE) {       // small control data is planned on the host (the reference syncs here too, model_para.py:187)
+        h->h_mask.resize((size_t)N * nl);
+        CU(h, cudaMemcpyAsync(h->h_mask.data(), pad_mask, (size_t)N * nl, cudaMemcpyDeviceToHost, s));
+        if (num_input) {
+            h->h_num_input.resize(N);
+            CU(h, cudaMemcpyAsync(h->h_num_input.data(), num_input, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            ni_h = h->h_num_input.data();
+        }
+        CU(h, cudaStreamSynchronize(s));
+        mask_h = h->h_mask.data();
+    }
+    if (h->opt_timing) CU(h, cudaEventRecord(h->ev[0], s));
+    FFB_TRY(plan_batch(h, mask_h, ni_h, N, s));
+    const float* coords_dev = coords;
+    if (loc == FFB_HOST) {
+        const size_t bytes = (size_t)N * nl * h->cfg.in_dim * sizeof(float);
+        CU(h, h->d_coords.ensure(bytes));
+        CU(h, cudaMemcpyAsync(h->d_coords.p, coords, bytes, cudaMemcpyHostToDevice, s));
+        coords_dev = h->d_coords.as<float>();
+    }
+    FFB_TRY(run_encoder(h, coords_dev, s));
+    if (h->opt_timing) CU(h, cudaEventRecord(h->ev[1], s));
+    h->encoded = true;
+    return FFB_OK;
+}
+
+int ffb_batch_info(const ffb_handle* h, int32_t* N, int32_t* F, int64_t* B, int64_t* B_eff, int64_t* R) {
+    if (!h || !h->encoded) return FFB_ERR_STATE;
+    if (N) *N = h->N;
+    if (F) *F = h->F;
+    if (B) *B = h->B_full;
+    if (B_eff) *B_eff = h->B;
+    if (R) *R = h->R;
+    return FFB_OK;
+}
+
+int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_run, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_decode_greedy before ffb_encode");
+    if (!predict) return fail(h, FFB_ERR_ARG, "predict is NULL");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)h->B, T = h->T;
+    int* st = h->state.as<int>();
+    if (h->opt_timing && !h->ev[1]) return fail(h, FFB_ERR_STATE, "timing events missing");
+    init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
+    h->launches++; CU(h, cudaGetLastError());
+    CU(h, cudaMemsetAsync(st + 2, 0, sizeof(int), s));
+    for (int step = 0; step < T - 1; ++step) FFB_TRY(run_step(h, step + 1, true, s));   // no host sync inside the loop
+    const long long n_slots = h->B_full;
+    long long* out_dev = reinterpret_cast<long long*>(predict);
+    if (loc == FFB_HOST) {
+        CU(h, h->d_predict.ensure((size_t)n_slots * T * sizeof(long long)));
+        out_dev = h->d_predict.as<long long>();
+    }
+    expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
+    h->launches++; CU(h, cudaGetLastError());
+    if (h->opt_timing) CU(h, cudaEventRecord(h->ev[2], s));
+    if (loc == FFB_HOST)
+        CU(h, cudaMemcpyAsync(predict, out_dev, (size_t)n_slots * T * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    if (steps_run) {
+        CU(h, cudaMemcpyAsync(steps_run, st + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+    } else if (loc == FFB_HOST) {
+        CU(h, cudaStreamSynchronize(s));
+    }
+    h->decoded = true;
+    return FFB_OK;
+}
+
+int ffb_forward_eval(ffb_handle* h, const float* coords, const uint8_t* pad_mask, const int64_t* num_input, int32_t N,
+                     int64_t* predict, int loc, int32_t* steps_run, void* stream) {
+    FFB_TRY(ffb_encode(h, coords, pad_mask, num_input, N, loc, stream));
+    return ffb_decode_greedy(h, predict, loc, steps_run, stream);
+}
+
+int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_get_memory before ffb_encode");
+    if (!memory) return fail(h, FFB_ERR_ARG, "memory is NULL");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)h->N * h->L * h->E * sizeof(float);
+    float* dst = memory;
+    if (loc == FFB_HOST) { CU(h, h->d_out_stage.ensure(bytes)); dst = h->d_out_stage.as<float>(); }
+    unpack_memory_kernel<<<grid1d((long long)h->N * h->L * (h->E / 4)), 256, 0, s>>>(h->mem.as<float>(), h->d_row_off.as<int>(),
+                                                                                  h->d_vlen.as<int>(), dst, h->N, h->L, h->E);
+    h->launches++; CU(h, cudaGetLastError());
+    if (loc == FFB_HOST) FFB_TRY(copy_out(h, dst, memory, bytes, loc, s));
+    return FFB_OK;
+}
+
+static int emit_logits(ffb_handle* h, float* logits, int loc, cudaStream_t s) {
+    const size_t bytes = (size_t)h->B_full * h->L * sizeof(float);
+    float* dst = logits;
+    if (loc == FFB_HOST) { CU(h, h->d_out_stage.ensure(bytes)); dst = h->d_out_stage.as<float>(); }
+    expand_rows_kernel<<<grid1d(h->B_full * h->L), 256, 0, s>>>(h->logits.as<float>(), h->d_slot_seq.as<int>(), dst, h->B_full, h->L);
+    h->launches++; CU(h, cudaGetLastError());
+    if (loc == FFB_HOST) FFB_TRY(copy_out(h, dst, logits, bytes, loc, s));
+    return FFB_OK;
+}
+
+int ffb_get_last_logits(ffb_handle* h, float* logits, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->decoded) return fail(h, FFB_ERR_STATE, "ffb_get_last_logits before a decode");
+    if (!logits) return fail(h, FFB_ERR_ARG, "logits is NULL");
+    FFB_TRY(set_device(h));
+    return emit_logits(h, logits, loc, (cudaStream_t)stream);
+}
+
+int ffb_get_last_pointer(ffb_handle* h, float* pointer, int32_t* P_out, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->decoded) return fail(h, FFB_ERR_STATE, "ffb_get_last_pointer before a decode");
+    if (h->opt_prune) return fail(h, FFB_ERR_STATE, "ffb_get_last_pointer needs FFB_OPT_PRUNE_LAST = 0");
+    if (!pointer) return fail(h, FFB_ERR_ARG, "pointer is NULL");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    int steps = 0;
+    CU(h, cudaMemcpyAsync(&steps, h->state.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (steps < 1) return fail(h, FFB_ERR_STATE, "no decode step was executed");
+    if (P_out) *P_out = steps;
+    // rows are (sequence, position): exactly [N, P, E] for the last executed step (later steps exited early)
+    return copy_out(h, h->att.p, pointer, (size_t)h->B * steps * h->E * sizeof(float), loc, s);
+}
+
+int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, float* logits, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_forced_prefix_logits before ffb_encode");
+    if (!prefix || !logits) return fail(h, FFB_ERR_ARG, "prefix / logits is NULL");
+    if (P < 1 || P > h->T - 1) return fail(h, FFB_ERR_ARG, "P must be in [1, T-1]");
+    if (h->B != h->B_full) return fail(h, FFB_ERR_STATE, "forced prefixes need FFB_OPT_DEDUP_PAD = 0 before ffb_encode");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t pbytes = (size_t)P * h->B_full * sizeof(int64_t);
+    const long long* pdev = reinterpret_cast<const long long*>(prefix);
+    if (loc == FFB_HOST) {
+        CU(h, h->d_prefix.ensure(pbytes));
+        CU(h, cudaMemcpyAsync(h->d_prefix.p, prefix, pbytes, cudaMemcpyHostToDevice, s));
+        pdev = h->d_prefix.as<long long>();
+    }
+    // validate on the host that every token addresses an un-masked memory row of its wireframe
+    {
+        std::vector<int64_t> hp((size_t)P * h->B_full);
+        CU(h, cudaMemcpyAsync(hp.data(), pdev, pbytes, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        for (int p = 0; p < P; ++p)
+            for (long long b = 0; b < h->B_full; ++b) {
+                const int wf = (int)(b / h->F);
+                const int64_t t = hp[(size_t)p * h->B_full + b];
+                if (t < 0 || t >= h->h_vlen[wf]) return fail(h, FFB_ERR_ARG, "prefix[%d,%lld]=%lld is not an un-masked row", p, b, (long long)t);
+            }
+    }
+    int* st = h->state.as<int>();
+    CU(h, cudaMemsetAsync(st, 0, 4 * sizeof(int), s));
+    load_prefix_kernel<<<grid1d((long long)P * h->B), 256, 0, s>>>(pdev, h->d_seq_slot.as<int>(), h->tok.as<int>(), P, (int)h->B_full, (int)h->B);
+    h->launches++; CU(h, cudaGetLastError());
+    FFB_TRY(run_step(h, P, false, s));
+    h->decoded = false;
+    return emit_logits(h, logits, loc, s);
+}
+
+int64_t ffb_kernel_launches(const ffb_handle* h) { return h ? h->launches : 0; }
+
+int ffb_phase_times(ffb_handle* h, float* out_ms, int32_t n) {
+    if (!h || !out_ms || n < 2) return FFB_ERR_ARG;
+    if (!h->opt_timing || !h->decoded) return fail(h, FFB_ERR_STATE, "timing not enabled or no forward recorded");
+    CU(h, cudaEventSynchronize(h->ev[2]));
+    CU(h, cudaEventElapsedTime(&out_ms[0], h->ev[0], h->ev[1]));
+    CU(h, cudaEventElapsedTime(&out_ms[1], h->ev[1], h->ev[2]));
+    return FFB_OK;
+}
+
+int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops, int64_t* launches) {
+    if (!h || !ms || !flops || !launches || n_classes < PC_COUNT) return FFB_ERR_ARG;
+    FFB_TRY(set_device(h));
+    CU(h, cudaDeviceSynchronize());
+    for (int c = 0; c < n_classes; ++c) { ms[c] = 0.f; flops[c] = 0.0; launches[c] = 0; }
+    for (size_t i = 0; i < h->prof_recs.size(); ++i) {
+        float t = 0.f;
+        CU(h, cudaEventElapsedTime(&t, h->prof_pool[2 * i], h->prof_pool[2 * i + 1]));
+        const int c = h->prof_recs[i].cls;
+        ms[c] += t; flops[c] += h->prof_recs[i].flops; launches[c] += 1;
+    }
+    h->prof_recs.clear();
+    return FFB_OK;
+}
+
+// ---- op-level hooks ---------------------------------------------------------------------------------
+int ffb_op_linear(ffb_handle* h, const float* A, const float* W, const float* bias, const float* R, const float* pos,
+                  int32_t pos_mod, int32_t pos_cols, float* C, int32_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    FFB_TRY(set_device(h));
+    Lin l; l.A = A; l.lda = K; l.W = W; l.ldw = K; l.bias = bias; l.C = C; l.ldc = N; l.R = R; l.ldr = N;
+    l.pos = pos; l.ldpos = K; l.pos_mod = pos_mod; l.pos_cols = pos_cols; l.M = M; l.N = N; l.K = K; l.relu = relu;
+    if (pos && pos_mod < 1) return fail(h, FFB_ERR_ARG, "op_linear: pos needs pos_mod >= 1");
+    return launch_linear(h, l, nullptr, (cudaStream_t)stream);
+}
+
+int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const float* beta, float* y, int32_t M, int32_t E, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (E % 128 != 0 || E > 1024) return fail(h, FFB_ERR_ARG, "op_layernorm: E must be a multiple of 128, <= 1024");
+    FFB_TRY(set_device(h));
+    return launch_ln(h, x, gamma, beta, y, M, E, nullptr, (cudaStream_t)stream);
+}
+
+int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k, const float* v, int32_t ldk,
+                     float* out, int32_t G, int32_t nq, int32_t nk, int32_t H, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (H != h->H) return fail(h, FFB_ERR_ARG, "op_attention: H must equal the handle's num_head");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kind == 0) return launch_attn_rows(h, q, ldq, k, v, ldk, out, H * 64, G, nq, nk, nq, 0, nk, nq, nullptr, s);
+    AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
+    return launch_attn_tiled(h, q, ldq, k, v, ldk, out, H * 64, g, G, nq, (double)G * nq * nk, nullptr, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,661 @@
+// kernels.cuh -- hand-written sm_100a kernels of the FaceFormer greedy pointer-decode path.
+//
+// fp32 end to end: the parity contract (token-exact vs the reference's CPU fp32 path, pointer
+// logits within 1e-4) leaves ~2x headroom over fp32 summation-order noise,
+// so every contraction here accumulates in fp32 with fp32 operands.
+//
+// Reference operations each kernel replaces (paths relative to /root/reference):
+//   linear_kernel      nn.Linear call sites: transformer.py:134,136,195,197, model_para.py:46,
+//                      embedding.py:15,17 and the in/out projections of nn.MultiheadAttention
+//                      (torch functional.py:5866-5873,6653); fuses with_pos_embed (transformer.py:
+//                      144-145,205-206), bias, ReLU and the residual add (transformer.py:172,176,246,..).
+//   layernorm_kernel   nn.LayerNorm (transformer.py:138-139,199-201, model_para.py:37,43)
+//   attn_rows_kernel   decoder self-attention core (transformer.py:244-245; NO tgt_mask in eval)
+//   attn_tiled_kernel  encoder self-attention / decoder cross-attention core with key-padding mask
+//                      realised as "only valid rows exist" (transformer.py:169-171,247-251)
+//   gather_tgt_kernel  torch.gather(memory, 0, predicts...) (model_para.py:217-219)
+//   pointer_kernel     select_next: bmm + masked_fill + argmax (model_para.py:173-179) + append +
+//                      stop predicate (model_para.py:229-233 / model.py:205-210)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+
+namespace ffb {
+
+#define FFB_STOP_CHECK(stop) do { if ((stop) != nullptr && *(stop) != 0) return; } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear: C[M,N] = act( (A[+pos]) W^T + bias ) (+ R)
+// ------------------------------------------------------------------------------------------------
+struct LinearArgs {
+    const float* A; int lda;          // [M,K] row-major (row stride lda)
+    const int* a_rows;                // optional gather: row r of the GEMM reads A[a_rows[r]]
+    const float* W; int ldw;          // [N,K] row-major == torch Linear.weight
+    const float* bias;                // [N] or null
+    float* C; int ldc;                // [M,N]
+    const int* c_rows;                // optional scatter: row r is written to C[c_rows[r]]
+    const float* R; int ldr;          // residual rows (same row mapping as C) or null; may alias C
+    const float* pos; int ldpos;      // positional table; added to A for column tiles n0 < pos_cols
+    const int* pos_idx; int pos_mod;  // table row of GEMM row r: pos_mod > 0 ? r % pos_mod : pos_idx[r]
+    int pos_cols;                     // multiple of 128 (or >= N)
+    int M, N, K;                      // K multiple of 4
+    int relu;
+    const int* stop;
+};
+
+constexpr int LBM = 128, LBN = 128, LBK = 16, LPAD = 4;
+
+__global__ void __launch_bounds__(256, 2) linear_kernel(const LinearArgs a) {
+    FFB_STOP_CHECK(a.stop);
+    __shared__ __align__(16) float As[2][LBK][LBM + LPAD];
+    __shared__ __align__(16) float Bs[2][LBK][LBN + LPAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    const bool add_pos = (a.pos != nullptr) && (n0 < a.pos_cols);
+
+    // global->smem staging: float4 index f = tid + i*256 -> tile row f>>2, k-quad f&3
+    const float* ap[2]; const float* pp[2]; const float* wp[2];
+    int srow[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int f = tid + i * 256;
+        const int row = f >> 2, kq = f & 3;
+        srow[i] = row;
+        const int gr = m0 + row;
+        ap[i] = nullptr; pp[i] = nullptr; wp[i] = nullptr;
+        if (gr < a.M) {
+            const int src = a.a_rows ? a.a_rows[gr] : gr;
+            ap[i] = a.A + (size_t)src * a.lda + kq * 4;
+            if (add_pos) {
+                const int pi = a.pos_mod > 0 ? (gr % a.pos_mod) : a.pos_idx[gr];
+                pp[i] = a.pos + (size_t)pi * a.ldpos + kq * 4;
+            }
+        }
+        const int gn = n0 + row;
+        if (gn < a.N) wp[i] = a.W + (size_t)gn * a.ldw + kq * 4;
+    }
+    const int kq4 = (tid & 3) * 4;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const bool kv = (k0 + kq4 + 4 <= a.K);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ap[i] != nullptr && kv) {
+                v = *reinterpret_cast<const float4*>(ap[i] + k0);
+                if (pp[i] != nullptr) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(pp[i] + k0));
+                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+            }
+            ra[i] = v;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wp[i] != nullptr && kv) w = __ldg(reinterpret_cast<const float4*>(wp[i] + k0));
+            rb[i] = w;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            As[buf][kq4 + 0][srow[i]] = ra[i].x; As[buf][kq4 + 1][srow[i]] = ra[i].y;
+            As[buf][kq4 + 2][srow[i]] = ra[i].z; As[buf][kq4 + 3][srow[i]] = ra[i].w;
+            Bs[buf][kq4 + 0][srow[i]] = rb[i].x; Bs[buf][kq4 + 1][srow[i]] = rb[i].y;
+            Bs[buf][kq4 + 2][srow[i]] = rb[i].z; Bs[buf][kq4 + 3][srow[i]] = rb[i].w;
+        }
+    };
+
+    const int nk = (a.K + LBK - 1) / LBK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * LBK);
+#pragma unroll
+        for (int kk = 0; kk < LBK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int lr = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+        const int gr = m0 + lr;
+        if (gr >= a.M) continue;
+        const int orow = a.c_rows ? a.c_rows[gr] : gr;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int gn = n0 + half * 64 + tx * 4;
+            if (gn >= a.N) continue;           // N is a multiple of 4
+            float4 v = make_float4(acc[i][half * 4 + 0], acc[i][half * 4 + 1],
+                                   acc[i][half * 4 + 2], acc[i][half * 4 + 3]);
+            if (a.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + gn));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (a.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (a.R) {
+                const float4 r = *reinterpret_cast<const float4*>(a.R + (size_t)orow * a.ldr + gn);
+                v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+            }
+            *reinterpret_cast<float4*>(a.C + (size_t)orow * a.ldc + gn) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layernorm: y[r] = (x[r] - mean) * rstd * gamma + beta, one warp per row, E multiple of 128, E <= 1024
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ y,
+                                                        int M, int E, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + (size_t)row * E;
+    float4 v[8];
+    const int nv = E >> 7;                    // float4 per lane
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+    const float var = warp_sum(q) / (float)E;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    float* yr = y + (size_t)row * E;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            const int c = i * 128 + lane * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = v[i].x * rstd * g.x + b.x; o.y = v[i].y * rstd * g.y + b.y;
+            o.z = v[i].z * rstd * g.z + b.z; o.w = v[i].w * rstd * g.w + b.w;
+            *reinterpret_cast<float4*>(yr + c) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention group geometry
+// ------------------------------------------------------------------------------------------------
+struct AttnGroups {
+    int ragged;                 // 0: uniform groups, 1: per-group arrays
+    // uniform: group g has queries [g*q_stride + q_off, +nq), keys [g*k_stride, +nk), outputs [g*o_stride, +nq)
+    int nq, nk, q_stride, q_off, k_stride, o_stride;
+    // ragged: queries (== output rows) [q_begin[g]*q_mul, q_begin[g+1]*q_mul); keys [k_begin[g], +k_len[g])
+    const int* q_begin; int q_mul; const int* k_begin; const int* k_len;
+};
+
+__device__ __forceinline__ void attn_group(const AttnGroups& g, int grp, long long& q0, int& nq,
+                                           long long& k0, int& nk, long long& o0) {
+    if (g.ragged) {
+        q0 = (long long)g.q_begin[grp] * g.q_mul;
+        nq = (int)((long long)g.q_begin[grp + 1] * g.q_mul - q0);
+        k0 = g.k_begin[grp]; nk = g.k_len[grp]; o0 = q0;
+    } else {
+        q0 = (long long)grp * g.q_stride + g.q_off; nq = g.nq;
+        k0 = (long long)grp * g.k_stride; nk = g.nk; o0 = (long long)grp * g.o_stride;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attn_rows: warp-per-query-row attention for short key sets (decoder self-attention, P <= T).
+// grid (group, head, q-tile of 64 rows); 4 warps; warp w owns rows w, w+4, ..., state in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int AR_BQ = 64, AR_BK = 32, AR_RPW = 16, AR_KS = 68;
+
+__global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict__ Q, int ldq,
+                                                        const float* __restrict__ K, const float* __restrict__ V, int ldk,
+                                                        float* __restrict__ O, int ldo, const AttnGroups g, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    __shared__ __align__(16) float Qs[AR_BQ][64];
+    __shared__ __align__(16) float Ks[AR_BK][AR_KS];
+    __shared__ __align__(16) float Vs[AR_BK][64];
+    __shared__ __align__(16) float Ps[4][AR_BK];
+
+    long long q0, k0, o0; int nq, nk;
+    attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
+    const int head = blockIdx.y;
+    const int qt0 = blockIdx.z * AR_BQ;
+    if (qt0 >= nq) return;
+    const int nqt = min(AR_BQ, nq - qt0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // stage Q tile (rows beyond nqt are zero)
+    for (int idx = tid; idx < AR_BQ * 16; idx += 128) {
+        const int r = idx >> 4, d4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nqt) v = *reinterpret_cast<const float4*>(Q + (size_t)(q0 + qt0 + r) * ldq + head * 64 + d4 * 4);
+        *reinterpret_cast<float4*>(&Qs[r][d4 * 4]) = v;
+    }
+
+    float m[AR_RPW], l[AR_RPW], oa[AR_RPW], ob[AR_RPW];
+#pragma unroll
+    for (int i = 0; i < AR_RPW; ++i) { m[i] = -INFINITY; l[i] = 0.f; oa[i] = 0.f; ob[i] = 0.f; }
+
+    for (int kt = 0; kt < nk; kt += AR_BK) {
+        __syncthreads();
+        for (int idx = tid; idx < AR_BK * 16; idx += 128) {
+            const int r = idx >> 4, d4 = idx & 15;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (kt + r < nk) {
+                const size_t off = (size_t)(k0 + kt + r) * ldk + head * 64 + d4 * 4;
+                kv = *reinterpret_cast<const float4*>(K + off);
+                vv = *reinterpret_cast<const float4*>(V + off);
+            }
+            *reinterpret_cast<float4*>(&Ks[r][d4 * 4]) = kv;
+            *reinterpret_cast<float4*>(&Vs[r][d4 * 4]) = vv;
+        }
+        __syncthreads();
+        const bool kvalid = (kt + lane) < nk;
+#pragma unroll
+        for (int i = 0; i < AR_RPW; ++i) {
+            const int r = w + 4 * i;
+            if (r < nqt) {                                   // warp-uniform
+                float s = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < 16; ++d4) {
+                    const float4 qv = *reinterpret_cast<const float4*>(&Qs[r][d4 * 4]);
+                    const float4 kv = *reinterpret_cast<const float4*>(&Ks[lane][d4 * 4]);
+                    s = fmaf(qv.x, kv.x, s); s = fmaf(qv.y, kv.y, s);
+                    s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
+                }
+                s = kvalid ? s * 0.125f : -INFINITY;          // q * sqrt(1/64): exact power of two
+                const float mn = fmaxf(m[i], warp_max(s));
+                const float p = expf(s - mn);                 // masked lanes: exp(-inf) = 0
+                const float corr = expf(m[i] - mn);           // first tile: exp(-inf) = 0
+                l[i] = l[i] * corr + warp_sum(p);
+                m[i] = mn;
+                __syncwarp();
+                Ps[w][lane] = p;
+                __syncwarp();
+                float a0 = oa[i] * corr, a1 = ob[i] * corr;
+#pragma unroll
+                for (int j4 = 0; j4 < AR_BK / 4; ++j4) {
+                    const float4 pv = *reinterpret_cast<const float4*>(&Ps[w][j4 * 4]);
+                    a0 = fmaf(pv.x, Vs[j4 * 4 + 0][lane], a0); a1 = fmaf(pv.x, Vs[j4 * 4 + 0][lane + 32], a1);
+                    a0 = fmaf(pv.y, Vs[j4 * 4 + 1][lane], a0); a1 = fmaf(pv.y, Vs[j4 * 4 + 1][lane + 32], a1);
+                    a0 = fmaf(pv.z, Vs[j4 * 4 + 2][lane], a0); a1 = fmaf(pv.z, Vs[j4 * 4 + 2][lane + 32], a1);
+                    a0 = fmaf(pv.w, Vs[j4 * 4 + 3][lane], a0); a1 = fmaf(pv.w, Vs[j4 * 4 + 3][lane + 32], a1);
+                }
+                oa[i] = a0; ob[i] = a1;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < AR_RPW; ++i) {
+        const int r = w + 4 * i;
+        if (r < nqt) {
+            float* orow = O + (size_t)(o0 + qt0 + r) * ldo + head * 64;
+            orow[lane] = oa[i] / l[i];
+            orow[lane + 32] = ob[i] / l[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attn_tiled: register-tiled flash attention (fp32), 64 queries x 64 keys per iteration, head dim 64.
+// grid (q-tile, head, group); 128 threads; thread (ty = tid/8, tx = tid%8) owns rows ty+16i, keys tx+8j.
+// ------------------------------------------------------------------------------------------------
+constexpr int AT_BQ = 64, AT_BK = 64, AT_S = 68;
+constexpr int AT_SMEM_BYTES = (3 * AT_BQ * AT_S + AT_BK * 64) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict__ Q, int ldq,
+                                                         const float* __restrict__ K, const float* __restrict__ V, int ldk,
+                                                         float* __restrict__ O, int ldo, const AttnGroups g, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    extern __shared__ __align__(16) float smem[];
+    float (*Qs)[AT_S] = reinterpret_cast<float (*)[AT_S]>(smem);
+    float (*Ks)[AT_S] = reinterpret_cast<float (*)[AT_S]>(smem + AT_BQ * AT_S);
+    float (*Ps)[AT_S] = reinterpret_cast<float (*)[AT_S]>(smem + 2 * AT_BQ * AT_S);
+    float (*Vs)[64] = reinterpret_cast<float (*)[64]>(smem + 3 * AT_BQ * AT_S);
+
+    long long q0, k0, o0; int nq, nk;
+    attn_group(g, blockIdx.z, q0, nq, k0, nk, o0);
+    const int head = blockIdx.y;
+    const int qt0 = blockIdx.x * AT_BQ;
+    if (qt0 >= nq) return;
+    const int nqt = min(AT_BQ, nq - qt0);
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+
+    for (int idx = tid; idx < AT_BQ * 16; idx += 128) {
+        const int r = idx >> 4, d4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nqt) v = *reinterpret_cast<const float4*>(Q + (size_t)(q0 + qt0 + r) * ldq + head * 64 + d4 * 4);
+        *reinterpret_cast<float4*>(&Qs[r][d4 * 4]) = v;
+    }
+
+    float m[4], l[4], o[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    }
+
+    for (int kt = 0; kt < nk; kt += AT_BK) {
+        __syncthreads();                                     // previous tile fully consumed (and Qs visible)
+        for (int idx = tid; idx < AT_BK * 16; idx += 128) {
+            const int r = idx >> 4, d4 = idx & 15;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (kt + r < nk) {
+                const size_t off = (size_t)(k0 + kt + r) * ldk + head * 64 + d4 * 4;
+                kv = *reinterpret_cast<const float4*>(K + off);
+                vv = *reinterpret_cast<const float4*>(V + off);
+            }
+            *reinterpret_cast<float4*>(&Ks[r][d4 * 4]) = kv;
+            *reinterpret_cast<float4*>(&Vs[r][d4 * 4]) = vv;
+        }
+        __syncthreads();
+
+        // S = Q K^T for rows ty+16i, keys tx+8j
+        float s[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+        for (int d4 = 0; d4 < 16; ++d4) {
+            float4 qv[4], kv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(&Qs[ty + 16 * i][d4 * 4]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) kv[j] = *reinterpret_cast<const float4*>(&Ks[tx + 8 * j][d4 * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s[i][j] = fmaf(qv[i].x, kv[j].x, s[i][j]); s[i][j] = fmaf(qv[i].y, kv[j].y, s[i][j]);
+                    s[i][j] = fmaf(qv[i].z, kv[j].z, s[i][j]); s[i][j] = fmaf(qv[i].w, kv[j].w, s[i][j]);
+                }
+        }
+        // online softmax
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[i][j] = (kt + tx + 8 * j < nk) ? s[i][j] * 0.125f : -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            const float mn = fmaxf(m[i], mx);                // finite: every tile has >= 1 valid key
+            const float corr = expf(m[i] - mn);
+            float ps = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = expf(s[i][j] - mn);
+                ps += p;
+                Ps[ty + 16 * i][tx + 8 * j] = p;
+            }
+            ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+            l[i] = l[i] * corr + ps;
+            m[i] = mn;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[i][j] *= corr;
+        }
+        __syncthreads();
+        // O += P V for rows ty+16i, dims tx*8 .. tx*8+7
+#pragma unroll 4
+        for (int j4 = 0; j4 < AT_BK / 4; ++j4) {
+            float4 pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pv[i] = *reinterpret_cast<const float4*>(&Ps[ty + 16 * i][j4 * 4]);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4 v0 = *reinterpret_cast<const float4*>(&Vs[j4 * 4 + jj][tx * 8]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&Vs[j4 * 4 + jj][tx * 8 + 4]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float p = (jj == 0) ? pv[i].x : (jj == 1) ? pv[i].y : (jj == 2) ? pv[i].z : pv[i].w;
+                    o[i][0] = fmaf(p, v0.x, o[i][0]); o[i][1] = fmaf(p, v0.y, o[i][1]);
+                    o[i][2] = fmaf(p, v0.z, o[i][2]); o[i][3] = fmaf(p, v0.w, o[i][3]);
+                    o[i][4] = fmaf(p, v1.x, o[i][4]); o[i][5] = fmaf(p, v1.y, o[i][5]);
+                    o[i][6] = fmaf(p, v1.z, o[i][6]); o[i][7] = fmaf(p, v1.w, o[i][7]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty + 16 * i;
+        if (r < nqt) {
+            const float inv = 1.0f / l[i];
+            float* orow = O + (size_t)(o0 + qt0 + r) * ldo + head * 64 + tx * 8;
+            *reinterpret_cast<float4*>(orow) = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+            *reinterpret_cast<float4*>(orow + 4) = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small data-movement kernels
+// ------------------------------------------------------------------------------------------------
+// x[b*P + p] = mem[row_off[seq_wf[b]] + tok[p*B + b]]   (model_para.py:217-219)
+__global__ void gather_tgt_kernel(const float* __restrict__ mem, const int* __restrict__ row_off,
+                                  const int* __restrict__ seq_wf, const int* __restrict__ tok,
+                                  float* __restrict__ x, int B, int P, int E, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    const int e4n = E >> 2;
+    const long long total = (long long)B * P * e4n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % e4n);
+        const long long r = i / e4n;
+        const int b = (int)(r / P), p = (int)(r % P);
+        const int src = row_off[seq_wf[b]] + tok[(size_t)p * B + b];
+        reinterpret_cast<float4*>(x)[r * e4n + c] = reinterpret_cast<const float4*>(mem)[(size_t)src * e4n + c];
+    }
+}
+
+// dst[r] = src[r*mul + off]  (rows of E floats)
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int mul, int off,
+                                 int E, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    const int e4n = E >> 2;
+    const long long total = (long long)rows * e4n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % e4n);
+        const long long r = i / e4n;
+        reinterpret_cast<float4*>(dst)[r * e4n + c] = reinterpret_cast<const float4*>(src)[((size_t)r * mul + off) * e4n + c];
+    }
+}
+
+// rows 0..3 of every wireframe's packed block <- special-token table (embedding.py:30-32,36)
+__global__ void token_rows_kernel(const float* __restrict__ table, const int* __restrict__ row_off, float* __restrict__ x,
+                                  int n_wf, int num_token, int E) {
+    const int e4n = E >> 2;
+    const int total = n_wf * num_token * e4n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % e4n;
+        const int t = (i / e4n) % num_token;
+        const int w = i / (e4n * num_token);
+        reinterpret_cast<float4*>(x)[(size_t)(row_off[w] + t) * e4n + c] = reinterpret_cast<const float4*>(table)[t * e4n + c];
+    }
+}
+
+// tok[0*B + b] = first token of sequence b (anchor or SOS); also resets the loop state
+__global__ void init_tokens_kernel(const int* __restrict__ seq_first, int* __restrict__ tok, int B,
+                                   int* stop, int* steps_run, int* eos_found) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) tok[i] = seq_first[i];
+    if (i == 0) { *stop = 0; *steps_run = 0; *eos_found = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointer head: logits[b, j] = <mem[row_off[w]+j], ptr[b]>, j < v_len[w]; first-max argmax; append.
+// One CTA (8 warps) per sequence; warp w scans rows w, w+8, ...; fixed reduction order.
+// ------------------------------------------------------------------------------------------------
+struct PointerArgs {
+    const float* mem;            // packed memory [R,E]
+    const float* ptr; int ptr_stride_rows; int ptr_off;   // pointer row of sequence b: ptr[(b*stride + off) * E]
+    const int* row_off; const int* v_len; const int* seq_wf;
+    float* logits; int L;        // [B, L] masked logits (finfo.min beyond v_len), or null
+    int* tok_out;                // tok[(P)*B + b] slot for the new token, or null (forced-prefix mode)
+    int B, E;
+    int num_token;
+    int* nonstop_count;          // parallel: number of sequences with next >= num_token this step
+    int* eos_count;              // seq2seq : cumulative count of next == EOS
+    const int* stop;
+};
+
+__global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
+    FFB_STOP_CHECK(a.stop);
+    __shared__ __align__(16) float ps[1024];
+    __shared__ float bestv[8];
+    __shared__ int besti[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float* pr = a.ptr + ((size_t)b * a.ptr_stride_rows + a.ptr_off) * a.E;
+    for (int c = tid; c < a.E; c += 256) ps[c] = pr[c];
+    __syncthreads();
+    const int wf = a.seq_wf[b];
+    const int r0 = a.row_off[wf], vl = a.v_len[wf];
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int j = w; j < vl; j += 8) {
+        const float* mr = a.mem + (size_t)(r0 + j) * a.E;
+        float s = 0.f;
+        for (int c = lane * 4; c < a.E; c += 128) {
+            const float4 mv = *reinterpret_cast<const float4*>(mr + c);
+            const float4 pv = *reinterpret_cast<const float4*>(&ps[c]);
+            s = fmaf(mv.x, pv.x, s); s = fmaf(mv.y, pv.y, s); s = fmaf(mv.z, pv.z, s); s = fmaf(mv.w, pv.w, s);
+        }
+        s = warp_sum(s);
+        if (a.logits && lane == 0) a.logits[(size_t)b * a.L + j] = s;
+        if (s > bv) { bv = s; bi = j; }                    // strictly greater: first max within this warp's rows
+    }
+    if (a.logits) for (int j = vl + tid; j < a.L; j += 256) a.logits[(size_t)b * a.L + j] = -FLT_MAX;   // finfo.min
+    if (lane == 0) { bestv[w] = bv; besti[w] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        float v = bestv[0]; int idx = besti[0];
+        for (int k = 1; k < 8; ++k)
+            if (bestv[k] > v || (bestv[k] == v && besti[k] < idx)) { v = bestv[k]; idx = besti[k]; }
+        if (a.tok_out) {
+            a.tok_out[b] = idx;
+            if (a.nonstop_count && idx >= a.num_token) atomicAdd(a.nonstop_count, 1);
+            if (a.eos_count && idx == 3) atomicAdd(a.eos_count, 1);        // token.EOS == 3 (config.py:44)
+        }
+    }
+}
+
+// After each step: evaluate the reference's stop predicate and count the step.
+//   parallel (model_para.py:232): stop if all next < num_token  <=> nonstop_count == 0
+//   seq2seq  (model.py:207-210) : stop if cumulative EOS count == N
+__global__ void step_end_kernel(int mode, int n_seq, int* nonstop_count, int* eos_count, int* stop, int* steps_run) {
+    if (*stop) return;
+    *steps_run += 1;
+    if (mode == 0) {
+        if (*nonstop_count == 0) *stop = 1;
+        *nonstop_count = 0;
+    } else {
+        if (*eos_count == n_seq) *stop = 1;
+    }
+}
+
+// predict[w, f, t] (int64) from the step-major token buffer; zero after the executed steps.
+//   slot_seq[w*F + f] = decoded sequence feeding output slot (w,f)
+__global__ void expand_predict_kernel(const int* __restrict__ tok, const int* __restrict__ slot_seq,
+                                      const int* __restrict__ steps_run, long long* __restrict__ predict,
+                                      long long n_slots, int B, int T) {
+    const long long total = n_slots * T;
+    const int filled = *steps_run + 1;             // rows of `predicts` that exist (start token + S steps)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const long long s = i / T;
+        predict[i] = (t < filled) ? (long long)tok[(size_t)t * B + slot_seq[s]] : 0ll;
+    }
+}
+
+// logits_out[slot, :] = logits[slot_seq[slot], :]
+__global__ void expand_rows_kernel(const float* __restrict__ src, const int* __restrict__ slot_seq,
+                                   float* __restrict__ dst, long long n_slots, int L) {
+    const long long total = n_slots * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % L);
+        const long long s = i / L;
+        dst[i] = src[(size_t)slot_seq[s] * L + c];
+    }
+}
+
+// padded [N, L, E] view of the packed memory (zeros in padded rows)
+__global__ void unpack_memory_kernel(const float* __restrict__ mem, const int* __restrict__ row_off,
+                                     const int* __restrict__ v_len, float* __restrict__ out, int n_wf, int L, int E) {
+    const int e4n = E >> 2;
+    const long long total = (long long)n_wf * L * e4n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % e4n);
+        const long long r = i / e4n;
+        const int j = (int)(r % L), w = (int)(r / L);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < v_len[w]) v = reinterpret_cast<const float4*>(mem)[(size_t)(row_off[w] + j) * e4n + c];
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// int64 prefix [P, B_full] -> int32 tok [P, B_eff] through seq -> first slot map
+__global__ void load_prefix_kernel(const long long* __restrict__ prefix, const int* __restrict__ seq_slot,
+                                   int* __restrict__ tok, int P, int B_full, int B) {
+    const int total = P * B;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / B, b = i % B;
+        tok[i] = (int)prefix[(size_t)p * B_full + seq_slot[b]];
+    }
+}
+
+}  // namespace ffb

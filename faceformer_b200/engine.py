@@ -1,0 +1,267 @@
+"""Host-side owner of one libffb200 handle (one per device per process).
+
+PyTorch is plumbing here: it supplies device memory (``torch.Tensor.data_ptr``)
+and the current CUDA stream; all arithmetic happens inside libffb200.so.
+Inputs may be CUDA tensors (device path: what ``Trainer.forward`` hands the model
+after Lightning moved the batch, trainer.py:27-28) or host arrays / pinned tensors
+(host path: the library does the H2D/D2H copies itself).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .config import MODE_PARALLEL, MODE_SEQ2SEQ, ModelConfig
+from .lib import FFB_DEVICE, FFB_HOST, FFBError
+from .synth import state_dict_names
+
+
+def pack_state_dict(sd, cfg: ModelConfig, mode: int) -> np.ndarray:
+    """Strictly validate a reference ``state_dict`` (names, shapes) and
+    concatenate its float tensors in state_dict order into the fp32 blob ``ffb_load_weights``
+    expects.  Accepts numpy arrays or torch tensors; a leading ``model.`` prefix (Lightning
+    checkpoints, trainer.py:20) is stripped."""
+    clean = {}
+    for k, v in sd.items():
+        k = k[6:] if k.startswith("model.") else k
+        clean[k] = v
+    expected = state_dict_names(cfg, mode)
+    names = {n for n, _, _ in expected}
+    missing = [n for n in names if n not in clean]
+    unexpected = [k for k in clean if k not in names]
+    if missing or unexpected:
+        raise FFBError(f"state_dict mismatch: missing {sorted(missing)[:5]} unexpected {sorted(unexpected)[:5]}")
+    parts = []
+    for name, shape, dt in expected:
+        v = clean[name]
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().numpy()
+        v = np.asarray(v)
+        if tuple(v.shape) != tuple(shape):
+            raise FFBError(f"state_dict[{name!r}] has shape {tuple(v.shape)}, expected {tuple(shape)}")
+        if dt == "i8":
+            if not np.array_equal(v.reshape(-1), np.arange(shape[1])):
+                raise FFBError(f"{name} must be arange (embedding.py:98-99)")
+            continue
+        parts.append(np.ascontiguousarray(v, dtype=np.float32).reshape(-1))
+    return np.concatenate(parts)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _is_cuda(a) -> bool:
+    return hasattr(a, "is_cuda") and bool(a.is_cuda)
+
+
+class Engine:
+    """``model(batch)`` for one device.  Not thread-safe (one handle, stream-ordered calls)."""
+
+    def __init__(self, cfg: ModelConfig, mode: int, device: int = 0):
+        self.cfg, self.mode, self.device = cfg, mode, int(device)
+        self._lib = _lib.load()
+        c = _lib.ffb_config(abi_version=_lib.FFB_ABI_VERSION, mode=mode, num_model=cfg.num_model,
+                            num_head=cfg.num_head, num_feedforward=cfg.num_feedforward,
+                            num_encoder_layers=cfg.num_encoder_layers, num_decoder_layers=cfg.num_decoder_layers,
+                            in_dim=cfg.in_dim, num_lines=cfg.num_lines, num_token=cfg.num_token,
+                            seq_len=cfg.seq_len(mode), device=self.device)
+        self._c = c
+        self._h = C.c_void_p()
+        st = self._lib.ffb_create(C.byref(c), C.byref(self._h))
+        if st != 0:
+            raise FFBError(f"ffb_create failed ({st}): {_lib.last_error(None)}")
+        self.weights_loaded = False
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ffb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        _lib.check(st, self._h)
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- weights --------------------------------------------------------------------------------
+    def weight_count(self) -> int:
+        return int(self._lib.ffb_weight_count(C.byref(self._c)))
+
+    def load_state_dict(self, sd):
+        blob = pack_state_dict(sd, self.cfg, self.mode)
+        self.load_blob(blob)
+
+    def load_blob(self, blob):
+        """blob: fp32 numpy array (host) or CUDA tensor in ffb_load_weights order."""
+        loc = FFB_DEVICE if _is_cuda(blob) else FFB_HOST
+        n = blob.numel() if hasattr(blob, "numel") else blob.size
+        if loc == FFB_HOST:
+            blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._check(self._lib.ffb_load_weights(self._h, _ptr(blob), n, loc, self._stream()))
+        self.weights_loaded = True
+
+    def set_option(self, opt: int, value: int):
+        self._check(self._lib.ffb_set_option(self._h, opt, int(value)))
+
+    # -- the path -------------------------------------------------------------------------------
+    def _prep_inputs(self, coords, pad_mask, num_input):
+        import torch
+        dev = _is_cuda(coords)
+        if dev:
+            coords = coords.contiguous().float()
+            pad_mask = pad_mask.to(device=coords.device).contiguous().to(torch.uint8)
+            if num_input is not None:
+                num_input = torch.as_tensor(num_input).to(device=coords.device, dtype=torch.int64).contiguous()
+            n = coords.shape[0]
+        else:
+            if hasattr(coords, "numpy"):
+                coords = coords.numpy()
+            if hasattr(pad_mask, "numpy"):
+                pad_mask = pad_mask.numpy()
+            if num_input is not None and hasattr(num_input, "numpy"):
+                num_input = num_input.numpy()
+            coords = np.ascontiguousarray(coords, dtype=np.float32)
+            pad_mask = np.ascontiguousarray(pad_mask).astype(np.uint8, copy=False)
+            if num_input is not None:
+                num_input = np.ascontiguousarray(num_input, dtype=np.int64)
+            n = coords.shape[0]
+        exp = (n, self.cfg.num_lines)
+        if tuple(coords.shape[:2]) != exp or int(np.prod(coords.shape[2:])) != self.cfg.in_dim:
+            raise FFBError(f"input has shape {tuple(coords.shape)}, expected [N,{self.cfg.num_lines},P,D] with P*D={self.cfg.in_dim}")
+        if tuple(pad_mask.shape) != exp:
+            raise FFBError(f"input_mask has shape {tuple(pad_mask.shape)}, expected {exp}")
+        if self.mode == MODE_PARALLEL and num_input is None:
+            raise FFBError("num_input is required for SurfaceFormer_Parallel (model_para.py:187)")
+        if self.mode == MODE_SEQ2SEQ:
+            num_input = None
+        return coords, pad_mask, num_input, n, (FFB_DEVICE if dev else FFB_HOST)
+
+    def encode(self, coords, pad_mask, num_input=None):
+        coords, pad_mask, num_input, n, loc = self._prep_inputs(coords, pad_mask, num_input)
+        self._keep = (coords, pad_mask, num_input)          # keep alive until the stream consumed them
+        self._check(self._lib.ffb_encode(self._h, _ptr(coords), _ptr(pad_mask), _ptr(num_input), n, loc, self._stream()))
+        self._loc, self._n = loc, n
+        return self.batch_info()
+
+    def batch_info(self) -> dict:
+        n, f = C.c_int32(), C.c_int32()
+        b, be, r = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.ffb_batch_info(self._h, C.byref(n), C.byref(f), C.byref(b), C.byref(be), C.byref(r)))
+        return dict(N=n.value, F=f.value, B=b.value, B_eff=be.value, R=r.value)
+
+    def _alloc(self, shape, dtype, loc):
+        import torch
+        if loc == FFB_DEVICE:
+            return torch.empty(shape, dtype=dtype, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype={torch.int64: np.int64, torch.float32: np.float32}[dtype])
+
+    def decode_greedy(self, want_steps: bool = True, out=None):
+        """Returns (predict, steps).  predict is int64 [N,F,T] / [N,T] on the inputs' side (CUDA tensor or numpy)."""
+        import torch
+        info = self.batch_info()
+        T = self.cfg.seq_len(self.mode)
+        shape = (info["N"], info["F"], T) if self.mode == MODE_PARALLEL else (info["N"], T)
+        predict = out if out is not None else self._alloc(shape, torch.int64, self._loc)
+        steps = C.c_int32(-1)
+        self._check(self._lib.ffb_decode_greedy(self._h, _ptr(predict), self._loc,
+                                                C.byref(steps) if want_steps else None, self._stream()))
+        return predict, (steps.value if want_steps else None)
+
+    def forward_eval(self, coords, pad_mask, num_input=None, want_steps: bool = True, out=None):
+        self.encode(coords, pad_mask, num_input)
+        return self.decode_greedy(want_steps, out)
+
+    # -- parity hooks ---------------------------------------------------------------------------
+    def get_memory(self):
+        import torch
+        info = self.batch_info()
+        out = self._alloc((info["N"], self.cfg.mem_len, self.cfg.num_model), torch.float32, self._loc)
+        self._check(self._lib.ffb_get_memory(self._h, _ptr(out), self._loc, self._stream()))
+        return out
+
+    def get_last_logits(self):
+        import torch
+        info = self.batch_info()
+        out = self._alloc((info["B"], self.cfg.mem_len), torch.float32, self._loc)
+        self._check(self._lib.ffb_get_last_logits(self._h, _ptr(out), self._loc, self._stream()))
+        return out
+
+    def get_last_pointer(self):
+        import torch
+        info = self.batch_info()
+        T = self.cfg.seq_len(self.mode)
+        buf = self._alloc((info["B_eff"], T - 1, self.cfg.num_model), torch.float32, self._loc)
+        P = C.c_int32()
+        self._check(self._lib.ffb_get_last_pointer(self._h, _ptr(buf), C.byref(P), self._loc, self._stream()))
+        flat = buf.reshape(-1)[: info["B_eff"] * P.value * self.cfg.num_model]
+        return flat.reshape(info["B_eff"], P.value, self.cfg.num_model)
+
+    def forced_prefix_logits(self, prefix):
+        """prefix int64 [P,B] (numpy or CUDA tensor) -> logits [B,L]."""
+        import torch
+        info = self.batch_info()
+        dev = _is_cuda(prefix)
+        if dev:
+            prefix = prefix.contiguous().to(torch.int64)
+        else:
+            prefix = np.ascontiguousarray(prefix, dtype=np.int64)
+        if tuple(prefix.shape[1:]) != (info["B"],):
+            raise FFBError(f"prefix has shape {tuple(prefix.shape)}, expected [P,{info['B']}]")
+        loc = FFB_DEVICE if dev else FFB_HOST
+        out = self._alloc((info["B"], self.cfg.mem_len), torch.float32, loc)
+        self._check(self._lib.ffb_forced_prefix_logits(self._h, _ptr(prefix), int(prefix.shape[0]), _ptr(out), loc, self._stream()))
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.ffb_kernel_launches(self._h))
+
+    def phase_times(self):
+        arr = (C.c_float * 2)()
+        self._check(self._lib.ffb_phase_times(self._h, arr, 2))
+        return float(arr[0]), float(arr[1])
+
+    def profile_read(self) -> dict:
+        """class -> dict(ms, flops, launches) since profiling was enabled / last read."""
+        n = len(_lib.PROFILE_CLASSES)
+        ms, fl, ln = (C.c_float * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        self._check(self._lib.ffb_profile_read(self._h, n, ms, fl, ln))
+        return {c: dict(ms=float(ms[i]), flops=float(fl[i]), launches=int(ln[i])) for i, c in enumerate(_lib.PROFILE_CLASSES)}
+
+    # -- op-level hooks (CUDA tensors)------------------------------------------------------------
+    def op_linear(self, A, W, bias=None, R=None, pos=None, pos_mod=0, pos_cols=0, relu=False):
+        import torch
+        M, K = A.shape
+        N = W.shape[0]
+        Cc = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        self._check(self._lib.ffb_op_linear(self._h, _ptr(A), _ptr(W), _ptr(bias), _ptr(R), _ptr(pos), pos_mod, pos_cols,
+                                            _ptr(Cc), M, N, K, int(relu), self._stream()))
+        return Cc
+
+    def op_layernorm(self, x, gamma, beta):
+        import torch
+        y = torch.empty_like(x)
+        self._check(self._lib.ffb_op_layernorm(self._h, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.shape[0], x.shape[1], self._stream()))
+        return y
+
+    def op_attention(self, kind, q, k, v, G, nq, nk):
+        import torch
+        H = self.cfg.num_head
+        out = torch.empty((G * nq, H * 64), dtype=torch.float32, device=q.device)
+        self._check(self._lib.ffb_op_attention(self._h, kind, _ptr(q), q.stride(0), _ptr(k), _ptr(v), k.stride(0), _ptr(out),
+                                               G, nq, nk, H, self._stream()))
+        return out

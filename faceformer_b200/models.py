@@ -1,0 +1,177 @@
+"""Drop-in model classes for the reference's model boundary.
+
+``SurfaceFormer_Parallel_B200`` / ``SurfaceFormer_B200`` take the reference constructors'
+kwargs (model_para.py:14-19, model.py:14-18; built as ``model_class(**cfg.model)``,
+trainer.py:20), hold parameters under the reference's ``state_dict`` names (strict
+``load_state_dict`` of a reference checkpoint works) and implement
+``forward(inputs: dict) -> dict`` for eval (model_para.py:243-259): the same dict comes back
+with ``inputs['predict']`` (int64 [N,F,T] or [N,T]) on the input's device.
+
+The modules below are parameter CONTAINERS only; no arithmetic of the path runs in PyTorch.
+``forward`` hands device pointers to libffb200.so through ``Engine``.  Training
+(``forward_train``, model_para.py:99-171) is out of scope and raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .config import MODE_PARALLEL, MODE_SEQ2SEQ, ModelConfig
+from .engine import Engine
+from .lib import FFBError
+
+
+class _Attn(nn.Module):
+    """Parameter layout of nn.MultiheadAttention (in_proj_weight/bias, out_proj.*)."""
+
+    def __init__(self, E):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * E, E))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * E))
+        self.out_proj = nn.Linear(E, E)
+
+
+class _EncLayer(nn.Module):
+    def __init__(self, E, FF):
+        super().__init__()
+        self.self_attn = _Attn(E)
+        self.linear1 = nn.Linear(E, FF)
+        self.linear2 = nn.Linear(FF, E)
+        self.norm1 = nn.LayerNorm(E)
+        self.norm2 = nn.LayerNorm(E)
+
+
+class _DecLayer(nn.Module):
+    def __init__(self, E, FF):
+        super().__init__()
+        self.self_attn = _Attn(E)
+        self.multihead_attn = _Attn(E)
+        self.linear1 = nn.Linear(E, FF)
+        self.linear2 = nn.Linear(FF, E)
+        self.norm1 = nn.LayerNorm(E)
+        self.norm2 = nn.LayerNorm(E)
+        self.norm3 = nn.LayerNorm(E)
+
+
+class _Stack(nn.Module):
+    def __init__(self, layers, E):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.norm = nn.LayerNorm(E)
+
+
+class _ValEnc(nn.Module):
+    def __init__(self, in_dim, E, num_token):
+        super().__init__()
+        self.embedding_token = nn.Embedding(num_token, E)
+        self.embedding_value = nn.Sequential(nn.Linear(in_dim, E), nn.ReLU(), nn.Linear(E, E))
+
+
+class _PosEnc(nn.Module):
+    def __init__(self, E, max_len):
+        super().__init__()
+        self.register_buffer("position", torch.arange(0, max_len, dtype=torch.long).unsqueeze(0))
+        self.pos_embed = nn.Embedding(max_len, E)
+
+
+class _SurfaceFormerB200Base(nn.Module):
+    MODE = MODE_PARALLEL
+
+    def __init__(self, num_model=512, num_head=8, num_feedforward=2048, num_encoder_layers=6,
+                 num_decoder_layers=6, dropout=0.1, activation="relu", normalize_before=True,
+                 num_points_per_line=50, num_lines=64, point_dim=2, seq_length=10, token=None,
+                 teacher_forcing_ratio=0, **kwargs):
+        super().__init__()
+        if activation != "relu" or not normalize_before:
+            raise FFBError("only the reference's shipped configuration is supported: pre-norm + ReLU "
+                           "(model_para.py:16; neither key is in faceformer/config.py)")
+        num_token = int(token.len) if token is not None else 4
+        kw = dict(num_model=num_model, num_head=num_head, num_feedforward=num_feedforward,
+                  num_encoder_layers=num_encoder_layers, num_decoder_layers=num_decoder_layers,
+                  num_points_per_line=num_points_per_line, num_lines=num_lines, point_dim=point_dim,
+                  num_token=num_token, dropout=dropout)
+        kw["max_face_length" if self.MODE == MODE_PARALLEL else "label_seq_length"] = seq_length
+        self.cfg = ModelConfig(**kw)
+        self.num_model = num_model
+        self.token = token
+        self.num_token = num_token
+        E, FF = num_model, num_feedforward
+        self.val_enc = _ValEnc(self.cfg.in_dim, E, num_token)
+        self.pos_enc = _PosEnc(E, num_lines + num_token)
+        self.query_pos_enc = _PosEnc(E, seq_length)
+        self.encoder = _Stack([_EncLayer(E, FF) for _ in range(num_encoder_layers)], E)
+        self.decoder = _Stack([_DecLayer(E, FF) for _ in range(num_decoder_layers)], E)
+        self.project = nn.Linear(E, E)
+        for _, p in self.named_parameters():               # model_para.py:50-53
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._engines = {}
+        self._weights_version = 0
+        self.last_steps = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
+
+    # -- weights -----------------------------------------------------------------------------
+    def invalidate_weights(self):
+        """Call after mutating parameters in place; load_state_dict does it automatically."""
+        self._weights_version += 1
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
+        return out
+
+    def engine(self, device_index: int) -> Engine:
+        ent = self._engines.get(device_index)
+        if ent is None:
+            ent = [Engine(self.cfg, self.MODE, device_index), -1]
+            self._engines[device_index] = ent
+        if ent[1] != self._weights_version:
+            ent[0].load_state_dict(self.state_dict())
+            ent[1] = self._weights_version
+        return ent[0]
+
+    # -- forward -----------------------------------------------------------------------------
+    def forward_train(self, inputs):
+        raise NotImplementedError("training is out of scope of faceformer_b200 (SURVEY.md section 8f4); "
+                                  "train with the reference classes and load the state_dict here")
+
+    def forward_eval(self, inputs):
+        coords = inputs["input"]
+        if not (torch.is_tensor(coords) and coords.is_cuda):
+            raise FFBError("faceformer_b200 has no CPU path: move the batch to a CUDA device "
+                           "(Lightning does so before Trainer.forward, trainer.py:27-28)")
+        eng = self.engine(coords.device.index if coords.device.index is not None else torch.cuda.current_device())
+        num_input = inputs.get("num_input") if self.MODE == MODE_PARALLEL else None
+        with torch.cuda.device(coords.device):
+            predict, steps = eng.forward_eval(coords.flatten(2), inputs["input_mask"], num_input, want_steps=True)
+            self.last_steps = steps
+            if self.MODE == MODE_SEQ2SEQ:                   # model.py:216-217
+                inputs["embedding"] = eng.get_memory()
+                inputs["pointer"] = eng.get_last_pointer()
+        inputs["predict"] = predict
+        return inputs
+
+    def forward(self, inputs):
+        if self.training:
+            return self.forward_train(inputs)
+        return self.forward_eval(inputs)
+
+
+class SurfaceFormer_Parallel_B200(_SurfaceFormerB200Base):
+    """Replaces SurfaceFormer_Parallel (model_para.py:12-259) on the eval path."""
+    MODE = MODE_PARALLEL
+
+    def __init__(self, *args, max_face_length=10, **kwargs):
+        kwargs.pop("seq_length", None)
+        super().__init__(*args, seq_length=max_face_length, **kwargs)
+        self.max_face_length = max_face_length
+
+
+class SurfaceFormer_B200(_SurfaceFormerB200Base):
+    """Replaces SurfaceFormer (model.py:12-237) on the eval path."""
+    MODE = MODE_SEQ2SEQ
+
+    def __init__(self, *args, label_seq_length=2000, num_lines=1000, **kwargs):
+        kwargs.pop("seq_length", None)
+        super().__init__(*args, seq_length=label_seq_length, num_lines=num_lines, **kwargs)
+        self.num_labels = label_seq_length

@@ -1,0 +1,180 @@
+/*
+ * ffb200.h -- C ABI of libffb200.so: FaceFormer greedy pointer-decode on B200 (sm_100a).
+ *
+ * The reference (manycore-research/faceformer) is pure Python/PyTorch and has NO
+ * FFI of its own; the boundary this library replaces is the model call
+ *     Trainer.forward(batch) -> self.model(batch)        faceformer/trainer.py:27-28
+ * i.e. SurfaceFormer_Parallel.forward_eval                faceformer/models/model_para.py:181-241
+ * and  SurfaceFormer.forward_eval                         faceformer/models/model.py:169-219
+ * over faceformer/transformer.py and faceformer/embedding.py.  The entry points
+ * below are what a ctypes binding in faceformer/models/ would call (INTEGRATION.md
+ * shows that binding).  Plain C types only: no torch / CUDA types in signatures
+ * (a CUDA stream is passed as void*).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ffb_status on failure;
+ *     ffb_last_error() returns a message.  Nothing throws or exits across the ABI.
+ *   - "loc" arguments say where caller buffers live: FFB_HOST or FFB_DEVICE.
+ *     With FFB_HOST the library performs the H2D/D2H copies itself (on `stream`).
+ *   - one handle per device per process; calls on one handle are not re-entrant;
+ *     work is stream-ordered on the stream passed in.
+ *   - the library owns only the handle, the packed weights and its workspaces
+ *     (edge memory, cross-attention K/V cache, token buffer, activations).
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_ABI_VERSION 1
+
+typedef struct ffb_handle ffb_handle;
+
+typedef enum {
+    FFB_OK = 0,
+    FFB_ERR_ARG = -1,          /* bad argument / unsupported geometry            */
+    FFB_ERR_CUDA = -2,         /* CUDA runtime error (message has the details)   */
+    FFB_ERR_STATE = -3,        /* call sequence error (e.g. decode before encode)*/
+    FFB_ERR_UNSUPPORTED = -4   /* valid in the reference, not supported here     */
+} ffb_status;
+
+enum { FFB_HOST = 0, FFB_DEVICE = 1 };
+enum { FFB_MODE_PARALLEL = 0,  /* SurfaceFormer_Parallel, model_para.py          */
+       FFB_MODE_SEQ2SEQ = 1 }; /* SurfaceFormer,          model.py               */
+
+/* Constructor arguments of the reference models (model_para.py:14-19, model.py:14-18;
+ * values from faceformer/config.py:27-49 and configs/\*.yml). */
+typedef struct {
+    int32_t abi_version;          /* FFB_ABI_VERSION                                         */
+    int32_t mode;                 /* FFB_MODE_*                                              */
+    int32_t num_model;            /* E, multiple of 64; head dim must be 64                  */
+    int32_t num_head;             /* H = E / 64                                              */
+    int32_t num_feedforward;      /* FF                                                      */
+    int32_t num_encoder_layers;
+    int32_t num_decoder_layers;
+    int32_t in_dim;               /* num_points_per_line * point_dim (multiple of 4)         */
+    int32_t num_lines;            /* max edges per wireframe; memory rows L = num_lines+num_token */
+    int32_t num_token;            /* token.len (4)                                           */
+    int32_t seq_len;              /* T = max_face_length (parallel) or label_seq_length      */
+    int32_t device;               /* CUDA device ordinal                                     */
+} ffb_config;
+
+/* Options for ffb_set_option. */
+enum {
+    FFB_OPT_DEDUP_PAD = 1,   /* 1 (default): the F-n_i padded-anchor sequences of a wireframe
+                                (all start with token 3, model_para.py:204-205) are decoded once
+                                and broadcast; 0: decode all N*F sequences like the reference.   */
+    FFB_OPT_PRUNE_LAST = 2   /* 1 (default in parallel mode): in the last decoder layer only the
+                                last position is carried past self-attention (only pointer[-1]
+                                is consumed, model_para.py:176); 0: all positions (seq2seq
+                                default, so that 'pointer' [N,P,E] of model.py:217 is complete). */
+};
+
+/* Number of fp32 elements ffb_load_weights expects for this config: the reference
+ * state_dict's float tensors, concatenated in state_dict order;
+ * the two int64 `position` buffers are skipped.  Returns 0 for an invalid config. */
+size_t ffb_weight_count(const ffb_config* cfg);
+
+int ffb_create(const ffb_config* cfg, ffb_handle** out);
+int ffb_destroy(ffb_handle* h);
+
+/* Message for the last failure on this handle (h may be NULL: last ffb_create failure). */
+const char* ffb_last_error(const ffb_handle* h);
+
+int ffb_set_option(ffb_handle* h, int option, int value);
+
+/* Replaces model.load_state_dict (main.py:46 via Trainer.load_from_checkpoint). */
+int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, void* stream);
+
+/* Everything before the decode loop (model_para.py:183-214 / model.py:171-186):
+ * embedding, encoder, anchors, and -- once per wireframe instead of once per step --
+ * the cross-attention K/V projections of every decoder layer.
+ *   coords    float [N, num_lines, in_dim]     inputs['input'] flattened over (P,D)
+ *   pad_mask  uint8 [N, num_lines]             inputs['input_mask'] (1 = padding); must be of
+ *                                              prefix form (valid edges first), as
+ *                                              data_para.py:67-68 builds it, else FFB_ERR_UNSUPPORTED
+ *   num_input int64 [N]                        inputs['num_input'] (parallel mode; NULL in seq2seq)
+ * pad_mask and num_input are read on the host (the reference also syncs on max(num_input),
+ * model_para.py:187); with loc == FFB_DEVICE they are copied back first. */
+int ffb_encode(ffb_handle* h, const float* coords, const uint8_t* pad_mask,
+               const int64_t* num_input, int32_t n_wireframes, int loc, void* stream);
+
+/* Geometry of the encoded batch: F = max(num_input) (1 in seq2seq), B = N*F sequences the
+ * reference would decode, B_eff = sequences actually decoded, R = packed memory rows. */
+int ffb_batch_info(const ffb_handle* h, int32_t* n_wireframes, int32_t* F, int64_t* B,
+                   int64_t* B_eff, int64_t* R);
+
+/* The greedy loop (model_para.py:216-240 / model.py:193-218), entirely on the device:
+ * no host synchronisation per step; early stop is a device-side flag.
+ *   predict   int64 [N, F, T] (parallel) or [N, T] (seq2seq)      inputs['predict']
+ *   steps_run number of executed decode steps S (host int32, written after a stream sync;
+ *             may be NULL, in which case the call is fully asynchronous for loc == FFB_DEVICE) */
+int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_run, void* stream);
+
+/* ffb_encode + ffb_decode_greedy: the whole `model(batch)` call. */
+int ffb_forward_eval(ffb_handle* h, const float* coords, const uint8_t* pad_mask,
+                     const int64_t* num_input, int32_t n_wireframes, int64_t* predict,
+                     int loc, int32_t* steps_run, void* stream);
+
+/* Parity hooks (used by tests; they do not change decode results). */
+
+/* Encoder memory, float [N, L, E] (= inputs['embedding'] of model.py:216); rows of padded
+ * edges are written as zeros (the reference computes values there that nothing reads). */
+int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream);
+
+/* Masked pointer logits [B, L] (select_next up to masked_fill, model_para.py:173-177) of the
+ * LAST executed decode step, expanded to the reference's B = N*F rows. */
+int ffb_get_last_logits(ffb_handle* h, float* logits, int loc, void* stream);
+
+/* seq2seq only: inputs['pointer'] [N, P, E] of the last executed step (model.py:217);
+ * requires FFB_OPT_PRUNE_LAST = 0.  *P_out receives P. */
+int ffb_get_last_pointer(ffb_handle* h, float* pointer, int32_t* P_out, int loc, void* stream);
+
+/* One loop body on a caller-supplied token prefix (forced-prefix parity):
+ *   prefix int64 [P, B] with B = N*F (parallel) or N (seq2seq), logits float [B, L].
+ * Requires FFB_OPT_DEDUP_PAD = 0 at encode time in parallel mode. */
+int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, float* logits,
+                             int loc, void* stream);
+
+/* Count of this library's kernels launched on the handle since creation (bench `gpu_launches`). */
+int64_t ffb_kernel_launches(const ffb_handle* h);
+
+/* Device-time of the phases of the last forward (ms, CUDA events; valid after a stream sync):
+ * out[0] = encode (embedding + encoder + cross-K/V), out[1] = decode loop.  Timing is only
+ * recorded when enabled with ffb_set_option(h, FFB_OPT_TIMING, 1). */
+enum { FFB_OPT_TIMING = 3 };
+int ffb_phase_times(ffb_handle* h, float* out_ms, int32_t n);
+
+/* Per-kernel-class device time (CUDA events recorded around EVERY launch on the launching stream) and
+ * algorithmic FLOPs since profiling was enabled with ffb_set_option(h, FFB_OPT_PROFILE, 1) or last read.
+ * Classes: 0 linear, 1 layernorm, 2 attention (decoder self), 3 attention (encoder / cross), 4 pointer,
+ * 5 other.  Perturbs timing slightly: bench.py uses it on an extra, untimed step.  Synchronises the device. */
+enum { FFB_OPT_PROFILE = 4, FFB_PROFILE_CLASSES = 6 };
+int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops, int64_t* launches);
+
+/* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
+ * They exist so that tests can compare each kernel with the oracle's primitive. */
+
+/* C[M,N] = act((A (+pos[r % pos_mod] on columns n < pos_cols)) W^T + bias) (+ R)          */
+int ffb_op_linear(ffb_handle* h, const float* A, const float* W, const float* bias, const float* R,
+                  const float* pos, int32_t pos_mod, int32_t pos_cols, float* C,
+                  int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
+/* y = LayerNorm(x) over rows of length E (eps 1e-5)                                         */
+int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const float* beta,
+                     float* y, int32_t M, int32_t E, void* stream);
+/* Multi-head attention core (softmax(q k^T / 8) v) for G equal-sized groups:
+ * q [G*nq, ldq], k/v [G*nk, ldk] with head h in columns [64h, 64h+64); out [G*nq, H*64].
+ * kind 0 = warp-per-row kernel (decoder self-attention), 1 = tiled kernel (encoder / cross).  */
+int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k,
+                     const float* v, int32_t ldk, float* out, int32_t G, int32_t nq, int32_t nk,
+                     int32_t H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */
