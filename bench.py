@@ -138,7 +138,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from faceformer_b200.engine import Engine, pack_state_dict
-    from faceformer_b200.lib import FFB_OPT_PROFILE
+    from faceformer_b200.lib import FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE
     from faceformer_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,6 +163,7 @@ def run_ours(args):
         sd, blob = None, torch.empty(nw, dtype=torch.float32, device=dev)
     sharding.broadcast_weights(blob, 0)
     eng.load_blob(blob)
+    eng.set_option(FFB_OPT_TENSOR_CORE, args.tc)
 
     # one batch per rank (weak scaling: fixed work per GPU)
     batch = synth.synth_batch(cfg, mode, args.batch, seed=args.seed + 1000 * rank)
@@ -246,12 +247,16 @@ def run_ours(args):
     if rank == 0:
         peaks = load_peaks()
         tot_ms = sum(v["ms"] for v in prof.values())
-        lin = prof["linear"]
+        use_tc = prof["linear_tc"]["ms"] > prof["linear"]["ms"]
+        lin = prof["linear_tc"] if use_tc else prof["linear"]
         ach = lin["flops"] / (lin["ms"] * 1e-3) / 1e12 if lin["ms"] > 0 else 0.0
-        passes = 1                      # MMA passes of the precision mode: fp32 SIMT today (no tensor pipe yet)
+        # MMA passes of the precision mode: bf16x3 split = 6 bf16 MMAs per fp32-equivalent product;
+        # the fp32 SIMT kernel does not use the tensor pipe at all and is compared with the un-divided peak.
+        passes = 6 if use_tc else 1
         peak = peaks["bf16_sustained"] / passes
-        roofline = {"bound": "tensor", "kernel": "linear_kernel (fp32 SIMT FFMA)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+        kname = "tc::gemm_kernel (tcgen05 bf16x3 split, 6 MMA passes)" if use_tc else "linear_kernel (fp32 SIMT FFMA)"
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "mma_passes": passes,
+                    "frac": ach / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / {passes} ({peaks['source']})",
                     "avg_launch_ms": lin["ms"] / max(1, lin["launches"]), "launches_per_step": lin["launches"],
                     "share_of_step": lin["ms"] / tot_ms if tot_ms else None,
                     "fp32_ffma_peak_tflops": 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
@@ -288,6 +293,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc", type=int, default=1, choices=[0, 1, 2],
+                    help="decode-step linear layers: 0 fp32 SIMT, 1 auto (tcgen05 bf16x3 when >= 2048 rows), 2 force tcgen05")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,6 +12,7 @@
 //   x, x2, qkv, att, h   activations of the current step, rows ordered (sequence, position)
 #include "../../include/ffb200.h"
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -83,6 +84,17 @@ struct ffb_handle {
     // activations
     DevBuf x, x2, qkv, att, hb, xl;
     int last_P = 0;                               // P of the last executed pointer projection (seq2seq 'pointer')
+    // tensor-core path (gemm_tc.cuh): bf16x3 split weights + activation operands, TMA tensor maps
+    bool tc_ok = false;                           // geometry supported (E, FF multiples of 256)
+    int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
+    int num_sms = 148;
+    DevBuf wsplit;
+    struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; };
+    std::vector<DecTcW> tcw;
+    CUtensorMap tc_proj;
+    DevBuf a_x2, a_x2p, a_att, a_h;               // [3][cap_rows][E or FF] bf16
+    long long cap_rows = 0;
+    CUtensorMap m_x2, m_x2p, m_att, m_h;
     // per-kernel-class profiling (FFB_OPT_PROFILE): event pairs around every launch
     int opt_profile = 0;
     std::vector<cudaEvent_t> prof_pool;
@@ -107,7 +119,8 @@ int fail(ffb_handle* h, int code, const char* fmt, ...) {
     return fail((h), FFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 #define FFB_TRY(expr) do { int _r = (expr); if (_r != FFB_OK) return _r; } while (0)
 
-enum { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_ROWS, PC_ATTN_TILED, PC_POINTER, PC_OTHER, PC_COUNT };
+enum { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_ROWS, PC_ATTN_TILED, PC_POINTER, PC_OTHER, PC_LINEAR_TC, PC_COUNT };
+constexpr int TC_MIN_ROWS = 2048;
 
 inline void prof_begin(ffb_handle* h, int cls, double flops, cudaStream_t s) {
     if (!h->opt_profile) return;
@@ -219,12 +232,13 @@ int launch_ln(ffb_handle* h, const float* x, const float* g, const float* b, flo
 }
 
 int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
-                     int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s) {
+                     int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s,
+                     __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || nq <= 0) return FFB_OK;
     AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
     dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
     prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * (double)G * h->H * nq * nk, s);
-    attn_rows_kernel<<<grid, 128, 0, s>>>(Q, ldq, K, V, ldk, O, ldo, g, stop);
+    attn_rows_kernel<<<grid, 128, 0, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -232,16 +246,80 @@ int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, con
 }
 
 int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
-                      const AttnGroups& g, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s) {
+                      const AttnGroups& g, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
+                      __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
     if (G > 65535) return fail(h, FFB_ERR_ARG, "attention: more than 65535 groups");
     dim3 grid((max_q_rows + AT_BQ - 1) / AT_BQ, h->H, G);
     prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * qk_pairs, s);
-    attn_tiled_kernel<<<grid, 128, AT_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, g, stop);
+    attn_tiled_kernel<<<grid, 128, AT_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
     return FFB_OK;
+}
+
+// ---- tensor-core path helpers ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+// bf16 [3][rows][K] operand array -> 3-D map (k, row, split), box {32, box_rows, 1}, 64-byte swizzle
+int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, uint32_t box_rows) {
+    if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {K, rows, 3};
+    const cuuint64_t strides[2] = {K * 2, rows * K * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)tc::BK, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (K=%llu rows=%llu)", (int)r,
+                                       (unsigned long long)K, (unsigned long long)rows);
+    return FFB_OK;
+}
+
+struct TcLin {
+    const CUtensorMap* A0 = nullptr; const CUtensorMap* A1 = nullptr; int n_switch = 1 << 30;
+    const CUtensorMap* W = nullptr; const float* bias = nullptr;
+    float* C = nullptr; int ldc = 0; const float* R = nullptr; int ldr = 0;
+    __nv_bfloat16* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
+    int M = 0, N = 0, K = 0, relu = 0;
+};
+
+int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
+    if (l.M <= 0) return FFB_OK;
+    if (l.N % tc::BN != 0 || l.K % tc::BK != 0) return fail(h, FFB_ERR_ARG, "tc gemm: N %% 256 and K %% 32 must be 0 (N=%d K=%d)", l.N, l.K);
+    tc::Params p{};
+    p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.bias = l.bias; p.C = l.C; p.ldc = l.ldc; p.R = l.R; p.ldr = l.ldr;
+    p.Cs = l.Cs; p.cs_split_stride = l.cs_stride; p.ldcs = l.ldcs; p.relu = l.relu; p.stop = stop;
+    const int tiles = ((l.M + tc::BM - 1) / tc::BM) * (l.N / tc::BN);
+    const int grid = std::min(tiles, h->num_sms);
+    prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
+    tc::gemm_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* out_plain, __nv_bfloat16* out_pos,
+                    long long split_stride, const float* pos, int pos_mod, int M, int E, const int* stop, cudaStream_t s) {
+    if (M <= 0) return FFB_OK;
+    prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
+    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int split_weight(ffb_handle* h, const float* src, __nv_bfloat16* dst, size_t rows, size_t K, CUtensorMap* map, cudaStream_t s) {
+    const long long n4 = (long long)(rows * K / 4);
+    split_array_kernel<<<grid1d(n4), 256, 0, s>>>(src, dst, n4);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return encode_operand_map(h, map, dst, K, rows, tc::BN);
 }
 
 int set_device(ffb_handle* h) {
@@ -378,6 +456,16 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     CU(h, h->att.ensure(rows * E * f4));
     CU(h, h->hb.ensure(std::max(rows, (size_t)Re) * std::max(FF, E) * f4));
     CU(h, h->xl.ensure((size_t)std::max<long long>(h->B, 1) * E * f4));
+    if (h->tc_ok && h->opt_tc) {
+        h->cap_rows = (long long)((rows + 127) / 128 * 128);
+        const size_t cr = (size_t)h->cap_rows;
+        CU(h, h->a_x2.ensure(3 * cr * E * 2)); CU(h, h->a_x2p.ensure(3 * cr * E * 2));
+        CU(h, h->a_att.ensure(3 * cr * E * 2)); CU(h, h->a_h.ensure(3 * cr * FF * 2));
+        FFB_TRY(encode_operand_map(h, &h->m_x2, h->a_x2.p, E, cr, tc::BM));
+        FFB_TRY(encode_operand_map(h, &h->m_x2p, h->a_x2p.p, E, cr, tc::BM));
+        FFB_TRY(encode_operand_map(h, &h->m_att, h->a_att.p, E, cr, tc::BM));
+        FFB_TRY(encode_operand_map(h, &h->m_h, h->a_h.p, FF, cr, tc::BM));
+    }
     return FFB_OK;
 }
 
@@ -446,49 +534,95 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     h->launches++; CU(h, cudaGetLastError());
 
     float* cur = x; int rows = M; int Pq = P;            // rows carried through the rest of the layer
+    const bool tc = h->tc_ok && h->opt_tc && (int)h->tcw.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS);
+    __nv_bfloat16* ax2 = h->a_x2.as<__nv_bfloat16>(); __nv_bfloat16* ax2p = h->a_x2p.as<__nv_bfloat16>();
+    __nv_bfloat16* aatt = h->a_att.as<__nv_bfloat16>(); __nv_bfloat16* ah = h->a_h.as<__nv_bfloat16>();
+    const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the bf16x3 splits
     for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
         const DecLayerW& Lw = w.dec[li];
         const bool last = h->opt_prune && (li == Ld - 1);
-        // self-attention over the whole prefix, NO causal mask (model_para.py:222-223)
-        FFB_TRY(launch_ln(h, x, Lw.n1w, Lw.n1b, x2, M, E, stop, s));
-        { Lin l; l.A = x2; l.lda = E; l.W = Lw.sa.in_w; l.ldw = E; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E;
-          l.pos = w.qpos; l.ldpos = E; l.pos_mod = P; l.pos_cols = 2 * E; l.M = M; l.N = 3 * E; l.K = E;
-          FFB_TRY(launch_linear(h, l, stop, s)); }
-        if (!last) {
-            FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s));
-            { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
-              l.M = M; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+        const float* qpos_cross = last ? w.qpos + (size_t)(P - 1) * E : w.qpos;
+        const int qmod_cross = last ? 1 : P;
+        if (!tc) {
+            // ---- fp32 SIMT path (small M, or geometries the tensor-core kernel does not cover) ----
+            // self-attention over the whole prefix, NO causal mask (model_para.py:222-223)
+            FFB_TRY(launch_ln(h, x, Lw.n1w, Lw.n1b, x2, M, E, stop, s));
+            { Lin l; l.A = x2; l.lda = E; l.W = Lw.sa.in_w; l.ldw = E; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E;
+              l.pos = w.qpos; l.ldpos = E; l.pos_mod = P; l.pos_cols = 2 * E; l.M = M; l.N = 3 * E; l.K = E;
+              FFB_TRY(launch_linear(h, l, stop, s)); }
+            if (!last) {
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s));
+                { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+                  l.M = M; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+            } else {
+                // only pointer[-1] is consumed (model_para.py:176): carry just the last position from here on
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s));
+                copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
+                h->launches++; CU(h, cudaGetLastError());
+                { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
+                  l.M = B; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+                cur = xl; rows = B; Pq = 1;
+            }
+            // cross-attention over the cached K/V of the owning wireframe
+            FFB_TRY(launch_ln(h, cur, Lw.n2w, Lw.n2b, x2, rows, E, stop, s));
+            { Lin l; l.A = x2; l.lda = E; l.W = Lw.ca.in_w; l.ldw = E; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E;
+              l.pos = qpos_cross; l.ldpos = E; l.pos_mod = qmod_cross; l.pos_cols = E; l.M = rows; l.N = E; l.K = E;
+              FFB_TRY(launch_linear(h, l, stop, s)); }
+            { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
+              FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
+                                        att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s)); }
+            { Lin l; l.A = att; l.lda = E; l.W = Lw.ca.out_w; l.ldw = E; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+              l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
+            // feed-forward
+            FFB_TRY(launch_ln(h, cur, Lw.n3w, Lw.n3b, x2, rows, E, stop, s));
+            { Lin l; l.A = x2; l.lda = E; l.W = Lw.l1w; l.ldw = E; l.bias = Lw.l1b; l.C = hb; l.ldc = FF; l.M = rows; l.N = FF; l.K = E; l.relu = 1;
+              FFB_TRY(launch_linear(h, l, stop, s)); }
+            { Lin l; l.A = hb; l.lda = FF; l.W = Lw.l2w; l.ldw = FF; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+              l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, stop, s)); }
         } else {
-            // only pointer[-1] is consumed (model_para.py:176): carry just the last position from here on
-            FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s));
-            copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
-            h->launches++; CU(h, cudaGetLastError());
-            { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
-              l.M = B; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
-            cur = xl; rows = B; Pq = 1;
+            // ---- tensor-core path: every GEMM operand is produced directly as bf16x3 splits ----
+            const ffb_handle::DecTcW& Tw = h->tcw[li];
+            FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
+            { TcLin l; l.A0 = &h->m_x2p; l.A1 = &h->m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
+              l.W = &Tw.sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.M = M; l.N = 3 * E; l.K = E;
+              FFB_TRY(launch_tc(h, l, stop, s)); }
+            if (!last) {
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
+                { TcLin l; l.A0 = &h->m_att; l.W = &Tw.sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+                  l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
+            } else {
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
+                copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
+                h->launches++; CU(h, cudaGetLastError());
+                { TcLin l; l.A0 = &h->m_att; l.W = &Tw.sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
+                  l.M = B; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
+                cur = xl; rows = B; Pq = 1;
+            }
+            FFB_TRY(launch_ln_split(h, cur, Lw.n2w, Lw.n2b, nullptr, ax2p, ssE, qpos_cross, qmod_cross, rows, E, stop, s));
+            { TcLin l; l.A0 = &h->m_x2p; l.W = &Tw.ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+              FFB_TRY(launch_tc(h, l, stop, s)); }
+            { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
+              FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
+                                        att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s, aatt, ssE)); }
+            { TcLin l; l.A0 = &h->m_att; l.W = &Tw.ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+              l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
+            FFB_TRY(launch_ln_split(h, cur, Lw.n3w, Lw.n3b, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
+            { TcLin l; l.A0 = &h->m_x2; l.W = &Tw.l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
+              l.M = rows; l.N = FF; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
+            { TcLin l; l.A0 = &h->m_h; l.W = &Tw.l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+              l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_tc(h, l, stop, s)); }
         }
-        // cross-attention over the cached K/V of the owning wireframe
-        FFB_TRY(launch_ln(h, cur, Lw.n2w, Lw.n2b, x2, rows, E, stop, s));
-        { Lin l; l.A = x2; l.lda = E; l.W = Lw.ca.in_w; l.ldw = E; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E;
-          l.pos = last ? w.qpos + (size_t)(P - 1) * E : w.qpos; l.ldpos = E;
-          l.pos_mod = last ? 1 : P; l.pos_cols = E; l.M = rows; l.N = E; l.K = E;
-          FFB_TRY(launch_linear(h, l, stop, s)); }
-        { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
-          FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
-                                    att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s)); }
-        { Lin l; l.A = att; l.lda = E; l.W = Lw.ca.out_w; l.ldw = E; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
-          l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
-        // feed-forward
-        FFB_TRY(launch_ln(h, cur, Lw.n3w, Lw.n3b, x2, rows, E, stop, s));
-        { Lin l; l.A = x2; l.lda = E; l.W = Lw.l1w; l.ldw = E; l.bias = Lw.l1b; l.C = hb; l.ldc = FF; l.M = rows; l.N = FF; l.K = E; l.relu = 1;
-          FFB_TRY(launch_linear(h, l, stop, s)); }
-        { Lin l; l.A = hb; l.lda = FF; l.W = Lw.l2w; l.ldw = FF; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
-          l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, stop, s)); }
     }
     // decoder.norm (transformer.py:115-116) + project (model_para.py:225) + select_next (model_para.py:173-179)
-    FFB_TRY(launch_ln(h, cur, w.dec_nw, w.dec_nb, x2, rows, E, stop, s));
-    { Lin l; l.A = x2; l.lda = E; l.W = w.proj_w; l.ldw = E; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
-      FFB_TRY(launch_linear(h, l, stop, s)); }
+    if (!tc) {
+        FFB_TRY(launch_ln(h, cur, w.dec_nw, w.dec_nb, x2, rows, E, stop, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = w.proj_w; l.ldw = E; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+          FFB_TRY(launch_linear(h, l, stop, s)); }
+    } else {
+        FFB_TRY(launch_ln_split(h, cur, w.dec_nw, w.dec_nb, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
+        { TcLin l; l.A0 = &h->m_x2; l.W = &h->tc_proj; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+          FFB_TRY(launch_tc(h, l, stop, s)); }
+    }
     PointerArgs pa{};
     pa.mem = h->mem.as<float>(); pa.ptr = att; pa.ptr_stride_rows = Pq; pa.ptr_off = Pq - 1;
     pa.row_off = row_off; pa.v_len = vlen; pa.seq_wf = h->d_seq_wf.as<int>();
@@ -543,8 +677,20 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
         return fail(nullptr, FFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libffb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
     e = cudaFuncSetAttribute(attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(tc::gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(nullptr, FFB_ERR_CUDA, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+        g_encode_tiled = (EncodeTiledFn)fn;
+    }
     ffb_handle* h = new (std::nothrow) ffb_handle();
     if (!h) return fail(nullptr, FFB_ERR_ARG, "out of host memory");
+    h->num_sms = prop.multiProcessorCount;
+    h->tc_ok = (cfg->num_model % tc::BN == 0) && (cfg->num_feedforward % tc::BN == 0);
     h->cfg = *cfg;
     h->E = cfg->num_model; h->H = cfg->num_head; h->FF = cfg->num_feedforward;
     h->L = cfg->num_lines + cfg->num_token; h->T = cfg->seq_len;
@@ -562,7 +708,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl};
+                      &h->att, &h->hb, &h->xl, &h->wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -577,6 +723,10 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_PRUNE_LAST: h->opt_prune = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TIMING: h->opt_timing = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; h->prof_recs.clear(); return FFB_OK;
+        case FFB_OPT_TENSOR_CORE:
+            if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
+            if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
+            h->opt_tc = value; h->encoded = false; return FFB_OK;
         default: return fail(h, FFB_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -603,6 +753,24 @@ int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, vo
         CU(h, cudaMemcpyAsync(cvb + l * E, ca.in_b + 2 * E, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     h->w.ckw = ckw; h->w.cvw = cvw; h->w.ckb = ckb; h->w.cvb = cvb;
+    if (h->tc_ok) {
+        // bf16x3 splits of every decoder-step weight matrix, [3][N][K] each, + their TMA maps
+        const size_t FF = h->FF;
+        const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
+        CU(h, h->wsplit.ensure(3 * (Ld * per_layer + E * E) * sizeof(__nv_bfloat16)));
+        __nv_bfloat16* wp = h->wsplit.as<__nv_bfloat16>();
+        h->tcw.resize(Ld);
+        for (size_t l = 0; l < Ld; ++l) {
+            const DecLayerW& L = h->w.dec[l];
+            FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &h->tcw[l].sa_in, s)); wp += 3 * 3 * E * E;
+            FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &h->tcw[l].sa_out, s)); wp += 3 * E * E;
+            FFB_TRY(split_weight(h, L.ca.in_w, wp, E, E, &h->tcw[l].ca_q, s)); wp += 3 * E * E;      // q rows of the cross in_proj
+            FFB_TRY(split_weight(h, L.ca.out_w, wp, E, E, &h->tcw[l].ca_out, s)); wp += 3 * E * E;
+            FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &h->tcw[l].l1, s)); wp += 3 * FF * E;
+            FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &h->tcw[l].l2, s)); wp += 3 * E * FF;
+        }
+        FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &h->tc_proj, s));
+    }
     CU(h, cudaStreamSynchronize(s));
     h->weights_loaded = true;
     return FFB_OK;
@@ -816,6 +984,53 @@ int ffb_op_linear(ffb_handle* h, const float* A, const float* W, const float* bi
     l.pos = pos; l.ldpos = K; l.pos_mod = pos_mod; l.pos_cols = pos_cols; l.M = M; l.N = N; l.K = K; l.relu = relu;
     if (pos && pos_mod < 1) return fail(h, FFB_ERR_ARG, "op_linear: pos needs pos_mod >= 1");
     return launch_linear(h, l, nullptr, (cudaStream_t)stream);
+}
+
+int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float* bias, const float* R, float* C,
+                     int32_t M, int32_t N, int32_t K, int32_t relu, int32_t via_split, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (M < 1 || N % tc::BN != 0 || K % tc::BK != 0) return fail(h, FFB_ERR_ARG, "op_linear_tc: need M >= 1, N %% 256 == 0, K %% 32 == 0");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t Mp = ((size_t)M + 127) / 128 * 128;
+    DevBuf as, ws, cs;
+    int rc = FFB_OK;
+    do {
+        if (as.ensure(3 * Mp * K * 2) != cudaSuccess || ws.ensure(3 * (size_t)N * K * 2) != cudaSuccess ||
+            cs.ensure(3 * Mp * (size_t)N * 2) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_linear_tc: out of device memory"); break; }
+        if (cudaMemsetAsync(as.p, 0, 3 * Mp * K * 2, s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "memset failed"); break; }
+        // split A row block by row block so that the split stride is Mp*K (the padded capacity)
+        {
+            // A is [M,K] contiguous: splitting it as one array of M*K elements uses stride M*K; use the padded layout instead
+            const long long n4 = (long long)M * K / 4;
+            split_array_kernel<<<grid1d(n4), 256, 0, s>>>(A, as.as<__nv_bfloat16>(), n4);   // stride 4*n4 = M*K
+            h->launches++;
+        }
+        CUtensorMap mA, mW;
+        // A splits are M*K apart (not Mp*K): describe exactly that
+        {
+            if (!g_encode_tiled) { rc = fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable"); break; }
+            const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 3};
+            const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
+            const cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = g_encode_tiled(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, as.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { rc = fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r); break; }
+        }
+        if ((rc = split_weight(h, W, ws.as<__nv_bfloat16>(), N, K, &mW, s)) != FFB_OK) break;
+        TcLin l; l.A0 = &mA; l.W = &mW; l.bias = bias; l.M = M; l.N = N; l.K = K; l.relu = relu;
+        if (via_split) { l.Cs = cs.as<__nv_bfloat16>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
+        else { l.C = C; l.ldc = N; l.R = R; l.ldr = N; }
+        if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;
+        if (via_split) {
+            sum_split_kernel<<<grid1d((long long)M * N), 256, 0, s>>>(cs.as<__nv_bfloat16>(), (long long)Mp * N, C, (long long)M * N);
+            h->launches++;
+        }
+        if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_linear_tc: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    as.release(); ws.release(); cs.release();
+    return rc;
 }
 
 int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const float* beta, float* y, int32_t M, int32_t E, void* stream) {

@@ -1,0 +1,297 @@
+// gemm_tc.cuh -- split-precision tensor-core GEMM for the decode-step linear layers (sm_100a only).
+//
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T )      A, W given as bf16x3 splits:  x = x0 + x1 + x2 (exact to 2^-26)
+//
+// Why split precision: the parity contract (token-exact, logits within 1e-4 of the reference's fp32 CPU path)
+// needs fp32-class products; one bf16 pass is ~6000x over budget.  Six bf16 MMAs
+//   A0W0 + A0W1 + A1W0 + A1W1 + A0W2 + A2W0       (dropped terms <= 2^-26 relative)
+// reproduce the fp32 product to better than fp32 rounding, at 1/6 of the bf16 tensor rate (~230 TFLOP/s of
+// fp32-equivalent work at the measured 1382 TFLOP/s) instead of the ~37 TFLOP/s of the SIMT FFMA kernel.
+//
+// Accumulation: the tensor core's fp32 accumulator is only trusted over ONE k-block (BK = 32): each k-block
+// is accumulated in TMEM with the five small correction products issued first and the dominant A0W0 product
+// last, then drained by the epilogue warps and added into fp32 REGISTER accumulators with round-to-nearest
+// FADDs.  Chains of tensor-core adds at full magnitude are therefore 2 long, independent of K.
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x 256):
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: k, row, split) into a 3-stage smem ring
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, ping-pong per k-block)
+//   warps 4-11  epilogue: tcgen05.ld 32x32b -> register accumulate -> bias / ReLU / residual -> global
+// Pipelines: full/empty mbarriers (TMA <-> MMA) and tfull/tempty mbarriers (MMA <-> epilogue).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ffb {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32;          // BK bf16 = 64-byte rows -> SWIZZLE_64B
+constexpr int NSPLIT = 3;
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = BM * BK * 2;           //  8 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;           // 16 KB
+constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);   // 72 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+
+struct Params {
+    int M, N, K;                 // N % 256 == 0, K % 32 == 0
+    int n_switch;                // n-tiles >= n_switch read mapA1 instead of mapA0
+    const float* bias;           // [N] or null
+    float* C; int ldc;           // fp32 output (or null)
+    const float* R; int ldr;     // residual added to the fp32 output (may alias C) or null
+    __nv_bfloat16* Cs; long long cs_split_stride; int ldcs;   // bf16x3 split output [3][*][ldcs] (or null)
+    int relu;
+    const int* stop;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 64-byte rows, SWIZZLE_64B: 8-row groups are 512 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address      bits [ 0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset bits [16,30) (ignored for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset  bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version  bits [46,48) = 1 on sm_100
+    d |= (uint64_t)4 << 61;                         // layout type         bits [61,64): 4 = SWIZZLE_64B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// x = b0 + b1 + b2 with bf16 parts (round-to-nearest each; residuals are exact in fp32)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& b0, __nv_bfloat16& b1, __nv_bfloat16& b2) {
+    b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b0);
+    b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    b2 = __float2bfloat16_rn(r2);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+            const __grid_constant__ CUtensorMap mapW, const Params p) {
+    if (p.stop != nullptr && *p.stop != 0) return;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_chunks = p.K / BK;
+    const int num_tiles = m_tiles * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int mt = t / n_tiles, nt = t % n_tiles;
+                const CUtensorMap* mapA = (nt >= p.n_switch) ? &mapA1 : &mapA0;
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + NSPLIT * A_TILE_BYTES;
+#pragma unroll
+                    for (int s = 0; s < NSPLIT; ++s) tma_load_3d(sa + s * A_TILE_BYTES, mapA, full_bar(stage), kc * BK, mt * BM, s);
+#pragma unroll
+                    for (int s = 0; s < NSPLIT; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN, s);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
+            int stage = 0; uint32_t phase = 0; uint32_t c = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                    const uint32_t buf = c & 1u;
+                    mbar_wait(tempty_bar(buf), ((c >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                    mbar_wait(full_bar(stage), phase);                     // operands landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + NSPLIT * A_TILE_BYTES;
+                    const uint32_t d = tmem_base + buf * BN;
+                    // correction products first (small), dominant A0.W0 last
+                    const int pa[6] = {0, 1, 1, 0, 2, 0};
+                    const int pb[6] = {1, 0, 1, 2, 0, 0};
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        const uint64_t da = make_smem_desc(sa + pa[q] * A_TILE_BYTES);
+                        const uint64_t db = make_smem_desc(sb + pb[q] * B_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {               // +32 B per K=16 step inside the 64-byte swizzle row
+                            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(empty_bar(stage));                         // smem stage free once these MMAs retire
+                    umma_commit(tfull_bar(buf));                           // accumulator ready for the epilogue
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int e = warp - EPI_WARP0;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int hcol = e >> 2;                      // which 128-column half of the tile
+        float acc[128];
+        uint32_t c = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int mt = t / n_tiles, nt = t % n_tiles;
+            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                const uint32_t buf = c & 1u;
+                mbar_wait(tfull_bar(buf), (c >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + j * 32, v);
+                    tmem_ld_wait();
+                    if (kc == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __uint_as_float(v[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+            }
+            // ---- tile epilogue: bias / ReLU / residual, direct row stores ----
+            const int row = mt * BM + q * 32 + lane;
+            const int col0 = nt * BN + hcol * 128;
+            if (row < p.M) {
+                if (p.C != nullptr) {
+                    float* crow = p.C + (size_t)row * p.ldc + col0;
+                    const float* rrow = p.R ? p.R + (size_t)row * p.ldr + col0 : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 128; i += 4) {
+                        float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (rrow) {
+                            const float4 r = *reinterpret_cast<const float4*>(rrow + i);
+                            v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + i) = v;
+                    }
+                }
+                if (p.Cs != nullptr) {
+                    __nv_bfloat16* s0 = p.Cs + (size_t)row * p.ldcs + col0;
+#pragma unroll
+                    for (int i = 0; i < 128; i += 8) {
+                        __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            float x = acc[i + u];
+                            if (p.bias) x += __ldg(p.bias + col0 + i + u);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            split3(x, o0[u], o1[u], o2[u]);
+                        }
+                        *reinterpret_cast<uint4*>(s0 + i) = *reinterpret_cast<const uint4*>(o0);
+                        *reinterpret_cast<uint4*>(s0 + p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o1);
+                        *reinterpret_cast<uint4*>(s0 + 2 * p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o2);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace tc
+}  // namespace ffb

@@ -17,6 +17,7 @@
 //   pointer_kernel     select_next: bmm + masked_fill + argmax (model_para.py:173-179) + append +
 //                      stop predicate (model_para.py:229-233 / model.py:205-210)
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
@@ -35,6 +36,36 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// bf16x3 split of an fp32 value (operand format of the tensor-core GEMM, gemm_tc.cuh): x = b0 + b1 + b2
+__device__ __forceinline__ void split3_bf16(float x, __nv_bfloat16& b0, __nv_bfloat16& b1, __nv_bfloat16& b2) {
+    b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b0);
+    b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    b2 = __float2bfloat16_rn(r2);
+}
+// write 4 consecutive values as splits: dst points at split 0, splits are `stride` elements apart
+__device__ __forceinline__ void store_split4(__nv_bfloat16* dst, long long stride, float4 v) {
+    __align__(8) __nv_bfloat16 o0[4], o1[4], o2[4];
+    split3_bf16(v.x, o0[0], o1[0], o2[0]); split3_bf16(v.y, o0[1], o1[1], o2[1]);
+    split3_bf16(v.z, o0[2], o1[2], o2[2]); split3_bf16(v.w, o0[3], o1[3], o2[3]);
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o0);
+    *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(o1);
+    *reinterpret_cast<uint2*>(dst + 2 * stride) = *reinterpret_cast<const uint2*>(o2);
+}
+
+// dst[3][rows*cols] bf16 <- src[rows*cols] fp32 (weights, once at load time)
+__global__ void split_array_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        store_split4(dst + 4 * i, 4 * n4, reinterpret_cast<const float4*>(src)[i]);
+}
+
+// dst[i] = s0[i] + s1[i] + s2[i]  (test hook: re-sum a bf16x3 split array)
+__global__ void sum_split_kernel(const __nv_bfloat16* __restrict__ src, long long stride, float* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (__bfloat162float(src[i]) + __bfloat162float(src[i + stride])) + __bfloat162float(src[i + 2 * stride]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,6 +259,59 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// layernorm + operand formatting for the tensor-core GEMM: writes bf16x3 splits of y = LN(x) (out_plain) and/or of
+// y + pos[r % pos_mod] (out_pos) -- with_pos_embed (transformer.py:144-145,205-206) fused into the producer.
+__global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_plain,
+                                                              __nv_bfloat16* __restrict__ out_pos, long long split_stride,
+                                                              const float* __restrict__ pos, int pos_mod,
+                                                              int M, int E, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + (size_t)row * E;
+    float4 v[8];
+    const int nv = E >> 7;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+    const float var = warp_sum(q) / (float)E;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float* prow = (out_pos != nullptr) ? pos + (size_t)(row % pos_mod) * E : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            const int c = i * 128 + lane * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = v[i].x * rstd * g.x + b.x; o.y = v[i].y * rstd * g.y + b.y;
+            o.z = v[i].z * rstd * g.z + b.z; o.w = v[i].w * rstd * g.w + b.w;
+            if (out_plain) store_split4(out_plain + (size_t)row * E + c, split_stride, o);
+            if (out_pos) {
+                const float4 pp = __ldg(reinterpret_cast<const float4*>(prow + c));
+                o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+                store_split4(out_pos + (size_t)row * E + c, split_stride, o);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // attention group geometry
 // ------------------------------------------------------------------------------------------------
@@ -259,7 +343,8 @@ constexpr int AR_BQ = 64, AR_BK = 32, AR_RPW = 16, AR_KS = 68;
 
 __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict__ Q, int ldq,
                                                         const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                        float* __restrict__ O, int ldo, const AttnGroups g, const int* stop) {
+                                                        float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ Os,
+                                                        long long os_stride, const AttnGroups g, const int* stop) {
     FFB_STOP_CHECK(stop);
     __shared__ __align__(16) float Qs[AR_BQ][64];
     __shared__ __align__(16) float Ks[AR_BK][AR_KS];
@@ -339,9 +424,17 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict_
     for (int i = 0; i < AR_RPW; ++i) {
         const int r = w + 4 * i;
         if (r < nqt) {
-            float* orow = O + (size_t)(o0 + qt0 + r) * ldo + head * 64;
-            orow[lane] = oa[i] / l[i];
-            orow[lane + 32] = ob[i] / l[i];
+            const float r0 = oa[i] / l[i], r1 = ob[i] / l[i];
+            const size_t off = (size_t)(o0 + qt0 + r) * ldo + head * 64;
+            if (Os == nullptr) {
+                O[off + lane] = r0;
+                O[off + lane + 32] = r1;
+            } else {                                   // operand of the tensor-core out-projection: bf16x3 splits
+                __nv_bfloat16 a0, a1, a2, b0, b1, b2;
+                split3_bf16(r0, a0, a1, a2); split3_bf16(r1, b0, b1, b2);
+                Os[off + lane] = a0; Os[off + os_stride + lane] = a1; Os[off + 2 * os_stride + lane] = a2;
+                Os[off + lane + 32] = b0; Os[off + os_stride + lane + 32] = b1; Os[off + 2 * os_stride + lane + 32] = b2;
+            }
         }
     }
 }
@@ -355,7 +448,8 @@ constexpr int AT_SMEM_BYTES = (3 * AT_BQ * AT_S + AT_BK * 64) * (int)sizeof(floa
 
 __global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict__ Q, int ldq,
                                                          const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                         float* __restrict__ O, int ldo, const AttnGroups g, const int* stop) {
+                                                         float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ Os,
+                                                         long long os_stride, const AttnGroups g, const int* stop) {
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) float smem[];
     float (*Qs)[AT_S] = reinterpret_cast<float (*)[AT_S]>(smem);
@@ -478,9 +572,16 @@ __global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict
         const int r = ty + 16 * i;
         if (r < nqt) {
             const float inv = 1.0f / l[i];
-            float* orow = O + (size_t)(o0 + qt0 + r) * ldo + head * 64 + tx * 8;
-            *reinterpret_cast<float4*>(orow) = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-            *reinterpret_cast<float4*>(orow + 4) = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
+            const size_t off = (size_t)(o0 + qt0 + r) * ldo + head * 64 + tx * 8;
+            const float4 lo4 = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+            const float4 hi4 = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
+            if (Os == nullptr) {
+                *reinterpret_cast<float4*>(O + off) = lo4;
+                *reinterpret_cast<float4*>(O + off + 4) = hi4;
+            } else {
+                store_split4(Os + off, os_stride, lo4);
+                store_split4(Os + off + 4, os_stride, hi4);
+            }
         }
     }
 }

@@ -252,6 +252,15 @@ class Engine:
                                             _ptr(Cc), M, N, K, int(relu), self._stream()))
         return Cc
 
+    def op_linear_tc(self, A, W, bias=None, R=None, relu=False, via_split=False):
+        import torch
+        M, K = A.shape
+        N = W.shape[0]
+        Cc = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        self._check(self._lib.ffb_op_linear_tc(self._h, _ptr(A), _ptr(W), _ptr(bias), _ptr(R), _ptr(Cc), M, N, K, int(relu),
+                                               int(via_split), self._stream()))
+        return Cc
+
     def op_layernorm(self, x, gamma, beta):
         import torch
         y = torch.empty_like(x)

@@ -152,10 +152,14 @@ int ffb_phase_times(ffb_handle* h, float* out_ms, int32_t n);
 
 /* Per-kernel-class device time (CUDA events recorded around EVERY launch on the launching stream) and
  * algorithmic FLOPs since profiling was enabled with ffb_set_option(h, FFB_OPT_PROFILE, 1) or last read.
- * Classes: 0 linear, 1 layernorm, 2 attention (decoder self), 3 attention (encoder / cross), 4 pointer,
- * 5 other.  Perturbs timing slightly: bench.py uses it on an extra, untimed step.  Synchronises the device. */
-enum { FFB_OPT_PROFILE = 4, FFB_PROFILE_CLASSES = 6 };
+ * Classes: 0 linear (fp32 SIMT), 1 layernorm, 2 attention (decoder self), 3 attention (encoder / cross),
+ * 4 pointer, 5 other, 6 linear (tcgen05 split-precision tensor-core GEMM).  Perturbs timing slightly: bench.py uses it on an extra, untimed step.  Synchronises the device. */
+enum { FFB_OPT_PROFILE = 4, FFB_PROFILE_CLASSES = 7 };
 int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops, int64_t* launches);
+
+/* Tensor-core path selection for the decode-step linear layers (gemm_tc.cuh: bf16x3 split-precision tcgen05 GEMM):
+ * 0 = off (fp32 SIMT everywhere), 1 = auto (default: steps with >= 2048 token rows), 2 = force (every step). */
+enum { FFB_OPT_TENSOR_CORE = 5 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
@@ -173,6 +177,12 @@ int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const fl
 int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k,
                      const float* v, int32_t ldk, float* out, int32_t G, int32_t nq, int32_t nk,
                      int32_t H, void* stream);
+
+/* The tensor-core GEMM alone on fp32 caller data (device pointers): A [M,K] and W [N,K] are split to bf16x3 inside,
+ * C[M,N] = act(A W^T + bias) (+ R).  via_split != 0 routes the result through the kernel's bf16x3 output format
+ * (used for the FFN hidden activations) and re-sums it.  N %% 256 == 0, K %% 32 == 0. */
+int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float* bias, const float* R, float* C,
+                     int32_t M, int32_t N, int32_t K, int32_t relu, int32_t via_split, void* stream);
 
 #ifdef __cplusplus
 }

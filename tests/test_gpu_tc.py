@@ -1,0 +1,130 @@
+"""The split-precision tensor-core path (tcgen05 bf16x3 GEMM, gemm_tc.cuh) through the C ABI:
+op-level accuracy against an fp64 product, and end-to-end parity with the reference's outputs when
+EVERY decode step is forced through it."""
+import numpy as np
+import pytest
+import torch
+
+from faceformer_b200.config import MODE_PARALLEL, OURS
+from faceformer_b200.engine import Engine
+from faceformer_b200.lib import FFB_OPT_DEDUP_PAD, FFB_OPT_TENSOR_CORE
+from util import LOGIT_TOL, load_case, logits_close, valid_rows_mask
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(OURS, MODE_PARALLEL, 0)
+    yield e
+    e.close()
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 32), (128, 256, 512), (100, 512, 512), (129, 1536, 512), (1000, 512, 1024),
+                                   (4097, 1024, 512), (20000, 512, 512)])
+@pytest.mark.parametrize("variant", ["plain", "bias_relu", "bias_res", "via_split"])
+def test_tc_linear_is_fp32_class(eng, M, N, K, variant):
+    rng = np.random.default_rng(M + N + K)
+    A = (rng.normal(size=(M, K)) * rng.choice([0.01, 1.0, 30.0], size=(M, 1))).astype(np.float32)
+    W = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    R = rng.normal(size=(M, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    if variant == "plain":
+        got = eng.op_linear_tc(_t(A), _t(W))
+    elif variant == "bias_relu":
+        got = eng.op_linear_tc(_t(A), _t(W), bias=_t(b), relu=True)
+        ref = np.maximum(ref + b, 0)
+    elif variant == "bias_res":
+        got = eng.op_linear_tc(_t(A), _t(W), bias=_t(b), R=_t(R))
+        ref = R + (ref + b)
+    else:
+        got = eng.op_linear_tc(_t(A), _t(W), bias=_t(b), relu=True, via_split=True)
+        ref = np.maximum(ref + b, 0)
+    got = got.cpu().numpy().astype(np.float64)
+    simt = eng.op_linear(_t(A), _t(W)).cpu().numpy().astype(np.float64)
+    plain_ref = A.astype(np.float64) @ W.astype(np.float64).T
+    # error of each path relative to the row scale of the exact product
+    scale = np.abs(plain_ref).max(axis=1, keepdims=True) + 1e-30
+    scale_out = np.maximum(scale, np.abs(ref).max(axis=1, keepdims=True))
+    err_tc = np.max(np.abs(got - ref) / scale_out)
+    err_simt = np.max(np.abs(simt - plain_ref) / scale)
+    assert err_tc <= 2e-6, (err_tc, err_simt)                   # fp32-class (one bf16 pass would be ~4e-3)
+    assert err_tc <= 4 * err_simt + 2e-7, (err_tc, err_simt)    # no worse than the fp32 FFMA kernel's own noise
+
+
+def test_tc_accumulation_has_no_truncation_bias(eng):
+    """All-positive operands: a round-toward-zero accumulator would show a systematic negative error."""
+    rng = np.random.default_rng(5)
+    M, N, K = 512, 256, 1024
+    A = rng.uniform(0.5, 1.5, size=(M, K)).astype(np.float32)
+    W = rng.uniform(0.5, 1.5, size=(N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    got = eng.op_linear_tc(_t(A), _t(W)).cpu().numpy().astype(np.float64)
+    rel = (got - ref) / ref
+    assert np.abs(rel).max() <= 3e-7
+    assert abs(rel.mean()) <= 3e-8, rel.mean()
+
+
+@pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64"])
+def test_golden_full_decode_forced_tensor_core(name):
+    g = load_case(name)
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_TENSOR_CORE, 2)
+    b = g["batch"]
+    coords = torch.from_numpy(b["input"]).cuda().flatten(2)
+    pred, steps = e.forward_eval(coords, torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda())
+    assert steps == g["steps"]
+    assert np.array_equal(pred.cpu().numpy(), g["predict"])
+    ok, d = logits_close(e.get_last_logits().cpu().numpy(), g["last_logits"])
+    assert ok, f"last-step logits differ by {d}"
+    prof_launches = e.kernel_launches()
+    assert prof_launches > 0
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64"])
+def test_golden_forced_prefix_logits_forced_tensor_core(name):
+    g = load_case(name)
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_TENSOR_CORE, 2)
+    e.set_option(FFB_OPT_DEDUP_PAD, 0)
+    b = g["batch"]
+    e.encode(b["input"].reshape(b["input"].shape[0], b["input"].shape[1], -1), b["input_mask"], b["num_input"])
+    lg = e.forced_prefix_logits(g["prefix"])
+    ok, d = logits_close(lg, g["prefix_logits"])
+    assert ok, f"forced-prefix logits differ by {d}"
+    e.close()
+
+
+def test_tensor_core_and_simt_paths_agree_on_a_real_batch():
+    """8 wireframes at ours.yml size (M up to ~30k rows, auto mode picks the tensor-core path):
+    identical tokens and logits within 1e-4 of the all-SIMT run."""
+    from faceformer_b200 import synth
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 8, seed=3, lo=40, hi=120)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    out = []
+    for mode in (0, 1):
+        e = Engine(cfg, MODE_PARALLEL, 0)
+        e.load_state_dict(sd)
+        e.set_option(FFB_OPT_TENSOR_CORE, mode)
+        from faceformer_b200.lib import FFB_OPT_PROFILE
+        e.set_option(FFB_OPT_PROFILE, 1)
+        pred, steps = e.forward_eval(coords, mask, ni)
+        prof = e.profile_read()
+        out.append((pred.cpu().numpy(), steps, e.get_last_logits().cpu().numpy(), prof))
+        e.close()
+    assert out[1][3]["linear_tc"]["launches"] > 0 and out[0][3]["linear_tc"]["launches"] == 0
+    assert out[0][1] == out[1][1]
+    assert np.array_equal(out[0][0], out[1][0]), f"{(out[0][0] != out[1][0]).sum()} token mismatches"
+    ok, d = logits_close(out[1][2], out[0][2])
+    assert ok, d
