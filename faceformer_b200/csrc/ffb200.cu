@@ -13,6 +13,7 @@
 #include "../../include/ffb200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "attn_mma.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -87,6 +88,7 @@ struct ffb_handle {
     // tensor-core path (gemm_tc.cuh): bf16x3 split weights + activation operands, TMA tensor maps
     bool tc_ok = false;                           // geometry supported (E, FF multiples of 256)
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
+    int opt_attn_mma = 1;                         // attention core: 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     int num_sms = 148;
     DevBuf wsplit;
     struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; };
@@ -231,14 +233,35 @@ int launch_ln(ffb_handle* h, const float* x, const float* g, const float* b, flo
     return FFB_OK;
 }
 
+int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
+                    const AttnGroups& g, int G, int max_q_rows, double qk_pairs, int prof_class, const int* stop, cudaStream_t s,
+                    __nv_bfloat16* Os, long long os_stride);
+
 int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                      int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s,
                      __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || nq <= 0) return FFB_OK;
     AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
+    if (h->opt_attn_mma)
+        return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, nq, (double)G * nq * nk, PC_ATTN_ROWS, stop, s, Os, os_stride);
     dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
     prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * (double)G * h->H * nq * nk, s);
     attn_rows_kernel<<<grid, 128, 0, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
+                    const AttnGroups& g, int G, int max_q_rows, double qk_pairs, int prof_class, const int* stop, cudaStream_t s,
+                    __nv_bfloat16* Os, long long os_stride) {
+    if (G <= 0 || max_q_rows <= 0) return FFB_OK;
+    const int qtiles = (max_q_rows + AM_BQ - 1) / AM_BQ;
+    if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
+    dim3 grid(G, h->H, qtiles);
+    prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
+    attn_mma_kernel<<<grid, 128, AM_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -249,6 +272,8 @@ int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, co
                       const AttnGroups& g, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
                       __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
+    if (h->opt_attn_mma)
+        return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, max_q_rows, qk_pairs, PC_ATTN_TILED, stop, s, Os, os_stride);
     if (G > 65535) return fail(h, FFB_ERR_ARG, "attention: more than 65535 groups");
     dim3 grid((max_q_rows + AT_BQ - 1) / AT_BQ, h->H, G);
     prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * qk_pairs, s);
@@ -677,6 +702,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
         return fail(nullptr, FFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libffb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
     e = cudaFuncSetAttribute(attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(tc::gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
     if (!g_encode_tiled) {
@@ -723,6 +750,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_PRUNE_LAST: h->opt_prune = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TIMING: h->opt_timing = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; h->prof_recs.clear(); return FFB_OK;
+        case FFB_OPT_ATTN_MMA: h->opt_attn_mma = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -1046,9 +1074,16 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
     if (H != h->H) return fail(h, FFB_ERR_ARG, "op_attention: H must equal the handle's num_head");
     FFB_TRY(set_device(h));
     cudaStream_t s = (cudaStream_t)stream;
-    if (kind == 0) return launch_attn_rows(h, q, ldq, k, v, ldk, out, H * 64, G, nq, nk, nq, 0, nk, nq, nullptr, s);
-    AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
-    return launch_attn_tiled(h, q, ldq, k, v, ldk, out, H * 64, g, G, nq, (double)G * nq * nk, nullptr, s);
+    const int saved = h->opt_attn_mma;
+    h->opt_attn_mma = (kind == 2) ? 1 : 0;
+    int rc;
+    if (kind == 0) rc = launch_attn_rows(h, q, ldq, k, v, ldk, out, H * 64, G, nq, nk, nq, 0, nk, nq, nullptr, s);
+    else {
+        AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
+        rc = launch_attn_tiled(h, q, ldq, k, v, ldk, out, H * 64, g, G, nq, (double)G * nq * nk, nullptr, s);
+    }
+    h->opt_attn_mma = saved;
+    return rc;
 }
 
 }  // extern "C"

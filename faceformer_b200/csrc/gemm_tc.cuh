@@ -8,10 +8,12 @@
 // reproduce the fp32 product to better than fp32 rounding, at 1/6 of the bf16 tensor rate (~230 TFLOP/s of
 // fp32-equivalent work at the measured 1382 TFLOP/s) instead of the ~37 TFLOP/s of the SIMT FFMA kernel.
 //
-// Accumulation: the tensor core's fp32 accumulator is only trusted over ONE k-block (BK = 32): each k-block
-// is accumulated in TMEM with the five small correction products issued first and the dominant A0W0 product
-// last, then drained by the epilogue warps and added into fp32 REGISTER accumulators with round-to-nearest
-// FADDs.  Chains of tensor-core adds at full magnitude are therefore 2 long, independent of K.
+// Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: a small negative
+// bias on all-positive data), so chains are kept short: DRAIN_KB k-blocks (BK = 32 each) are accumulated in
+// TMEM -- per k-block the five small correction products first, the dominant A0W0 product last -- then the
+// epilogue warps drain the accumulator and add it into fp32 REGISTER accumulators with round-to-nearest
+// FADDs.  DRAIN_KB = 2 balances the TMEM read port (a 128x256 fp32 drain costs ~2k cycles, measured) against
+// the MMA time of the k-blocks it covers; chains stay 24 MMAs long independent of K.
 //
 // Structure (one CTA per SM, persistent over output tiles of 128 x 256):
 //   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: k, row, split) into a 3-stage smem ring
@@ -31,6 +33,7 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 32;          // BK bf16 = 64-byte rows -> SWIZZLE_64B
 constexpr int NSPLIT = 3;
 constexpr int STAGES = 3;
+constexpr int DRAIN_KB = 2;                          // k-blocks accumulated in TMEM per drain
 constexpr int A_TILE_BYTES = BM * BK * 2;           //  8 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;           // 16 KB
 constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);   // 72 KB
@@ -184,11 +187,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             }
         } else if (warp == 1 && lane == 0) {
             // ===== MMA issuer =====
-            int stage = 0; uint32_t phase = 0; uint32_t c = 0;
+            int stage = 0; uint32_t phase = 0; uint32_t c = 0;            // c counts drains (accumulator uses)
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                for (int kc = 0; kc < k_chunks; ++kc) {
                     const uint32_t buf = c & 1u;
-                    mbar_wait(tempty_bar(buf), ((c >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                    const bool first_in_drain = (kc % DRAIN_KB) == 0;
+                    const bool last_in_drain = ((kc % DRAIN_KB) == DRAIN_KB - 1) || (kc == k_chunks - 1);
+                    if (first_in_drain) mbar_wait(tempty_bar(buf), ((c >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
                     mbar_wait(full_bar(stage), phase);                     // operands landed
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -197,7 +202,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     // correction products first (small), dominant A0.W0 last
                     const int pa[6] = {0, 1, 1, 0, 2, 0};
                     const int pb[6] = {1, 0, 1, 2, 0, 0};
-                    uint32_t acc = 0;
+                    uint32_t acc = first_in_drain ? 0u : 1u;
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
                         const uint64_t da = make_smem_desc(sa + pa[q] * A_TILE_BYTES);
@@ -209,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         }
                     }
                     umma_commit(empty_bar(stage));                         // smem stage free once these MMAs retire
-                    umma_commit(tfull_bar(buf));                           // accumulator ready for the epilogue
+                    if (last_in_drain) { umma_commit(tfull_bar(buf)); ++c; }   // accumulator ready for the epilogue
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -224,22 +229,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         uint32_t c = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int mt = t / n_tiles, nt = t % n_tiles;
-            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+            const int n_drains = (k_chunks + DRAIN_KB - 1) / DRAIN_KB;
+            for (int dr = 0; dr < n_drains; ++dr, ++c) {
                 const uint32_t buf = c & 1u;
                 mbar_wait(tfull_bar(buf), (c >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * 128;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + j * 32, v);
+                for (int j = 0; j < 2; ++j) {                  // two 32-column loads in flight per wait
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + j * 64, v0);
+                    tmem_ld32(taddr + j * 64 + 32, v1);
                     tmem_ld_wait();
-                    if (kc == 0) {
+                    if (dr == 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; ++i) { acc[j * 64 + i] = __uint_as_float(v0[i]); acc[j * 64 + 32 + i] = __uint_as_float(v1[i]); }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; ++i) { acc[j * 64 + i] += __uint_as_float(v0[i]); acc[j * 64 + 32 + i] += __uint_as_float(v1[i]); }
                     }
                 }
                 tc_fence_before();

@@ -66,8 +66,9 @@ def test_tc_accumulation_has_no_truncation_bias(eng):
     ref = A.astype(np.float64) @ W.astype(np.float64).T
     got = eng.op_linear_tc(_t(A), _t(W)).cpu().numpy().astype(np.float64)
     rel = (got - ref) / ref
-    assert np.abs(rel).max() <= 3e-7
-    assert abs(rel.mean()) <= 3e-8, rel.mean()
+    print("tc accumulation: max |rel| %.3e, mean rel %.3e" % (np.abs(rel).max(), rel.mean()))
+    assert np.abs(rel).max() <= 6e-7                 # a few fp32 ulps: 32 round-to-nearest register adds of k-block partials
+    assert abs(rel.mean()) <= 1e-7, rel.mean()       # a truncating 1024-long chain would sit near -3e-5
 
 
 @pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64"])
