@@ -1061,6 +1061,44 @@ int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float*
     return rc;
 }
 
+int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t flags, int32_t iters, float* ms_out, void* stream) {
+    if (!h || !ms_out || iters < 1) return FFB_ERR_ARG;
+    if (M < 1 || N % tc::BN != 0 || K % tc::BK != 0) return fail(h, FFB_ERR_ARG, "bench_linear_tc: need N %% 256 == 0, K %% 32 == 0");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t Mp = ((size_t)M + 127) / 128 * 128;
+    DevBuf as, ws, cs, cf, bias;
+    int rc = FFB_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if (as.ensure(3 * Mp * K * 2) != cudaSuccess || ws.ensure(3 * (size_t)N * K * 2) != cudaSuccess || bias.ensure((size_t)N * 4) != cudaSuccess ||
+            cs.ensure(3 * Mp * (size_t)N * 2) != cudaSuccess || cf.ensure(Mp * (size_t)N * 4) != cudaSuccess) {
+            rc = fail(h, FFB_ERR_CUDA, "bench_linear_tc: out of device memory"); break; }
+        cudaMemsetAsync(as.p, 0, 3 * Mp * K * 2, s); cudaMemsetAsync(ws.p, 0, 3 * (size_t)N * K * 2, s);
+        cudaMemsetAsync(cf.p, 0, Mp * (size_t)N * 4, s); cudaMemsetAsync(bias.p, 0, (size_t)N * 4, s);
+        CUtensorMap mA, mW;
+        if ((rc = encode_operand_map(h, &mA, as.p, K, Mp, tc::BM)) != FFB_OK) break;
+        if ((rc = encode_operand_map(h, &mW, ws.p, K, N, tc::BN)) != FFB_OK) break;
+        TcLin l; l.A0 = &mA; l.W = &mW; l.M = M; l.N = N; l.K = K;
+        if (flags & 1) l.bias = bias.as<float>();
+        if (flags & 4) l.relu = 1;
+        if (flags & 8) { l.Cs = cs.as<__nv_bfloat16>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
+        else if (!(flags & 16)) { l.C = cf.as<float>(); l.ldc = N; if (flags & 2) { l.R = cf.as<float>(); l.ldr = N; } }
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;          // warm-up
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters && rc == FFB_OK; ++i) rc = launch_tc(h, l, nullptr, s);
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "bench_linear_tc: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / iters;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    as.release(); ws.release(); cs.release(); cf.release(); bias.release();
+    return rc;
+}
+
 int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const float* beta, float* y, int32_t M, int32_t E, void* stream) {
     if (!h) return FFB_ERR_ARG;
     if (E % 128 != 0 || E > 1024) return fail(h, FFB_ERR_ARG, "op_layernorm: E must be a multiple of 128, <= 1024");

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libffb200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ffb200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "gemm_tc.cuh"),
-           os.path.join(ROOT, "include", "ffb200.h")]
+HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh", "attn_mma.cuh")] + \
+          [os.path.join(ROOT, "include", "ffb200.h")]
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
@@ -57,6 +57,7 @@ SIGNATURES = {
     "ffb_profile_read": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ffb_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ffb_op_linear_tc": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "ffb_bench_linear_tc": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
     "ffb_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "ffb_op_attention": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }

@@ -186,6 +186,10 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
 int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float* bias, const float* R, float* C,
                      int32_t M, int32_t N, int32_t K, int32_t relu, int32_t via_split, void* stream);
 
+/* Tuning aid: average device time (ms, CUDA events) of `iters` launches of the tensor-core GEMM on zero-filled
+ * operands of the given shape.  flags: 1 bias, 2 residual, 4 relu, 8 bf16x3 split output, 16 no output stores. */
+int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t flags, int32_t iters, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
