@@ -1,0 +1,113 @@
+"""Sharded decode == single-process decode (two ranks sharing cuda:0, gloo for the gather), and the
+size-independent properties the domain offers at realistic sizes (SURVEY.md section 4 level iv)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from faceformer_b200 import sharding, synth
+from faceformer_b200.config import MODE_PARALLEL, OURS
+from util import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_batch(eng, data, batch):
+    it = batch.items
+    coords = torch.from_numpy(data["input"][it]).cuda().flatten(2)
+    pred, _ = eng.forward_eval(coords, torch.from_numpy(data["input_mask"][it]).cuda(), torch.from_numpy(data["num_input"][it]).cuda())
+    return pred.cpu().numpy()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from faceformer_b200.engine import Engine, pack_state_dict
+        g = load_case("tiny_parallel_trained")
+        cfg = g["cfg"]
+        eng = Engine(cfg, MODE_PARALLEL, 0)
+        blob = torch.from_numpy(pack_state_dict(g["sd"], cfg, MODE_PARALLEL)) if rank == 0 else torch.zeros(eng.weight_count())
+        sharding.broadcast_weights(blob, 0)
+        eng.load_blob(blob.numpy())
+        data = synth.polygon_batch(cfg, 22, seed=7)
+        batches = sharding.plan_batches(data["num_input"], 4, cfg.max_face_length)
+        res, assignment = sharding.run_sharded(lambda b: _decode_batch(eng, data, b), batches, cfg.num_lines, cfg.max_face_length)
+        q.put((rank, {k: v.tolist() for k, v in res.items()}, assignment))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_decode_matches_single_process():
+    from faceformer_b200.engine import Engine
+    g = load_case("tiny_parallel_trained")
+    cfg = g["cfg"]
+    eng = Engine(cfg, MODE_PARALLEL, 0)
+    eng.load_state_dict(g["sd"])
+    data = synth.polygon_batch(cfg, 22, seed=7)
+    batches = sharding.plan_batches(data["num_input"], 4, cfg.max_face_length)
+    want = {b.index: _decode_batch(eng, data, b) for b in batches}
+    eng.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, assignment in got:
+        assert sorted(res) == sorted(want)
+        for k, v in res.items():
+            assert np.array_equal(np.asarray(v), want[k]), f"batch {k} differs on rank {rank}"
+
+
+def test_full_size_properties():
+    """configs/ours.yml geometry, 6 wireframes (too slow for the oracle): properties that must hold at any size."""
+    from faceformer_b200.engine import Engine
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 6, seed=11, lo=30, hi=90)
+    eng = Engine(cfg, MODE_PARALLEL, 0)
+    eng.load_state_dict(sd)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    p1, s1 = eng.forward_eval(coords, mask, ni)
+    p1 = p1.cpu().numpy()
+    lg1 = eng.get_last_logits().cpu().numpy()
+    p2, s2 = eng.forward_eval(coords, mask, ni)                 # determinism: bitwise identical re-run
+    assert s1 == s2 and np.array_equal(p1, p2.cpu().numpy())
+    assert np.array_equal(lg1, eng.get_last_logits().cpu().numpy())
+    F = int(batch["num_input"].max())
+    assert p1.shape == (6, F, cfg.max_face_length) and p1.dtype == np.int64
+    nvalid = batch["num_input"] + cfg.num_token
+    for i, n in enumerate(batch["num_input"]):
+        assert np.array_equal(p1[i, :n, 0], np.arange(n)) and np.all(p1[i, n:, 0] == 3)     # anchors (model_para.py:201-205)
+        assert np.all(p1[i, n:] == p1[i, n:n + 1])                                          # padded-anchor sequences identical
+        assert p1[i, :, :s1 + 1].max() < nvalid[i]                                          # never points at a masked row
+    assert np.all(p1[:, :, s1 + 1:] == 0)                                                   # zero padding after the executed steps
+    # batch-composition invariance of the per-sequence function: a wireframe decoded alone gives the same tokens
+    # for its real anchors as inside the batch (F and the stop step differ; the common prefix of steps must agree)
+    # (same kernel path for both runs: the auto mode would pick the tensor-core GEMM only for the larger batch)
+    from faceformer_b200.lib import FFB_OPT_TENSOR_CORE
+    for tc_mode in (0, 2):
+        eng.set_option(FFB_OPT_TENSOR_CORE, tc_mode)
+        pb, sb = eng.forward_eval(coords, mask, ni)
+        pb = pb.cpu().numpy()
+        assert np.array_equal(pb, p1) and sb == s1                                          # all three paths agree on tokens
+        i = int(np.argmin(batch["num_input"]))
+        pa, sa = eng.forward_eval(coords[i:i + 1], mask[i:i + 1], ni[i:i + 1])
+        pa = pa.cpu().numpy()
+        n, s = int(batch["num_input"][i]), min(sb, sa)
+        assert np.array_equal(pa[0, :n, :s + 1], pb[i, :n, :s + 1])
+    eng.close()
