@@ -138,7 +138,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from faceformer_b200.engine import Engine, pack_state_dict
-    from faceformer_b200.lib import FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE
+    from faceformer_b200.lib import FFB_OPT_PROFILE, FFB_OPT_TC_FORMAT, FFB_OPT_TENSOR_CORE
     from faceformer_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,6 +163,7 @@ def run_ours(args):
         sd, blob = None, torch.empty(nw, dtype=torch.float32, device=dev)
     sharding.broadcast_weights(blob, 0)
     eng.load_blob(blob)
+    eng.set_option(FFB_OPT_TC_FORMAT, args.tc_format)
     eng.set_option(FFB_OPT_TENSOR_CORE, args.tc)
 
     # one batch per rank (weak scaling: fixed work per GPU)
@@ -250,11 +251,13 @@ def run_ours(args):
         use_tc = prof["linear_tc"]["ms"] > prof["linear"]["ms"]
         lin = prof["linear_tc"] if use_tc else prof["linear"]
         ach = lin["flops"] / (lin["ms"] * 1e-3) / 1e12 if lin["ms"] > 0 else 0.0
-        # MMA passes of the precision mode: bf16x3 split = 6 bf16 MMAs per fp32-equivalent product;
+        # MMA passes of the precision mode: fp16x2 split = 3 fp16 MMAs per fp32-equivalent product, bf16x3 = 6;
         # the fp32 SIMT kernel does not use the tensor pipe at all and is compared with the un-divided peak.
-        passes = 6 if use_tc else 1
+        fmt = 3 if eng.fp16_fallbacks() else args.tc_format
+        passes = (3 if fmt == 2 else 6) if use_tc else 1
         peak = peaks["bf16_sustained"] / passes
-        kname = "tc::gemm_kernel (tcgen05 bf16x3 split, 6 MMA passes)" if use_tc else "linear_kernel (fp32 SIMT FFMA)"
+        kname = (f"tc::gemm_kernel<{fmt}> (tcgen05 {'fp16x2' if fmt == 2 else 'bf16x3'} split, {passes} MMA passes)" if use_tc
+                 else "linear_kernel (fp32 SIMT FFMA)")
         roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "mma_passes": passes,
                     "frac": ach / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / {passes} ({peaks['source']})",
                     "avg_launch_ms": lin["ms"] / max(1, lin["launches"]), "launches_per_step": lin["launches"],
@@ -293,6 +296,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-format", type=int, default=2, choices=[2, 3], help="tensor-core operand format: 2 fp16x2, 3 bf16x3")
     ap.add_argument("--tc", type=int, default=1, choices=[0, 1, 2],
                     help="decode-step linear layers: 0 fp32 SIMT, 1 auto (tcgen05 bf16x3 when >= 2048 rows), 2 force tcgen05")
     args = ap.parse_args()

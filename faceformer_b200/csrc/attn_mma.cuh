@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t tf32_lo(float x) {
 
 __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restrict__ Q, int ldq,
                                                           const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                          float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ Os,
+                                                          float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
                                                           long long os_stride, const AttnGroups g, const int* stop) {
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) float smem[];
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
                 *reinterpret_cast<float4*>(O + off) = c0;
                 *reinterpret_cast<float4*>(O + off + 4) = c1;
             } else {
-                store_split4(Os + off, os_stride, c0);
-                store_split4(Os + off + 4, os_stride, c1);
+                store_split4(Os + off, os_stride, c0, g.split_fmt, g.overflow);
+                store_split4(Os + off + 4, os_stride, c1, g.split_fmt, g.overflow);
             }
         }
     }

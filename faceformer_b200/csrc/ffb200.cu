@@ -90,13 +90,19 @@ struct ffb_handle {
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
     int opt_attn_mma = 1;                         // attention core: 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     int num_sms = 148;
-    DevBuf wsplit;
-    struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; };
-    std::vector<DecTcW> tcw;
-    CUtensorMap tc_proj;
-    DevBuf a_x2, a_x2p, a_att, a_h;               // [3][cap_rows][E or FF] bf16
+    int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
+    int fp16_fallbacks = 0;                       // decodes re-run in bf16x3 because an activation exceeded the fp16 range
+    struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; float s_sa_in, s_sa_out, s_ca_q, s_ca_out, s_l1, s_l2; };
+    struct TcSet {                                // everything that depends on the operand format
+        bool ready = false;
+        DevBuf wsplit;                            // [fmt][N][K] 16-bit splits of every decode-step weight matrix
+        std::vector<DecTcW> layers;
+        CUtensorMap proj; float s_proj = 1.f;
+        CUtensorMap m_x2, m_x2p, m_att, m_h;      // activation-operand maps (re-encoded per batch)
+    };
+    TcSet tcs[2];                                 // [fmt - 2]
+    DevBuf a_x2, a_x2p, a_att, a_h;               // [fmt][cap_rows][E or FF] 16-bit (sized for 3 splits)
     long long cap_rows = 0;
-    CUtensorMap m_x2, m_x2p, m_att, m_h;
     // per-kernel-class profiling (FFB_OPT_PROFILE): event pairs around every launch
     int opt_profile = 0;
     std::vector<cudaEvent_t> prof_pool;
@@ -235,13 +241,14 @@ int launch_ln(ffb_handle* h, const float* x, const float* g, const float* b, flo
 
 int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                     const AttnGroups& g, int G, int max_q_rows, double qk_pairs, int prof_class, const int* stop, cudaStream_t s,
-                    __nv_bfloat16* Os, long long os_stride);
+                    uint16_t* Os, long long os_stride);
 
 int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                      int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s,
-                     __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
+                     uint16_t* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || nq <= 0) return FFB_OK;
     AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
+    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
     if (h->opt_attn_mma)
         return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, nq, (double)G * nq * nk, PC_ATTN_ROWS, stop, s, Os, os_stride);
     dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
@@ -255,7 +262,7 @@ int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, con
 
 int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                     const AttnGroups& g, int G, int max_q_rows, double qk_pairs, int prof_class, const int* stop, cudaStream_t s,
-                    __nv_bfloat16* Os, long long os_stride) {
+                    uint16_t* Os, long long os_stride) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
     const int qtiles = (max_q_rows + AM_BQ - 1) / AM_BQ;
     if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
@@ -269,9 +276,11 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
 }
 
 int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
-                      const AttnGroups& g, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
-                      __nv_bfloat16* Os = nullptr, long long os_stride = 0) {
+                      const AttnGroups& g_in, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
+                      uint16_t* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
+    AttnGroups g = g_in;
+    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
     if (h->opt_attn_mma)
         return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, max_q_rows, qk_pairs, PC_ATTN_TILED, stop, s, Os, os_stride);
     if (G > 65535) return fail(h, FFB_ERR_ARG, "attention: more than 65535 groups");
@@ -290,15 +299,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
 
-// bf16 [3][rows][K] operand array -> 3-D map (k, row, split), box {32, box_rows, 1}, 64-byte swizzle
-int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, uint32_t box_rows) {
+// 16-bit [fmt][rows][K] operand array -> 3-D map (k, row, split), box {32, box_rows, 1}, 64-byte swizzle
+int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, uint32_t box_rows, int fmt) {
     if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
-    const cuuint64_t dims[3] = {K, rows, 3};
+    const cuuint64_t dims[3] = {K, rows, (cuuint64_t)fmt};
     const cuuint64_t strides[2] = {K * 2, rows * K * 2};
     const cuuint32_t box[3] = {(cuuint32_t)tc::BK, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode_tiled(m, fmt == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (K=%llu rows=%llu)", (int)r,
                                        (unsigned long long)K, (unsigned long long)rows);
     return FFB_OK;
@@ -306,9 +316,9 @@ int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, ui
 
 struct TcLin {
     const CUtensorMap* A0 = nullptr; const CUtensorMap* A1 = nullptr; int n_switch = 1 << 30;
-    const CUtensorMap* W = nullptr; const float* bias = nullptr;
+    const CUtensorMap* W = nullptr; float w_scale = 1.f; const float* bias = nullptr;
     float* C = nullptr; int ldc = 0; const float* R = nullptr; int ldr = 0;
-    __nv_bfloat16* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
+    uint16_t* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
     int M = 0, N = 0, K = 0, relu = 0;
 };
 
@@ -316,35 +326,95 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     if (l.M <= 0) return FFB_OK;
     if (l.N % tc::BN != 0 || l.K % tc::BK != 0) return fail(h, FFB_ERR_ARG, "tc gemm: N %% 256 and K %% 32 must be 0 (N=%d K=%d)", l.N, l.K);
     tc::Params p{};
-    p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.bias = l.bias; p.C = l.C; p.ldc = l.ldc; p.R = l.R; p.ldr = l.ldr;
-    p.Cs = l.Cs; p.cs_split_stride = l.cs_stride; p.ldcs = l.ldcs; p.relu = l.relu; p.stop = stop;
+    p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.out_scale = 1.0f / l.w_scale; p.bias = l.bias;
+    p.C = l.C; p.ldc = l.ldc; p.R = l.R; p.ldr = l.ldr;
+    p.Cs = l.Cs; p.cs_split_stride = l.cs_stride; p.ldcs = l.ldcs; p.relu = l.relu;
+    p.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr; p.stop = stop;
     const int tiles = ((l.M + tc::BM - 1) / tc::BM) * (l.N / tc::BN);
     const int grid = std::min(tiles, h->num_sms);
     prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
-    tc::gemm_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
+    if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
+    else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
     return FFB_OK;
 }
 
-int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* b, __nv_bfloat16* out_plain, __nv_bfloat16* out_pos,
+int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* b, uint16_t* out_plain, uint16_t* out_pos,
                     long long split_stride, const float* pos, int pos_mod, int M, int E, const int* stop, cudaStream_t s) {
     if (M <= 0) return FFB_OK;
     prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
-    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, stop);
+    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
+                                                       h->state.as<int>() ? h->state.as<int>() + 4 : nullptr, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
     return FFB_OK;
 }
 
-int split_weight(ffb_handle* h, const float* src, __nv_bfloat16* dst, size_t rows, size_t K, CUtensorMap* map, cudaStream_t s) {
+// Split one weight matrix [rows, K] into the operand format `fmt` (+ TMA map).  fp16x2: the matrix is pre-scaled by a
+// power of two so that max|w| lands near 2^13 (both halves of the split stay in fp16's normal range); *scale_out
+// receives that factor (undone in the GEMM epilogue, exact).
+int split_weight(ffb_handle* h, const float* src, uint16_t* dst, size_t rows, size_t K, CUtensorMap* map, int fmt, float* scale_out,
+                 cudaStream_t s) {
+    float scale = 1.f;
+    if (fmt == 2) {
+        int* d_max = nullptr; int bits = 0;
+        CU(h, cudaMalloc(&d_max, sizeof(int)));
+        cudaMemsetAsync(d_max, 0, sizeof(int), s);
+        absmax_kernel<<<grid1d((long long)(rows * K)), 256, 0, s>>>(src, (long long)(rows * K), d_max);
+        h->launches++;
+        cudaError_t e = cudaMemcpyAsync(&bits, d_max, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_max);
+        if (e != cudaSuccess) return fail(h, FFB_ERR_CUDA, "absmax: %s", cudaGetErrorString(e));
+        float mx; memcpy(&mx, &bits, sizeof mx);
+        if (!(mx <= 3.0e38f)) return fail(h, FFB_ERR_ARG, "weight matrix contains inf/nan");
+        if (mx > 0.f) {
+            int ex = (int)floorf(log2f(8192.0f / mx));
+            ex = std::max(-40, std::min(40, ex));
+            scale = ldexpf(1.0f, ex);
+        }
+    }
+    if (scale_out) *scale_out = scale;
     const long long n4 = (long long)(rows * K / 4);
-    split_array_kernel<<<grid1d(n4), 256, 0, s>>>(src, dst, n4);
+    split_array_kernel<<<grid1d(n4), 256, 0, s>>>(src, dst, n4, scale, fmt);
     h->launches++;
     CU(h, cudaGetLastError());
-    return encode_operand_map(h, map, dst, K, rows, tc::BN);
+    return encode_operand_map(h, map, dst, K, rows, tc::BN, fmt);
+}
+
+// Build (once per format) the split weights and (per batch) the activation-operand maps of format `fmt`.
+int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
+    ffb_handle::TcSet& T = h->tcs[fmt - 2];
+    const size_t E = h->E, FF = h->FF, Ld = h->Ld;
+    if (!T.ready) {
+        const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
+        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E) * 2));
+        uint16_t* wp = T.wsplit.as<uint16_t>();
+        T.layers.resize(Ld);
+        for (size_t l = 0; l < Ld; ++l) {
+            const DecLayerW& L = h->w.dec[l];
+            ffb_handle::DecTcW& D = T.layers[l];
+            FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &D.sa_in, fmt, &D.s_sa_in, s)); wp += fmt * 3 * E * E;
+            FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &D.sa_out, fmt, &D.s_sa_out, s)); wp += fmt * E * E;
+            FFB_TRY(split_weight(h, L.ca.in_w, wp, E, E, &D.ca_q, fmt, &D.s_ca_q, s)); wp += fmt * E * E;      // q rows of the cross in_proj
+            FFB_TRY(split_weight(h, L.ca.out_w, wp, E, E, &D.ca_out, fmt, &D.s_ca_out, s)); wp += fmt * E * E;
+            FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &D.l1, fmt, &D.s_l1, s)); wp += fmt * FF * E;
+            FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
+        }
+        FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &T.proj, fmt, &T.s_proj, s));
+        T.ready = true;
+    }
+    if (h->cap_rows > 0) {
+        const size_t cr = (size_t)h->cap_rows;
+        FFB_TRY(encode_operand_map(h, &T.m_x2, h->a_x2.p, E, cr, tc::BM, fmt));
+        FFB_TRY(encode_operand_map(h, &T.m_x2p, h->a_x2p.p, E, cr, tc::BM, fmt));
+        FFB_TRY(encode_operand_map(h, &T.m_att, h->a_att.p, E, cr, tc::BM, fmt));
+        FFB_TRY(encode_operand_map(h, &T.m_h, h->a_h.p, FF, cr, tc::BM, fmt));
+    }
+    return FFB_OK;
 }
 
 int set_device(ffb_handle* h) {
@@ -474,7 +544,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     CU(h, h->Vc.ensure((size_t)R * h->Ld * E * f4));
     CU(h, h->tok.ensure((size_t)h->T * h->B * sizeof(int)));
     CU(h, h->logits.ensure((size_t)h->B * h->L * f4));
-    CU(h, h->state.ensure(4 * sizeof(int)));
+    CU(h, h->state.ensure(8 * sizeof(int)));
     CU(h, h->x.ensure(rows * E * f4));
     CU(h, h->x2.ensure(rows * E * f4));
     CU(h, h->qkv.ensure(rows * 3 * E * f4));
@@ -486,10 +556,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         const size_t cr = (size_t)h->cap_rows;
         CU(h, h->a_x2.ensure(3 * cr * E * 2)); CU(h, h->a_x2p.ensure(3 * cr * E * 2));
         CU(h, h->a_att.ensure(3 * cr * E * 2)); CU(h, h->a_h.ensure(3 * cr * FF * 2));
-        FFB_TRY(encode_operand_map(h, &h->m_x2, h->a_x2.p, E, cr, tc::BM));
-        FFB_TRY(encode_operand_map(h, &h->m_x2p, h->a_x2p.p, E, cr, tc::BM));
-        FFB_TRY(encode_operand_map(h, &h->m_att, h->a_att.p, E, cr, tc::BM));
-        FFB_TRY(encode_operand_map(h, &h->m_h, h->a_h.p, FF, cr, tc::BM));
+        FFB_TRY(prepare_tc(h, h->tc_fmt, s));
     }
     return FFB_OK;
 }
@@ -559,9 +626,10 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     h->launches++; CU(h, cudaGetLastError());
 
     float* cur = x; int rows = M; int Pq = P;            // rows carried through the rest of the layer
-    const bool tc = h->tc_ok && h->opt_tc && (int)h->tcw.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS);
-    __nv_bfloat16* ax2 = h->a_x2.as<__nv_bfloat16>(); __nv_bfloat16* ax2p = h->a_x2p.as<__nv_bfloat16>();
-    __nv_bfloat16* aatt = h->a_att.as<__nv_bfloat16>(); __nv_bfloat16* ah = h->a_h.as<__nv_bfloat16>();
+    const ffb_handle::TcSet& TS = h->tcs[h->tc_fmt - 2];
+    const bool tc = h->tc_ok && h->opt_tc && TS.ready && (int)TS.layers.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS);
+    uint16_t* ax2 = h->a_x2.as<uint16_t>(); uint16_t* ax2p = h->a_x2p.as<uint16_t>();
+    uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>();
     const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the bf16x3 splits
     for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
         const DecLayerW& Lw = w.dec[li];
@@ -606,35 +674,35 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, stop, s)); }
         } else {
             // ---- tensor-core path: every GEMM operand is produced directly as bf16x3 splits ----
-            const ffb_handle::DecTcW& Tw = h->tcw[li];
+            const ffb_handle::DecTcW& Tw = TS.layers[li];
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
-            { TcLin l; l.A0 = &h->m_x2p; l.A1 = &h->m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
-              l.W = &Tw.sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.M = M; l.N = 3 * E; l.K = E;
+            { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
+              l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.M = M; l.N = 3 * E; l.K = E;
               FFB_TRY(launch_tc(h, l, stop, s)); }
             if (!last) {
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
-                { TcLin l; l.A0 = &h->m_att; l.W = &Tw.sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             } else {
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
                 copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
-                { TcLin l; l.A0 = &h->m_att; l.W = &Tw.sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
+                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
                   l.M = B; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
                 cur = xl; rows = B; Pq = 1;
             }
             FFB_TRY(launch_ln_split(h, cur, Lw.n2w, Lw.n2b, nullptr, ax2p, ssE, qpos_cross, qmod_cross, rows, E, stop, s));
-            { TcLin l; l.A0 = &h->m_x2p; l.W = &Tw.ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+            { TcLin l; l.A0 = &TS.m_x2p; l.W = &Tw.ca_q; l.w_scale = Tw.s_ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.M = rows; l.N = E; l.K = E;
               FFB_TRY(launch_tc(h, l, stop, s)); }
             { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
               FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
                                         att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s, aatt, ssE)); }
-            { TcLin l; l.A0 = &h->m_att; l.W = &Tw.ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+            { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.ca_out; l.w_scale = Tw.s_ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
               l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             FFB_TRY(launch_ln_split(h, cur, Lw.n3w, Lw.n3b, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
-            { TcLin l; l.A0 = &h->m_x2; l.W = &Tw.l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
+            { TcLin l; l.A0 = &TS.m_x2; l.W = &Tw.l1; l.w_scale = Tw.s_l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
               l.M = rows; l.N = FF; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
-            { TcLin l; l.A0 = &h->m_h; l.W = &Tw.l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+            { TcLin l; l.A0 = &TS.m_h; l.W = &Tw.l2; l.w_scale = Tw.s_l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
               l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_tc(h, l, stop, s)); }
         }
     }
@@ -645,7 +713,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
           FFB_TRY(launch_linear(h, l, stop, s)); }
     } else {
         FFB_TRY(launch_ln_split(h, cur, w.dec_nw, w.dec_nb, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
-        { TcLin l; l.A0 = &h->m_x2; l.W = &h->tc_proj; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+        { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.proj; l.w_scale = TS.s_proj; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
           FFB_TRY(launch_tc(h, l, stop, s)); }
     }
     PointerArgs pa{};
@@ -704,7 +772,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(tc::gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
     if (!g_encode_tiled) {
         void* fn = nullptr;
@@ -735,7 +804,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -750,6 +819,11 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_PRUNE_LAST: h->opt_prune = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TIMING: h->opt_timing = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; h->prof_recs.clear(); return FFB_OK;
+        case FFB_OPT_TC_FORMAT:
+            if (value != 2 && value != 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_TC_FORMAT: 2 = fp16x2, 3 = bf16x3");
+            h->tc_fmt = value; h->encoded = false;
+            if (h->weights_loaded && h->tc_ok && h->opt_tc) { int rc = prepare_tc(h, value, nullptr); if (rc != FFB_OK) return rc; }
+            return FFB_OK;
         case FFB_OPT_ATTN_MMA: h->opt_attn_mma = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
@@ -781,24 +855,8 @@ int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, vo
         CU(h, cudaMemcpyAsync(cvb + l * E, ca.in_b + 2 * E, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     h->w.ckw = ckw; h->w.cvw = cvw; h->w.ckb = ckb; h->w.cvb = cvb;
-    if (h->tc_ok) {
-        // bf16x3 splits of every decoder-step weight matrix, [3][N][K] each, + their TMA maps
-        const size_t FF = h->FF;
-        const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
-        CU(h, h->wsplit.ensure(3 * (Ld * per_layer + E * E) * sizeof(__nv_bfloat16)));
-        __nv_bfloat16* wp = h->wsplit.as<__nv_bfloat16>();
-        h->tcw.resize(Ld);
-        for (size_t l = 0; l < Ld; ++l) {
-            const DecLayerW& L = h->w.dec[l];
-            FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &h->tcw[l].sa_in, s)); wp += 3 * 3 * E * E;
-            FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &h->tcw[l].sa_out, s)); wp += 3 * E * E;
-            FFB_TRY(split_weight(h, L.ca.in_w, wp, E, E, &h->tcw[l].ca_q, s)); wp += 3 * E * E;      // q rows of the cross in_proj
-            FFB_TRY(split_weight(h, L.ca.out_w, wp, E, E, &h->tcw[l].ca_out, s)); wp += 3 * E * E;
-            FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &h->tcw[l].l1, s)); wp += 3 * FF * E;
-            FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &h->tcw[l].l2, s)); wp += 3 * E * FF;
-        }
-        FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &h->tc_proj, s));
-    }
+    for (auto& T : h->tcs) T.ready = false;                 // split weights are rebuilt lazily per operand format
+    if (h->tc_ok && h->opt_tc) FFB_TRY(prepare_tc(h, h->tc_fmt, s));
     CU(h, cudaStreamSynchronize(s));
     h->weights_loaded = true;
     return FFB_OK;
@@ -860,25 +918,34 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
     const int B = (int)h->B, T = h->T;
     int* st = h->state.as<int>();
     if (h->opt_timing && !h->ev[1]) return fail(h, FFB_ERR_STATE, "timing events missing");
-    init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
-    h->launches++; CU(h, cudaGetLastError());
-    CU(h, cudaMemsetAsync(st + 2, 0, sizeof(int), s));
-    for (int step = 0; step < T - 1; ++step) FFB_TRY(run_step(h, step + 1, true, s));   // no host sync inside the loop
     const long long n_slots = h->B_full;
     long long* out_dev = reinterpret_cast<long long*>(predict);
     if (loc == FFB_HOST) {
         CU(h, h->d_predict.ensure((size_t)n_slots * T * sizeof(long long)));
         out_dev = h->d_predict.as<long long>();
     }
-    expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
-    h->launches++; CU(h, cudaGetLastError());
-    if (h->opt_timing) CU(h, cudaEventRecord(h->ev[2], s));
-    if (loc == FFB_HOST)
-        CU(h, cudaMemcpyAsync(predict, out_dev, (size_t)n_slots * T * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    if (steps_run) {
-        CU(h, cudaMemcpyAsync(steps_run, st + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    const bool syncing = (steps_run != nullptr) || (loc == FFB_HOST);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
+        init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
+        h->launches++; CU(h, cudaGetLastError());
+        for (int step = 0; step < T - 1; ++step) FFB_TRY(run_step(h, step + 1, true, s));   // no host sync inside the loop
+        expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
+        h->launches++; CU(h, cudaGetLastError());
+        if (!syncing) break;                      // fully asynchronous call: the overflow flag is left for ffb_overflowed()
+        int host_state[2] = {0, 0};               // executed steps, fp16 overflow flag
+        CU(h, cudaMemcpyAsync(&host_state[0], st + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(&host_state[1], st + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
-    } else if (loc == FFB_HOST) {
+        if (steps_run) *steps_run = host_state[0];
+        if (host_state[1] == 0 || h->tc_fmt != 2) break;
+        // an activation left the fp16 range: switch this handle to the bf16x3 operand format (sticky) and decode again
+        h->tc_fmt = 3; h->fp16_fallbacks++;
+        FFB_TRY(prepare_tc(h, 3, s));
+    }
+    if (h->opt_timing) CU(h, cudaEventRecord(h->ev[2], s));
+    if (loc == FFB_HOST) {
+        CU(h, cudaMemcpyAsync(predict, out_dev, (size_t)n_slots * T * sizeof(long long), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
     }
     h->decoded = true;
@@ -969,15 +1036,26 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
             }
     }
     int* st = h->state.as<int>();
-    CU(h, cudaMemsetAsync(st, 0, 4 * sizeof(int), s));
+    CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
     load_prefix_kernel<<<grid1d((long long)P * h->B), 256, 0, s>>>(pdev, h->d_seq_slot.as<int>(), h->tok.as<int>(), P, (int)h->B_full, (int)h->B);
     h->launches++; CU(h, cudaGetLastError());
-    FFB_TRY(run_step(h, P, false, s));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FFB_TRY(run_step(h, P, false, s));
+        int ovf = 0;
+        CU(h, cudaMemcpyAsync(&ovf, st + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        if (ovf == 0 || h->tc_fmt != 2) break;
+        h->tc_fmt = 3; h->fp16_fallbacks++;
+        FFB_TRY(prepare_tc(h, 3, s));
+        CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
+    }
     h->decoded = false;
     return emit_logits(h, logits, loc, s);
 }
 
 int64_t ffb_kernel_launches(const ffb_handle* h) { return h ? h->launches : 0; }
+
+int ffb_fp16_fallbacks(const ffb_handle* h) { return h ? h->fp16_fallbacks : 0; }
 
 int ffb_phase_times(ffb_handle* h, float* out_ms, int32_t n) {
     if (!h || !out_ms || n < 2) return FFB_ERR_ARG;
@@ -1027,32 +1105,22 @@ int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float*
         if (as.ensure(3 * Mp * K * 2) != cudaSuccess || ws.ensure(3 * (size_t)N * K * 2) != cudaSuccess ||
             cs.ensure(3 * Mp * (size_t)N * 2) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_linear_tc: out of device memory"); break; }
         if (cudaMemsetAsync(as.p, 0, 3 * Mp * K * 2, s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "memset failed"); break; }
-        // split A row block by row block so that the split stride is Mp*K (the padded capacity)
-        {
-            // A is [M,K] contiguous: splitting it as one array of M*K elements uses stride M*K; use the padded layout instead
+        const int fmt = h->tc_fmt;
+        {   // A is [M,K] contiguous: split it as one array, the splits are then M*K elements apart
             const long long n4 = (long long)M * K / 4;
-            split_array_kernel<<<grid1d(n4), 256, 0, s>>>(A, as.as<__nv_bfloat16>(), n4);   // stride 4*n4 = M*K
+            split_array_kernel<<<grid1d(n4), 256, 0, s>>>(A, as.as<uint16_t>(), n4, 1.0f, fmt);
             h->launches++;
         }
         CUtensorMap mA, mW;
-        // A splits are M*K apart (not Mp*K): describe exactly that
-        {
-            if (!g_encode_tiled) { rc = fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable"); break; }
-            const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, 3};
-            const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
-            const cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM, 1};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            CUresult r = g_encode_tiled(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, as.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { rc = fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r); break; }
-        }
-        if ((rc = split_weight(h, W, ws.as<__nv_bfloat16>(), N, K, &mW, s)) != FFB_OK) break;
-        TcLin l; l.A0 = &mA; l.W = &mW; l.bias = bias; l.M = M; l.N = N; l.K = K; l.relu = relu;
-        if (via_split) { l.Cs = cs.as<__nv_bfloat16>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
+        if ((rc = encode_operand_map(h, &mA, as.p, K, M, tc::BM, fmt)) != FFB_OK) break;
+        float wscale = 1.f;
+        if ((rc = split_weight(h, W, ws.as<uint16_t>(), N, K, &mW, fmt, &wscale, s)) != FFB_OK) break;
+        TcLin l; l.A0 = &mA; l.W = &mW; l.w_scale = wscale; l.bias = bias; l.M = M; l.N = N; l.K = K; l.relu = relu;
+        if (via_split) { l.Cs = cs.as<uint16_t>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
         else { l.C = C; l.ldc = N; l.R = R; l.ldr = N; }
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;
         if (via_split) {
-            sum_split_kernel<<<grid1d((long long)M * N), 256, 0, s>>>(cs.as<__nv_bfloat16>(), (long long)Mp * N, C, (long long)M * N);
+            sum_split_kernel<<<grid1d((long long)M * N), 256, 0, s>>>(cs.as<uint16_t>(), (long long)Mp * N, C, (long long)M * N, fmt);
             h->launches++;
         }
         if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_linear_tc: %s", cudaGetErrorString(cudaGetLastError())); break; }
@@ -1077,12 +1145,12 @@ int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t 
         cudaMemsetAsync(as.p, 0, 3 * Mp * K * 2, s); cudaMemsetAsync(ws.p, 0, 3 * (size_t)N * K * 2, s);
         cudaMemsetAsync(cf.p, 0, Mp * (size_t)N * 4, s); cudaMemsetAsync(bias.p, 0, (size_t)N * 4, s);
         CUtensorMap mA, mW;
-        if ((rc = encode_operand_map(h, &mA, as.p, K, Mp, tc::BM)) != FFB_OK) break;
-        if ((rc = encode_operand_map(h, &mW, ws.p, K, N, tc::BN)) != FFB_OK) break;
+        if ((rc = encode_operand_map(h, &mA, as.p, K, Mp, tc::BM, h->tc_fmt)) != FFB_OK) break;
+        if ((rc = encode_operand_map(h, &mW, ws.p, K, N, tc::BN, h->tc_fmt)) != FFB_OK) break;
         TcLin l; l.A0 = &mA; l.W = &mW; l.M = M; l.N = N; l.K = K;
         if (flags & 1) l.bias = bias.as<float>();
         if (flags & 4) l.relu = 1;
-        if (flags & 8) { l.Cs = cs.as<__nv_bfloat16>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
+        if (flags & 8) { l.Cs = cs.as<uint16_t>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
         else if (!(flags & 16)) { l.C = cf.as<float>(); l.ldc = N; if (flags & 2) { l.R = cf.as<float>(); l.ldr = N; } }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;          // warm-up

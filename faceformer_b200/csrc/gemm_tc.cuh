@@ -1,6 +1,11 @@
 // gemm_tc.cuh -- split-precision tensor-core GEMM for the decode-step linear layers (sm_100a only).
 //
-//   C[M,N] = epilogue( A[M,K] . W[N,K]^T )      A, W given as bf16x3 splits:  x = x0 + x1 + x2 (exact to 2^-26)
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T )      A, W given as 16-bit splits of fp32 values (template NS):
+//       NS = 3  bf16x3:  x = x0 + x1 + x2 (exact to 2^-26), 6 MMAs  A0W0 + A0W1 + A1W0 + A1W1 + A0W2 + A2W0
+//       NS = 2  fp16x2:  x = h + l       (exact to 2^-22), 3 MMAs  hh + hl + lh; half the tensor work and 2/3 of the
+//               operand bytes, but fp16 range: weights are pre-scaled by a power of two per matrix (undone in the
+//               epilogue, exact) and producers raise an overflow flag if |activation| > 65504 (the host then re-runs
+//               the decode in bf16x3).
 //
 // Why split precision: the parity contract (token-exact, logits within 1e-4 of the reference's fp32 CPU path)
 // needs fp32-class products; one bf16 pass is ~6000x over budget.  Six bf16 MMAs
@@ -15,8 +20,12 @@
 // FADDs.  DRAIN_KB = 2 balances the TMEM read port (a 128x256 fp32 drain costs ~2k cycles, measured) against
 // the MMA time of the k-blocks it covers; chains stay 24 MMAs long independent of K.
 //
+// Epilogue: NS = 2 leaves room in shared memory for a per-warp 32x32 transposition buffer, so outputs (and the
+// residual read) go out as fully coalesced 128-byte rows; NS = 3 (3 x 72 KB of operand stages) writes one row per
+// thread directly (un-coalesced; measured 138 vs 350 TFLOP/s mainloop-only, profiles/tune_gemm.py).
+//
 // Structure (one CTA per SM, persistent over output tiles of 128 x 256):
-//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: k, row, split) into a 3-stage smem ring
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: k, row, split) into a 3/4-stage smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, ping-pong per k-block)
 //   warps 4-11  epilogue: tcgen05.ld 32x32b -> register accumulate -> bias / ReLU / residual -> global
@@ -24,32 +33,47 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "kernels.cuh"   // split3_bf16
 
 namespace ffb {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32;          // BK bf16 = 64-byte rows -> SWIZZLE_64B
-constexpr int NSPLIT = 3;
-constexpr int STAGES = 3;
-constexpr int DRAIN_KB = 2;                          // k-blocks accumulated in TMEM per drain
+constexpr int BM = 128, BN = 256, BK = 32;          // BK 16-bit elements = 64-byte rows -> SWIZZLE_64B
 constexpr int A_TILE_BYTES = BM * BK * 2;           //  8 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;           // 16 KB
-constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + B_TILE_BYTES);   // 72 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
+template <int NS> struct Cfg {
+    static_assert(NS == 2 || NS == 3, "NS: 2 = fp16x2, 3 = bf16x3");
+    static constexpr int STAGES = (NS == 2) ? 4 : 3;
+    static constexpr int DRAIN_KB = (NS == 2) ? 4 : 2;            // k-blocks accumulated in TMEM per drain (24 MMAs either way)
+    static constexpr int NPROD = (NS == 2) ? 3 : 6;
+    static constexpr int STAGE_BYTES = NS * (A_TILE_BYTES + B_TILE_BYTES);            // 48 KB / 72 KB
+    static constexpr bool STAGED_EPI = (NS == 2);
+    static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * 32 * 32 * 4 : 0;        // 32 KB
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    // kind::f16 instruction descriptor: D=f32 (bit 4), A/B format (0 = f16, 1 = bf16) at bits 7/10, K-major, N=256, M=128
+    static constexpr uint32_t FMT = (NS == 2) ? 0u : 1u;
+    static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<3>::SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+
 struct Params {
     int M, N, K;                 // N % 256 == 0, K % 32 == 0
     int n_switch;                // n-tiles >= n_switch read mapA1 instead of mapA0
+    float out_scale;             // accumulator scale (undoes the power-of-two weight pre-scaling of the fp16 format)
     const float* bias;           // [N] or null
     float* C; int ldc;           // fp32 output (or null)
     const float* R; int ldr;     // residual added to the fp32 output (may alias C) or null
-    __nv_bfloat16* Cs; long long cs_split_stride; int ldcs;   // bf16x3 split output [3][*][ldcs] (or null)
+    uint16_t* Cs; long long cs_split_stride; int ldcs;   // split output [NS][*][ldcs] in the operand format (or null)
     int relu;
+    int* overflow;               // set to 1 if a split output exceeds the fp16 range (NS = 2)
     const int* stop;
 };
 
@@ -121,34 +145,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)4 << 61;                         // layout type         bits [61,64): 4 = SWIZZLE_64B
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-// x = b0 + b1 + b2 with bf16 parts (round-to-nearest each; residuals are exact in fp32)
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& b0, __nv_bfloat16& b1, __nv_bfloat16& b2) {
-    b0 = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(b0);
-    b1 = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(b1);
-    b2 = __float2bfloat16_rn(r2);
-}
 
 // ---- the kernel -----------------------------------------------------------------------------------
+template <int NS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
             const __grid_constant__ CUtensorMap mapW, const Params p) {
+    using C_ = Cfg<NS>;
+    constexpr int STAGES = C_::STAGES, DRAIN_KB = C_::DRAIN_KB, STAGE_BYTES = C_::STAGE_BYTES;
     if (p.stop != nullptr && *p.stop != 0) return;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + C_::EPI_BYTES;
     // barriers: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));          // generic pointer to the aligned base
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_chunks = p.K / BK;
@@ -177,11 +195,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint32_t sb = sa + NSPLIT * A_TILE_BYTES;
+                    const uint32_t sb = sa + NS * A_TILE_BYTES;
 #pragma unroll
-                    for (int s = 0; s < NSPLIT; ++s) tma_load_3d(sa + s * A_TILE_BYTES, mapA, full_bar(stage), kc * BK, mt * BM, s);
+                    for (int s = 0; s < NS; ++s) tma_load_3d(sa + s * A_TILE_BYTES, mapA, full_bar(stage), kc * BK, mt * BM, s);
 #pragma unroll
-                    for (int s = 0; s < NSPLIT; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN, s);
+                    for (int s = 0; s < NS; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN, s);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -197,19 +215,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     mbar_wait(full_bar(stage), phase);                     // operands landed
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint32_t sb = sa + NSPLIT * A_TILE_BYTES;
+                    const uint32_t sb = sa + NS * A_TILE_BYTES;
                     const uint32_t d = tmem_base + buf * BN;
                     // correction products first (small), dominant A0.W0 last
-                    const int pa[6] = {0, 1, 1, 0, 2, 0};
-                    const int pb[6] = {1, 0, 1, 2, 0, 0};
+                    constexpr int pa3[6] = {0, 1, 1, 0, 2, 0}, pb3[6] = {1, 0, 1, 2, 0, 0};
+                    constexpr int pa2[3] = {1, 0, 0}, pb2[3] = {0, 1, 0};
                     uint32_t acc = first_in_drain ? 0u : 1u;
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        const uint64_t da = make_smem_desc(sa + pa[q] * A_TILE_BYTES);
-                        const uint64_t db = make_smem_desc(sb + pb[q] * B_TILE_BYTES);
+                    for (int q = 0; q < C_::NPROD; ++q) {
+                        const int ia = (NS == 2) ? pa2[q % 3] : pa3[q], ib = (NS == 2) ? pb2[q % 3] : pb3[q];
+                        const uint64_t da = make_smem_desc(sa + ia * A_TILE_BYTES);
+                        const uint64_t db = make_smem_desc(sb + ib * B_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {               // +32 B per K=16 step inside the 64-byte swizzle row
-                            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, acc);
+                            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C_::IDESC, acc);
                             acc = 1;
                         }
                     }
@@ -225,6 +244,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         const int e = warp - EPI_WARP0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int hcol = e >> 2;                      // which 128-column half of the tile
+        float* stg = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base)) + e * 1024;   // 32x32 floats per warp (NS = 2)
         float acc[128];
         uint32_t c = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -253,43 +273,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
             }
-            // ---- tile epilogue: bias / ReLU / residual, direct row stores ----
-            const int row = mt * BM + q * 32 + lane;
             const int col0 = nt * BN + hcol * 128;
-            if (row < p.M) {
-                if (p.C != nullptr) {
-                    float* crow = p.C + (size_t)row * p.ldc + col0;
-                    const float* rrow = p.R ? p.R + (size_t)row * p.ldr + col0 : nullptr;
+            const int row0 = mt * BM + q * 32;
+            if constexpr (C_::STAGED_EPI) {
+                // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----
 #pragma unroll
-                    for (int i = 0; i < 128; i += 4) {
-                        float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        }
-                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (rrow) {
-                            const float4 r = *reinterpret_cast<const float4*>(rrow + i);
-                            v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
-                        }
-                        *reinterpret_cast<float4*>(crow + i) = v;
+                for (int j = 0; j < 4; ++j) {                 // (fully unrolled: acc[] must stay in registers)
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const float4 v = make_float4(acc[j * 32 + 4 * cc] * p.out_scale, acc[j * 32 + 4 * cc + 1] * p.out_scale,
+                                                     acc[j * 32 + 4 * cc + 2] * p.out_scale, acc[j * 32 + 4 * cc + 3] * p.out_scale);
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) = v;
                     }
-                }
-                if (p.Cs != nullptr) {
-                    __nv_bfloat16* s0 = p.Cs + (size_t)row * p.ldcs + col0;
-#pragma unroll
-                    for (int i = 0; i < 128; i += 8) {
-                        __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            float x = acc[i + u];
-                            if (p.bias) x += __ldg(p.bias + col0 + i + u);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            split3(x, o0[u], o1[u], o2[u]);
+                    __syncwarp();
+                    const int col = col0 + j * 32 + lane;
+                    const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
+                    const int nrows = min(32, p.M - row0);
+                    if (p.C != nullptr) {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            if (r < nrows) {
+                                float v = stg[r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3)] + bv;
+                                if (p.relu) v = fmaxf(v, 0.f);
+                                const size_t grow = (size_t)(row0 + r);
+                                if (p.R) v = p.R[grow * p.ldr + col] + v;
+                                p.C[grow * p.ldc + col] = v;
+                            }
                         }
-                        *reinterpret_cast<uint4*>(s0 + i) = *reinterpret_cast<const uint4*>(o0);
-                        *reinterpret_cast<uint4*>(s0 + p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o1);
-                        *reinterpret_cast<uint4*>(s0 + 2 * p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o2);
+                    }
+                    if (p.Cs != nullptr) {
+                        __half* s0 = reinterpret_cast<__half*>(p.Cs);
+                        bool ovf = false;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            if (r < nrows) {
+                                float v = stg[r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3)] + bv;
+                                if (p.relu) v = fmaxf(v, 0.f);
+                                ovf |= !(fabsf(v) <= 65504.f);
+                                const __half h = __float2half_rn(v);
+                                const __half l = __float2half_rn(v - __half2float(h));
+                                const size_t off = (size_t)(row0 + r) * p.ldcs + col;
+                                s0[off] = h;
+                                s0[off + p.cs_split_stride] = l;
+                            }
+                        }
+                        if (ovf && p.overflow) *p.overflow = 1;
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // ---- direct epilogue: one row per thread (un-coalesced) ----
+                const int row = row0 + lane;
+                if (row < p.M) {
+                    if (p.C != nullptr) {
+                        float* crow = p.C + (size_t)row * p.ldc + col0;
+                        const float* rrow = p.R ? p.R + (size_t)row * p.ldr + col0 : nullptr;
+#pragma unroll
+                        for (int i = 0; i < 128; i += 4) {
+                            float4 v = make_float4(acc[i] * p.out_scale, acc[i + 1] * p.out_scale, acc[i + 2] * p.out_scale, acc[i + 3] * p.out_scale);
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (rrow) {
+                                const float4 r = *reinterpret_cast<const float4*>(rrow + i);
+                                v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+                            }
+                            *reinterpret_cast<float4*>(crow + i) = v;
+                        }
+                    }
+                    if (p.Cs != nullptr) {
+                        __nv_bfloat16* s0 = reinterpret_cast<__nv_bfloat16*>(p.Cs) + (size_t)row * p.ldcs + col0;
+#pragma unroll
+                        for (int i = 0; i < 128; i += 8) {
+                            __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                float x = acc[i + u] * p.out_scale;
+                                if (p.bias) x += __ldg(p.bias + col0 + i + u);
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                split3_bf16(x, o0[u], o1[u], o2[u]);
+                            }
+                            *reinterpret_cast<uint4*>(s0 + i) = *reinterpret_cast<const uint4*>(o0);
+                            *reinterpret_cast<uint4*>(s0 + p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o1);
+                            *reinterpret_cast<uint4*>(s0 + 2 * p.cs_split_stride + i) = *reinterpret_cast<const uint4*>(o2);
+                        }
                     }
                 }
             }

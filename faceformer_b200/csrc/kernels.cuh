@@ -18,6 +18,7 @@
 //                      stop predicate (model_para.py:229-233 / model.py:205-210)
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
@@ -46,26 +47,72 @@ __device__ __forceinline__ void split3_bf16(float x, __nv_bfloat16& b0, __nv_bfl
     const float r2 = r1 - __bfloat162float(b1);
     b2 = __float2bfloat16_rn(r2);
 }
-// write 4 consecutive values as splits: dst points at split 0, splits are `stride` elements apart
-__device__ __forceinline__ void store_split4(__nv_bfloat16* dst, long long stride, float4 v) {
-    __align__(8) __nv_bfloat16 o0[4], o1[4], o2[4];
-    split3_bf16(v.x, o0[0], o1[0], o2[0]); split3_bf16(v.y, o0[1], o1[1], o2[1]);
-    split3_bf16(v.z, o0[2], o1[2], o2[2]); split3_bf16(v.w, o0[3], o1[3], o2[3]);
-    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o0);
-    *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(o1);
-    *reinterpret_cast<uint2*>(dst + 2 * stride) = *reinterpret_cast<const uint2*>(o2);
+// Operand formats of the tensor-core GEMM (gemm_tc.cuh).  fmt 3: bf16x3 (x = b0+b1+b2); fmt 2: fp16x2 (x = h+l).
+// Arrays are opaque 16-bit words; split s lives `stride` elements after split s-1.
+// fp16 has a narrow range: |x| > 65504 raises *ovf (the host then re-runs the decode in the bf16x3 format).
+__device__ __forceinline__ void store_split4(uint16_t* dst, long long stride, float4 v, int fmt, int* ovf) {
+    if (fmt == 3) {
+        __align__(8) __nv_bfloat16 o0[4], o1[4], o2[4];
+        split3_bf16(v.x, o0[0], o1[0], o2[0]); split3_bf16(v.y, o0[1], o1[1], o2[1]);
+        split3_bf16(v.z, o0[2], o1[2], o2[2]); split3_bf16(v.w, o0[3], o1[3], o2[3]);
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o0);
+        *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(o1);
+        *reinterpret_cast<uint2*>(dst + 2 * stride) = *reinterpret_cast<const uint2*>(o2);
+    } else {
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        __align__(8) __half h[4], l[4];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bad |= !(fabsf(x[i]) <= 65504.f);
+            h[i] = __float2half_rn(x[i]);
+            l[i] = __float2half_rn(x[i] - __half2float(h[i]));
+        }
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(l);
+        if (bad && ovf) *ovf = 1;
+    }
+}
+__device__ __forceinline__ void store_split1(uint16_t* dst, long long stride, float x, int fmt, int* ovf) {
+    if (fmt == 3) {
+        __nv_bfloat16 b0, b1, b2;
+        split3_bf16(x, b0, b1, b2);
+        dst[0] = __bfloat16_as_ushort(b0); dst[stride] = __bfloat16_as_ushort(b1); dst[2 * stride] = __bfloat16_as_ushort(b2);
+    } else {
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        dst[0] = __half_as_ushort(h); dst[stride] = __half_as_ushort(l);
+        if (!(fabsf(x) <= 65504.f) && ovf) *ovf = 1;
+    }
 }
 
-// dst[3][rows*cols] bf16 <- src[rows*cols] fp32 (weights, once at load time)
-__global__ void split_array_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
-        store_split4(dst + 4 * i, 4 * n4, reinterpret_cast<const float4*>(src)[i]);
+// dst[fmt][n] 16-bit <- split(src[n] * scale)  (weights, once at load time; scale is a power of two)
+__global__ void split_array_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n4, float scale, int fmt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(src)[i];
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        store_split4(dst + 4 * i, 4 * n4, v, fmt, nullptr);
+    }
 }
 
-// dst[i] = s0[i] + s1[i] + s2[i]  (test hook: re-sum a bf16x3 split array)
-__global__ void sum_split_kernel(const __nv_bfloat16* __restrict__ src, long long stride, float* __restrict__ dst, long long n) {
+// out[0] = max |src[i]| (as int bits of a non-negative float; out must be zeroed first)
+__global__ void absmax_kernel(const float* __restrict__ src, long long n, int* __restrict__ out) {
+    float m = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = (__bfloat162float(src[i]) + __bfloat162float(src[i + stride])) + __bfloat162float(src[i + 2 * stride]);
+        m = fmaxf(m, fabsf(src[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_int(m));
+}
+
+// dst[i] = sum of the splits of element i  (test hook: re-sum a split array)
+__global__ void sum_split_kernel(const uint16_t* __restrict__ src, long long stride, float* __restrict__ dst, long long n, int fmt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (fmt == 3)
+            dst[i] = (__bfloat162float(__ushort_as_bfloat16(src[i])) + __bfloat162float(__ushort_as_bfloat16(src[i + stride]))) +
+                     __bfloat162float(__ushort_as_bfloat16(src[i + 2 * stride]));
+        else
+            dst[i] = __half2float(__ushort_as_half(src[i])) + __half2float(__ushort_as_half(src[i + stride]));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,10 +309,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // layernorm + operand formatting for the tensor-core GEMM: writes bf16x3 splits of y = LN(x) (out_plain) and/or of
 // y + pos[r % pos_mod] (out_pos) -- with_pos_embed (transformer.py:144-145,205-206) fused into the producer.
 __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_plain,
-                                                              __nv_bfloat16* __restrict__ out_pos, long long split_stride,
+                                                              const float* __restrict__ beta, uint16_t* __restrict__ out_plain,
+                                                              uint16_t* __restrict__ out_pos, long long split_stride,
                                                               const float* __restrict__ pos, int pos_mod,
-                                                              int M, int E, const int* stop) {
+                                                              int M, int E, int fmt, int* ovf, const int* stop) {
     FFB_STOP_CHECK(stop);
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -302,11 +349,11 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
             float4 o;
             o.x = v[i].x * rstd * g.x + b.x; o.y = v[i].y * rstd * g.y + b.y;
             o.z = v[i].z * rstd * g.z + b.z; o.w = v[i].w * rstd * g.w + b.w;
-            if (out_plain) store_split4(out_plain + (size_t)row * E + c, split_stride, o);
+            if (out_plain) store_split4(out_plain + (size_t)row * E + c, split_stride, o, fmt, ovf);
             if (out_pos) {
                 const float4 pp = __ldg(reinterpret_cast<const float4*>(prow + c));
                 o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
-                store_split4(out_pos + (size_t)row * E + c, split_stride, o);
+                store_split4(out_pos + (size_t)row * E + c, split_stride, o, fmt, ovf);
             }
         }
     }
@@ -321,6 +368,8 @@ struct AttnGroups {
     int nq, nk, q_stride, q_off, k_stride, o_stride;
     // ragged: queries (== output rows) [q_begin[g]*q_mul, q_begin[g+1]*q_mul); keys [k_begin[g], +k_len[g])
     const int* q_begin; int q_mul; const int* k_begin; const int* k_len;
+    // split output (operand of the tensor-core out-projection): format and overflow flag
+    int split_fmt; int* overflow;
 };
 
 __device__ __forceinline__ void attn_group(const AttnGroups& g, int grp, long long& q0, int& nq,
@@ -343,7 +392,7 @@ constexpr int AR_BQ = 64, AR_BK = 32, AR_RPW = 16, AR_KS = 68;
 
 __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict__ Q, int ldq,
                                                         const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                        float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ Os,
+                                                        float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
                                                         long long os_stride, const AttnGroups g, const int* stop) {
     FFB_STOP_CHECK(stop);
     __shared__ __align__(16) float Qs[AR_BQ][64];
@@ -429,11 +478,9 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict_
             if (Os == nullptr) {
                 O[off + lane] = r0;
                 O[off + lane + 32] = r1;
-            } else {                                   // operand of the tensor-core out-projection: bf16x3 splits
-                __nv_bfloat16 a0, a1, a2, b0, b1, b2;
-                split3_bf16(r0, a0, a1, a2); split3_bf16(r1, b0, b1, b2);
-                Os[off + lane] = a0; Os[off + os_stride + lane] = a1; Os[off + 2 * os_stride + lane] = a2;
-                Os[off + lane + 32] = b0; Os[off + os_stride + lane + 32] = b1; Os[off + 2 * os_stride + lane + 32] = b2;
+            } else {                                   // operand of the tensor-core out-projection
+                store_split1(Os + off + lane, os_stride, r0, g.split_fmt, g.overflow);
+                store_split1(Os + off + lane + 32, os_stride, r1, g.split_fmt, g.overflow);
             }
         }
     }
@@ -448,7 +495,7 @@ constexpr int AT_SMEM_BYTES = (3 * AT_BQ * AT_S + AT_BK * 64) * (int)sizeof(floa
 
 __global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict__ Q, int ldq,
                                                          const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                         float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ Os,
+                                                         float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
                                                          long long os_stride, const AttnGroups g, const int* stop) {
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) float smem[];
@@ -579,8 +626,8 @@ __global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict
                 *reinterpret_cast<float4*>(O + off) = lo4;
                 *reinterpret_cast<float4*>(O + off + 4) = hi4;
             } else {
-                store_split4(Os + off, os_stride, lo4);
-                store_split4(Os + off + 4, os_stride, hi4);
+                store_split4(Os + off, os_stride, lo4, g.split_fmt, g.overflow);
+                store_split4(Os + off + 4, os_stride, hi4, g.split_fmt, g.overflow);
             }
         }
     }

@@ -227,6 +227,9 @@ class Engine:
         self._check(self._lib.ffb_forced_prefix_logits(self._h, _ptr(prefix), int(prefix.shape[0]), _ptr(out), loc, self._stream()))
         return out
 
+    def fp16_fallbacks(self) -> int:
+        return int(self._lib.ffb_fp16_fallbacks(self._h))
+
     def kernel_launches(self) -> int:
         return int(self._lib.ffb_kernel_launches(self._h))
 

@@ -20,7 +20,7 @@ HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh",
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
-FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA = 1, 2, 3, 4, 5, 6
+FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT = 1, 2, 3, 4, 5, 6, 7
 PROFILE_CLASSES = ("linear", "layernorm", "attn_rows", "attn_tiled", "pointer", "other", "linear_tc")
 
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "ffb_get_last_pointer": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),
     "ffb_forced_prefix_logits": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int, _P]),
     "ffb_kernel_launches": (C.c_int64, [_P]),
+    "ffb_fp16_fallbacks": (C.c_int, [_P]),
     "ffb_phase_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "ffb_profile_read": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ffb_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

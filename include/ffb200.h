@@ -141,6 +141,10 @@ int ffb_get_last_pointer(ffb_handle* h, float* pointer, int32_t* P_out, int loc,
 int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, float* logits,
                              int loc, void* stream);
 
+/* Number of decodes that had to be re-run in bf16x3 because an activation left the fp16 range (see FFB_OPT_TC_FORMAT).
+ * A fully asynchronous ffb_decode_greedy (device buffers, steps_run == NULL) cannot re-run: poll this afterwards. */
+int ffb_fp16_fallbacks(const ffb_handle* h);
+
 /* Count of this library's kernels launched on the handle since creation (bench `gpu_launches`). */
 int64_t ffb_kernel_launches(const ffb_handle* h);
 
@@ -162,6 +166,10 @@ int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops,
 enum { FFB_OPT_TENSOR_CORE = 5 };
 /* Attention core: 1 (default) = tensor-pipe kernel (mma.sync m16n8k8, 3xTF32 split, attn_mma.cuh); 0 = fp32 SIMT kernels. */
 enum { FFB_OPT_ATTN_MMA = 6 };
+/* Operand format of the tensor-core GEMM: 2 (default) = fp16x2 (3 MMA passes; weights pre-scaled by a power of two;
+ * if an activation exceeds the fp16 range the decode is transparently re-run in format 3 and the handle stays there),
+ * 3 = bf16x3 (6 MMA passes, full fp32 range). */
+enum { FFB_OPT_TC_FORMAT = 7 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */

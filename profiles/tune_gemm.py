@@ -11,14 +11,19 @@ import torch  # noqa: F401,E402  (creates the CUDA context / stream plumbing)
 from faceformer_b200.config import MODE_PARALLEL, OURS  # noqa: E402
 from faceformer_b200.engine import Engine  # noqa: E402
 
+from faceformer_b200.lib import FFB_OPT_TC_FORMAT  # noqa: E402
+
 e = Engine(OURS, MODE_PARALLEL, 0)
 FLAGS = {"nostore": 16, "plain": 0, "bias": 1, "bias+res": 3, "bias+relu+split": 13}
-print(f"{'M':>8} {'N':>6} {'K':>6} " + " ".join(f"{k:>16}" for k in FLAGS))
-for M, N, K in [(131072, 512, 512), (131072, 1536, 512), (131072, 1024, 512), (131072, 512, 1024), (32768, 512, 512), (4096, 512, 512)]:
-    row = []
-    for name, fl in FLAGS.items():
-        ms = C.c_float()
-        e._check(e._lib.ffb_bench_linear_tc(e._h, M, N, K, fl, 10, C.byref(ms), e._stream()))
-        row.append(f"{ms.value:7.3f}ms {2.0 * M * N * K / ms.value / 1e9:6.1f}TF")
-    print(f"{M:>8} {N:>6} {K:>6} " + " ".join(f"{r:>16}" for r in row))
+for fmt in (2, 3):
+  e.set_option(FFB_OPT_TC_FORMAT, fmt)
+  print(f"--- operand format {fmt} ({'fp16x2, 3 MMA passes' if fmt == 2 else 'bf16x3, 6 MMA passes'})")
+  print(f"{'M':>8} {'N':>6} {'K':>6} " + " ".join(f"{k:>16}" for k in FLAGS))
+  for M, N, K in [(131072, 512, 512), (131072, 1536, 512), (131072, 1024, 512), (131072, 512, 1024), (32768, 512, 512), (4096, 512, 512)]:
+      row = []
+      for name, fl in FLAGS.items():
+          ms = C.c_float()
+          e._check(e._lib.ffb_bench_linear_tc(e._h, M, N, K, fl, 10, C.byref(ms), e._stream()))
+          row.append(f"{ms.value:7.3f}ms {2.0 * M * N * K / ms.value / 1e9:6.1f}TF")
+      print(f"{M:>8} {N:>6} {K:>6} " + " ".join(f"{r:>16}" for r in row))
 e.close()

@@ -30,7 +30,7 @@ def test_library_is_built_in_tree():
 def test_header_symbols_are_all_exported_and_bound():
     hdr = open(os.path.join(ROOT, "include", "ffb200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(ffb_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(ffb_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations found"
     lib = L.load()
     for name in declared:
