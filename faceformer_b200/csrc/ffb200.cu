@@ -88,6 +88,7 @@ struct ffb_handle {
     // tensor-core path (gemm_tc.cuh): bf16x3 split weights + activation operands, TMA tensor maps
     bool tc_ok = false;                           // geometry supported (E, FF multiples of 256)
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
+    int opt_stagger = 1;                          // de-phase persistent GEMM CTAs (see gemm_tc.cuh)
     int opt_attn_mma = 1;                         // attention core: 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     int num_sms = 148;
     int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
@@ -332,6 +333,9 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     p.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr; p.stop = stop;
     const int tiles = ((l.M + tc::BM - 1) / tc::BM) * (l.N / tc::BN);
     const int grid = std::min(tiles, h->num_sms);
+    // phase-stagger only when every CTA has several tiles to amortise it: a quarter of one tile's mainloop time per group
+    // (~130 ns per k-block per MMA pass at the measured rates)
+    if (h->opt_stagger && tiles >= 4 * grid) p.stagger_ns = (unsigned)((l.K / tc::BK) * 130 * (h->tc_fmt == 2 ? 3 : 6) / 4);
     prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
     if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
     else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
@@ -824,6 +828,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             h->tc_fmt = value; h->encoded = false;
             if (h->weights_loaded && h->tc_ok && h->opt_tc) { int rc = prepare_tc(h, value, nullptr); if (rc != FFB_OK) return rc; }
             return FFB_OK;
+        case FFB_OPT_STAGGER: h->opt_stagger = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ATTN_MMA: h->opt_attn_mma = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");

@@ -74,6 +74,7 @@ struct Params {
     uint16_t* Cs; long long cs_split_stride; int ldcs;   // split output [NS][*][ldcs] in the operand format (or null)
     int relu;
     int* overflow;               // set to 1 if a split output exceeds the fp16 range (NS = 2)
+    unsigned stagger_ns;         // start delay per phase group (blockIdx & 3), 0 = none
     const int* stop;
 };
 
@@ -183,6 +184,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // De-phase the persistent CTAs: with identical tiles they would all reach their store phase together and hit the
+    // HBM write path as one burst while the tensor pipe idles, then all compute while the write path idles
+    // (measured: store time ADDED to mainloop time).  Four phase groups spread the bursts over a tile period.
+    if (p.stagger_ns > 0) __nanosleep((blockIdx.x & 3u) * p.stagger_ns);
+
     if (warp < EPI_WARP0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0 && lane == 0) {
@@ -290,14 +296,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
                     const int nrows = min(32, p.M - row0);
                     if (p.C != nullptr) {
-#pragma unroll 8
+                        // R may alias C (in-place residual add): every lane reads exactly the addresses it writes below, so all
+                        // 32 residual loads are issued up front (the compiler cannot hoist them past the stores by itself)
+                        float rv[32];
+                        if (p.R) {
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) rv[r] = (r < nrows) ? p.R[(size_t)(row0 + r) * p.ldr + col] : 0.f;
+                        }
+#pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             if (r < nrows) {
                                 float v = stg[r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3)] + bv;
                                 if (p.relu) v = fmaxf(v, 0.f);
-                                const size_t grow = (size_t)(row0 + r);
-                                if (p.R) v = p.R[grow * p.ldr + col] + v;
-                                p.C[grow * p.ldc + col] = v;
+                                if (p.R) v = rv[r] + v;
+                                p.C[(size_t)(row0 + r) * p.ldc + col] = v;
                             }
                         }
                     }

@@ -170,6 +170,8 @@ enum { FFB_OPT_ATTN_MMA = 6 };
  * if an activation exceeds the fp16 range the decode is transparently re-run in format 3 and the handle stays there),
  * 3 = bf16x3 (6 MMA passes, full fp32 range). */
 enum { FFB_OPT_TC_FORMAT = 7 };
+/* 1 (default): de-phase the persistent GEMM CTAs so that their store bursts overlap other CTAs' mainloops; 0 = off. */
+enum { FFB_OPT_STAGGER = 8 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
