@@ -88,7 +88,9 @@ struct ffb_handle {
     // tensor-core path (gemm_tc.cuh): bf16x3 split weights + activation operands, TMA tensor maps
     bool tc_ok = false;                           // geometry supported (E, FF multiples of 256)
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
-    int opt_stagger = 1;                          // de-phase persistent GEMM CTAs (see gemm_tc.cuh)
+    int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
+    int opt_tma_out = 1;                          // fp16x2 GEMM: asynchronous TMA store / reduce-add epilogue
+    CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
     int opt_attn_mma = 1;                         // attention core: 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     int num_sms = 148;
     int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
@@ -315,10 +317,24 @@ int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, ui
     return FFB_OK;
 }
 
+// fp32 [rows, ld] output buffer -> 2-D map, box 32 x 32 floats (128-byte rows), SWIZZLE_128B (the staging layout of the epilogue)
+int encode_output_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint64_t rows) {
+    if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[2] = {ld, rows};
+    const cuuint64_t strides[1] = {ld * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
+    return FFB_OK;
+}
+
 struct TcLin {
     const CUtensorMap* A0 = nullptr; const CUtensorMap* A1 = nullptr; int n_switch = 1 << 30;
     const CUtensorMap* W = nullptr; float w_scale = 1.f; const float* bias = nullptr;
     float* C = nullptr; int ldc = 0; const float* R = nullptr; int ldr = 0;
+    const CUtensorMap* Cmap = nullptr;          // fp32 [rows, ldc] map of C (box 32x32, SWIZZLE_128B): enables the TMA epilogue (fp16x2)
     uint16_t* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
     int M = 0, N = 0, K = 0, relu = 0;
 };
@@ -337,8 +353,11 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     // (~130 ns per k-block per MMA pass at the measured rates)
     if (h->opt_stagger && tiles >= 4 * grid) p.stagger_ns = (unsigned)((l.K / tc::BK) * 130 * (h->tc_fmt == 2 ? 3 : 6) / 4);
     prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
-    if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
-    else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, p);
+    // TMA epilogue: only when the residual (if any) is the in-place form C += ..., which a reduce-add expresses exactly
+    p.tma_out = (h->opt_tma_out && h->tc_fmt == 2 && l.Cmap && l.C && (!l.R || (l.R == l.C && l.ldr == l.ldc))) ? 1 : 0;
+    const CUtensorMap& mc = l.Cmap ? *l.Cmap : *l.W;
+    if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+    else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -542,7 +561,8 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
 
     // workspaces
     const size_t E = h->E, FF = h->FF, f4 = sizeof(float);
-    const size_t rows = (size_t)std::max<long long>(std::max<long long>(R, Mmax), 1);
+    // rows padded to the GEMM tile height: the TMA epilogue writes whole 32-row blocks (rows >= M hold don't-care values)
+    const size_t rows = ((size_t)std::max<long long>(std::max<long long>(R, Mmax), 1) + 127) / 128 * 128;
     CU(h, h->mem.ensure((size_t)R * E * f4));
     CU(h, h->Kc.ensure((size_t)R * h->Ld * E * f4));
     CU(h, h->Vc.ensure((size_t)R * h->Ld * E * f4));
@@ -554,13 +574,19 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     CU(h, h->qkv.ensure(rows * 3 * E * f4));
     CU(h, h->att.ensure(rows * E * f4));
     CU(h, h->hb.ensure(std::max(rows, (size_t)Re) * std::max(FF, E) * f4));
-    CU(h, h->xl.ensure((size_t)std::max<long long>(h->B, 1) * E * f4));
+    const size_t rows_b = ((size_t)std::max<long long>(h->B, 1) + 127) / 128 * 128;
+    CU(h, h->xl.ensure(rows_b * E * f4));
     if (h->tc_ok && h->opt_tc) {
         h->cap_rows = (long long)((rows + 127) / 128 * 128);
         const size_t cr = (size_t)h->cap_rows;
         CU(h, h->a_x2.ensure(3 * cr * E * 2)); CU(h, h->a_x2p.ensure(3 * cr * E * 2));
         CU(h, h->a_att.ensure(3 * cr * E * 2)); CU(h, h->a_h.ensure(3 * cr * FF * 2));
         FFB_TRY(prepare_tc(h, h->tc_fmt, s));
+        FFB_TRY(encode_output_map(h, &h->mc_x, h->x.p, E, rows));
+        FFB_TRY(encode_output_map(h, &h->mc_xl, h->xl.p, E, rows_b));
+        FFB_TRY(encode_output_map(h, &h->mc_qkv3, h->qkv.p, 3 * E, rows));
+        FFB_TRY(encode_output_map(h, &h->mc_qkv1, h->qkv.p, E, rows));
+        FFB_TRY(encode_output_map(h, &h->mc_att, h->att.p, E, rows));
     }
     return FFB_OK;
 }
@@ -681,32 +707,32 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             const ffb_handle::DecTcW& Tw = TS.layers[li];
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
             { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
-              l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.M = M; l.N = 3 * E; l.K = E;
+              l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.Cmap = &h->mc_qkv3; l.M = M; l.N = 3 * E; l.K = E;
               FFB_TRY(launch_tc(h, l, stop, s)); }
             if (!last) {
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
-                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E; l.Cmap = &h->mc_x;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             } else {
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
                 copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
-                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
+                { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E; l.Cmap = &h->mc_xl;
                   l.M = B; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
                 cur = xl; rows = B; Pq = 1;
             }
             FFB_TRY(launch_ln_split(h, cur, Lw.n2w, Lw.n2b, nullptr, ax2p, ssE, qpos_cross, qmod_cross, rows, E, stop, s));
-            { TcLin l; l.A0 = &TS.m_x2p; l.W = &Tw.ca_q; l.w_scale = Tw.s_ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+            { TcLin l; l.A0 = &TS.m_x2p; l.W = &Tw.ca_q; l.w_scale = Tw.s_ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.Cmap = &h->mc_qkv1; l.M = rows; l.N = E; l.K = E;
               FFB_TRY(launch_tc(h, l, stop, s)); }
             { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
               FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
                                         att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s, aatt, ssE)); }
-            { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.ca_out; l.w_scale = Tw.s_ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+            { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.ca_out; l.w_scale = Tw.s_ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E; l.Cmap = (cur == x) ? &h->mc_x : &h->mc_xl;
               l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             FFB_TRY(launch_ln_split(h, cur, Lw.n3w, Lw.n3b, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
             { TcLin l; l.A0 = &TS.m_x2; l.W = &Tw.l1; l.w_scale = Tw.s_l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
               l.M = rows; l.N = FF; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
-            { TcLin l; l.A0 = &TS.m_h; l.W = &Tw.l2; l.w_scale = Tw.s_l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
+            { TcLin l; l.A0 = &TS.m_h; l.W = &Tw.l2; l.w_scale = Tw.s_l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E; l.Cmap = (cur == x) ? &h->mc_x : &h->mc_xl;
               l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_tc(h, l, stop, s)); }
         }
     }
@@ -717,7 +743,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
           FFB_TRY(launch_linear(h, l, stop, s)); }
     } else {
         FFB_TRY(launch_ln_split(h, cur, w.dec_nw, w.dec_nb, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
-        { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.proj; l.w_scale = TS.s_proj; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
+        { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.proj; l.w_scale = TS.s_proj; l.bias = w.proj_b; l.C = att; l.ldc = E; l.Cmap = &h->mc_att; l.M = rows; l.N = E; l.K = E;
           FFB_TRY(launch_tc(h, l, stop, s)); }
     }
     PointerArgs pa{};
@@ -829,6 +855,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (h->weights_loaded && h->tc_ok && h->opt_tc) { int rc = prepare_tc(h, value, nullptr); if (rc != FFB_OK) return rc; }
             return FFB_OK;
         case FFB_OPT_STAGGER: h->opt_stagger = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_TMA_EPILOGUE: h->opt_tma_out = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ATTN_MMA: h->opt_attn_mma = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
@@ -1123,6 +1150,8 @@ int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float*
         TcLin l; l.A0 = &mA; l.W = &mW; l.w_scale = wscale; l.bias = bias; l.M = M; l.N = N; l.K = K; l.relu = relu;
         if (via_split) { l.Cs = cs.as<uint16_t>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
         else { l.C = C; l.ldc = N; l.R = R; l.ldr = N; }
+        CUtensorMap mC;
+        if (!via_split) { if ((rc = encode_output_map(h, &mC, C, N, M)) != FFB_OK) break; l.Cmap = &mC; }
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;
         if (via_split) {
             sum_split_kernel<<<grid1d((long long)M * N), 256, 0, s>>>(cs.as<uint16_t>(), (long long)Mp * N, C, (long long)M * N, fmt);
@@ -1157,6 +1186,8 @@ int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t 
         if (flags & 4) l.relu = 1;
         if (flags & 8) { l.Cs = cs.as<uint16_t>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
         else if (!(flags & 16)) { l.C = cf.as<float>(); l.ldc = N; if (flags & 2) { l.R = cf.as<float>(); l.ldr = N; } }
+        CUtensorMap mC;
+        if (l.C) { if ((rc = encode_output_map(h, &mC, cf.p, N, Mp)) != FFB_OK) break; l.Cmap = &mC; }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;          // warm-up
         cudaEventRecord(e0, s);

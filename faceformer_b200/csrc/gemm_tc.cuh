@@ -75,6 +75,7 @@ struct Params {
     int relu;
     int* overflow;               // set to 1 if a split output exceeds the fp16 range (NS = 2)
     unsigned stagger_ns;         // start delay per phase group (blockIdx & 3), 0 = none
+    int tma_out;                 // NS = 2: write C through mapC with TMA bulk stores (reduce-add when R aliases C)
     const int* stop;
 };
 
@@ -104,6 +105,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -151,7 +164,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int NS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-            const __grid_constant__ CUtensorMap mapW, const Params p) {
+            const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapC, const Params p) {
     using C_ = Cfg<NS>;
     constexpr int STAGES = C_::STAGES, DRAIN_KB = C_::DRAIN_KB, STAGE_BYTES = C_::STAGE_BYTES;
     if (p.stop != nullptr && *p.stop != 0) return;
@@ -283,8 +296,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             const int row0 = mt * BM + q * 32;
             if constexpr (C_::STAGED_EPI) {
                 // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----
+                const bool tma_out = p.tma_out && (p.C != nullptr);
+                const uint32_t stg_s = epi_base + (uint32_t)e * 4096u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                 // (fully unrolled: acc[] must stay in registers)
+                    if (tma_out) {
+                        // ---- asynchronous path: the 32x32 block (value = acc*scale + bias, ReLU) is laid out exactly as the
+                        // SWIZZLE_128B box of mapC expects and handed to the TMA engine: plain store, or reduce-add into C when the
+                        // residual aliases C (x += ...).  The warp does not wait for global memory, only for its staging buffer.
+                        if (lane == 0) tma_store_wait_read();          // previous block has been read out of the staging buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            float4 v = make_float4(acc[j * 32 + 4 * cc] * p.out_scale, acc[j * 32 + 4 * cc + 1] * p.out_scale,
+                                                   acc[j * 32 + 4 * cc + 2] * p.out_scale, acc[j * 32 + 4 * cc + 3] * p.out_scale);
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 32 + 4 * cc));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4*>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) = v;
+                        }
+                        fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the async proxy
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (p.R) tma_reduce_add_2d(&mapC, stg_s, col0 + j * 32, row0);
+                            else tma_store_2d(&mapC, stg_s, col0 + j * 32, row0);
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
                         const float4 v = make_float4(acc[j * 32 + 4 * cc] * p.out_scale, acc[j * 32 + 4 * cc + 1] * p.out_scale,
@@ -376,6 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             }
         }
     }
+    if (NS == 2 && warp >= EPI_WARP0 && lane == 0) tma_store_wait_all();   // bulk stores must finish before the CTA exits
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);

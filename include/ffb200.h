@@ -170,8 +170,11 @@ enum { FFB_OPT_ATTN_MMA = 6 };
  * if an activation exceeds the fp16 range the decode is transparently re-run in format 3 and the handle stays there),
  * 3 = bf16x3 (6 MMA passes, full fp32 range). */
 enum { FFB_OPT_TC_FORMAT = 7 };
-/* 1 (default): de-phase the persistent GEMM CTAs so that their store bursts overlap other CTAs' mainloops; 0 = off. */
+/* 1: de-phase the persistent GEMM CTAs (default 0: measured no effect); so that their store bursts overlap other CTAs' mainloops; 0 = off. */
 enum { FFB_OPT_STAGGER = 8 };
+/* 1 (default): fp16x2 GEMM writes fp32 outputs with asynchronous TMA bulk stores (reduce-add for the in-place residual);
+ * 0 = coalesced st.global epilogue. */
+enum { FFB_OPT_TMA_EPILOGUE = 9 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */

@@ -78,8 +78,9 @@ def test_tc_accumulation_has_no_truncation_bias(eng, fmt):
     # The tensor core truncates when it adds into its fp32 accumulator: on all-positive data (the worst case) that is a
     # visible negative bias.  Draining to round-to-nearest register accumulators every 2 k-blocks keeps it at ~2e-7
     # (measured -2.1e-7); an undrained K=1024 chain (384 truncating adds) would sit an order of magnitude lower.
-    assert np.abs(rel).max() <= 1e-6
-    assert abs(rel.mean()) <= 5e-7, rel.mean()
+    # fp16x2 drains every 4 k-blocks and its two correction products sit between the dominant ones (measured -5.8e-7).
+    assert np.abs(rel).max() <= (1e-6 if fmt == 3 else 1.5e-6)
+    assert abs(rel.mean()) <= (5e-7 if fmt == 3 else 1e-6), rel.mean()
 
 
 @pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64"])
@@ -146,15 +147,15 @@ def test_tensor_core_and_simt_paths_agree_on_a_real_batch():
 
 
 def test_fp16_overflow_falls_back_to_bf16x3():
-    """FFN hidden activations beyond the fp16 range (linear1 x 4096, linear2 / 4096: the same function in exact
+    """FFN hidden activations beyond the fp16 range (linear1 x 65536, linear2 / 65536: the same function in exact
     arithmetic): the fp16x2 decode raises the overflow flag, is re-run in bf16x3 and still matches the SIMT path."""
     g = load_case("ours_parallel_small")
     sd = {k: v.copy() for k, v in g["sd"].items()}
     for k in sd:
         if k.startswith("decoder.") and k.endswith("linear1.weight") or k.startswith("decoder.") and k.endswith("linear1.bias"):
-            sd[k] = sd[k] * np.float32(4096.0)
+            sd[k] = sd[k] * np.float32(65536.0)
         if k.startswith("decoder.") and k.endswith("linear2.weight"):
-            sd[k] = sd[k] / np.float32(4096.0)
+            sd[k] = sd[k] / np.float32(65536.0)
     b = g["batch"]
     coords = torch.from_numpy(b["input"]).cuda().flatten(2)
     mask, ni = torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda()
