@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "attn_mma.cuh"
+#include "attn_f16.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -91,7 +92,9 @@ struct ffb_handle {
     int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
     int opt_tma_out = 1;                          // fp16x2 GEMM: asynchronous TMA store / reduce-add epilogue
     CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
-    int opt_attn_mma = 1;                         // attention core: 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
+    int opt_attn_mma = 2;                         // attention core: 2 = mma.sync fp16x2 kernel (decode, while the GEMM format is fp16x2),
+                                                  // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
+    bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
     int num_sms = 148;
     int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
     int fp16_fallbacks = 0;                       // decodes re-run in bf16x3 because an activation exceeded the fp16 range
@@ -270,8 +273,10 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
     const int qtiles = (max_q_rows + AM_BQ - 1) / AM_BQ;
     if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
     dim3 grid(G, h->H, qtiles);
+    const bool f16 = h->opt_attn_mma == 2 && h->tc_fmt == 2 && h->attn_allow_f16;
     prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
-    attn_mma_kernel<<<grid, 128, AM_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
+    if (f16) attn_f16_kernel<<<grid, 128, AF_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
+    else attn_mma_kernel<<<grid, 128, AM_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -800,6 +805,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
         return fail(nullptr, FFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libffb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
     e = cudaFuncSetAttribute(attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_f16_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
@@ -856,7 +863,9 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             return FFB_OK;
         case FFB_OPT_STAGGER: h->opt_stagger = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TMA_EPILOGUE: h->opt_tma_out = value ? 1 : 0; return FFB_OK;
-        case FFB_OPT_ATTN_MMA: h->opt_attn_mma = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_ATTN_MMA:
+            if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
+            h->opt_attn_mma = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -925,7 +934,10 @@ int ffb_encode(ffb_handle* h, const float* coords, const uint8_t* pad_mask, cons
         CU(h, cudaMemcpyAsync(h->d_coords.p, coords, bytes, cudaMemcpyHostToDevice, s));
         coords_dev = h->d_coords.as<float>();
     }
-    FFB_TRY(run_encoder(h, coords_dev, s));
+    h->attn_allow_f16 = false;
+    const int enc_rc = run_encoder(h, coords_dev, s);
+    h->attn_allow_f16 = true;
+    FFB_TRY(enc_rc);
     if (h->opt_timing) CU(h, cudaEventRecord(h->ev[1], s));
     h->encoded = true;
     return FFB_OK;
@@ -1216,15 +1228,16 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
     if (H != h->H) return fail(h, FFB_ERR_ARG, "op_attention: H must equal the handle's num_head");
     FFB_TRY(set_device(h));
     cudaStream_t s = (cudaStream_t)stream;
-    const int saved = h->opt_attn_mma;
-    h->opt_attn_mma = (kind == 2) ? 1 : 0;
+    const int saved = h->opt_attn_mma, saved_fmt = h->tc_fmt;
+    h->opt_attn_mma = (kind == 2) ? 1 : (kind == 3) ? 2 : 0;
+    if (kind == 3) h->tc_fmt = 2;
     int rc;
     if (kind == 0) rc = launch_attn_rows(h, q, ldq, k, v, ldk, out, H * 64, G, nq, nk, nq, 0, nk, nq, nullptr, s);
     else {
         AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
         rc = launch_attn_tiled(h, q, ldq, k, v, ldk, out, H * 64, g, G, nq, (double)G * nq * nk, nullptr, s);
     }
-    h->opt_attn_mma = saved;
+    h->opt_attn_mma = saved; h->tc_fmt = saved_fmt;
     return rc;
 }
 

@@ -725,15 +725,19 @@ __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
         }
         s = warp_sum(s);
         if (a.logits && lane == 0) a.logits[(size_t)b * a.L + j] = s;
-        if (s > bv) { bv = s; bi = j; }                    // strictly greater: first max within this warp's rows
+        // strictly greater: first max within this warp's rows; like torch.argmax a NaN counts as the maximum (first NaN wins)
+        if (bi == 0x7fffffff || s > bv || (s != s && bv == bv)) { bv = s; bi = j; }
     }
     if (a.logits) for (int j = vl + tid; j < a.L; j += 256) a.logits[(size_t)b * a.L + j] = -FLT_MAX;   // finfo.min
     if (lane == 0) { bestv[w] = bv; besti[w] = bi; }
     __syncthreads();
     if (tid == 0) {
         float v = bestv[0]; int idx = besti[0];
-        for (int k = 1; k < 8; ++k)
-            if (bestv[k] > v || (bestv[k] == v && besti[k] < idx)) { v = bestv[k]; idx = besti[k]; }
+        for (int k = 1; k < 8; ++k) {
+            if (besti[k] == 0x7fffffff) continue;                  // this warp had no rows
+            const bool vn = (v != v), kn = (bestv[k] != bestv[k]);
+            if ((kn && (!vn || besti[k] < idx)) || (!vn && !kn && (bestv[k] > v || (bestv[k] == v && besti[k] < idx)))) { v = bestv[k]; idx = besti[k]; }
+        }
         if (a.tok_out) {
             a.tok_out[b] = idx;
             if (a.nonstop_count && idx >= a.num_token) atomicAdd(a.nonstop_count, 1);

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libffb200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ffb200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh", "attn_mma.cuh")] + \
+HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh", "attn_mma.cuh", "attn_f16.cuh")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
 
 FFB_ABI_VERSION = 1

@@ -164,7 +164,9 @@ int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops,
 /* Tensor-core path selection for the decode-step linear layers (gemm_tc.cuh: bf16x3 split-precision tcgen05 GEMM):
  * 0 = off (fp32 SIMT everywhere), 1 = auto (default: steps with >= 2048 token rows), 2 = force (every step). */
 enum { FFB_OPT_TENSOR_CORE = 5 };
-/* Attention core: 1 (default) = tensor-pipe kernel (mma.sync m16n8k8, 3xTF32 split, attn_mma.cuh); 0 = fp32 SIMT kernels. */
+/* Attention core of the decode loop: 2 (default) = mma.sync m16n8k16 fp16x2 split (attn_f16.cuh; used while the GEMM operand
+ * format is fp16x2, same overflow fallback), 1 = mma.sync m16n8k8 3xTF32 split (attn_mma.cuh; also what the encoder uses),
+ * 0 = fp32 SIMT kernels. */
 enum { FFB_OPT_ATTN_MMA = 6 };
 /* Operand format of the tensor-core GEMM: 2 (default) = fp16x2 (3 MMA passes; weights pre-scaled by a power of two;
  * if an activation exceeds the fp16 range the decode is transparently re-run in format 3 and the handle stays there),
@@ -188,7 +190,7 @@ int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const fl
                      float* y, int32_t M, int32_t E, void* stream);
 /* Multi-head attention core (softmax(q k^T / 8) v) for G equal-sized groups:
  * q [G*nq, ldq], k/v [G*nk, ldk] with head h in columns [64h, 64h+64); out [G*nq, H*64].
- * kind 0 = SIMT warp-per-row kernel, 1 = SIMT tiled kernel, 2 = tensor-pipe kernel (3xTF32 mma.sync).  */
+ * kind 0 = SIMT warp-per-row kernel, 1 = SIMT tiled kernel, 2 = 3xTF32 mma.sync kernel, 3 = fp16x2 mma.sync kernel.  */
 int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k,
                      const float* v, int32_t ldk, float* out, int32_t G, int32_t nq, int32_t nk,
                      int32_t H, void* stream);

@@ -79,7 +79,7 @@ def _attn_ref(q, k, v, G, nq, nk, H):
     return out
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
 @pytest.mark.parametrize("G,nq,nk", [(3, 1, 1), (5, 7, 7), (4, 36, 36), (2, 37, 37), (2, 70, 70), (3, 64, 220),
                                      (2, 130, 65), (1, 258, 258), (2, 5, 516)])
 def test_attention(eng, kind, G, nq, nk):
