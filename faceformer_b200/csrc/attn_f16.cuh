@@ -5,15 +5,15 @@
 // Same contract as attn_mma.cuh (3xTF32), half the tensor work: every fp32 operand x is carried as two halves
 // x = h + l (h = RN_f16(x), l = RN_f16(x - h), exact to 2^-22 in fp16's normal range) and every product as
 // h*h + (l*h + h*l) -- 3 MMAs per 16-wide k-step instead of 6 per two 8-wide ones.  The split is done ONCE per tile
-// while staging into shared memory (Q is pre-scaled by 1/8, exact).  |x| > 65504 raises the shared overflow flag
+// while staging into shared memory (the 1/8 score scale is applied to the fp32 scores, exact).  |x| > 65504 raises the shared overflow flag
 // (the host then re-runs the decode with the TF32 attention kernel and the bf16x3 GEMM).
 //
 // Shared-memory layouts are permuted so that every fragment is two conflict-free LDS.128:
 //   * head dim d of Q/K rows is stored at column 16*t + 4*s + 2*j + e  with  d = 16*s + 8*j + 2*t + e
 //     (s = k-step, t = thread-in-quad, j = low/high k-half, e = element of the pair): thread t owns 16 contiguous halves;
-//   * V is staged TRANSPOSED ([head dim][key]) with the same permutation applied to the key index, so the B fragment
-//     of P.V is contiguous too, and the S accumulators of key blocks 2s, 2s+1 ARE the A fragment of k-step s;
-//   * output column n of tile u is head dim 16*(n/2) + 2*u + (n%2): a thread ends up with 16 contiguous outputs.
+//   * V is staged row-major ([key][head dim]); ldmatrix.x4.trans delivers the (key-pair, head-dim) B fragments of P.V
+//     (row stride 144 B: conflict-free), and the S accumulators of key blocks 2s, 2s+1 ARE the A fragment of k-step s;
+//   * two lanes of a quad swap one pair per tile pair at the end, so every lane stores 4 contiguous outputs.
 #pragma once
 #include "kernels.cuh"
 
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
     extern __shared__ __align__(16) uint16_t smem_h[];
     uint16_t* Qh = smem_h;              uint16_t* Ql = smem_h + AF_TILE;
     uint16_t* Kh = smem_h + 2 * AF_TILE; uint16_t* Kl = smem_h + 3 * AF_TILE;
-    uint16_t* Vh = smem_h + 4 * AF_TILE; uint16_t* Vl = smem_h + 5 * AF_TILE;     // [head dim][permuted key]
+    uint16_t* Vh = smem_h + 4 * AF_TILE; uint16_t* Vl = smem_h + 5 * AF_TILE;     // [key][head dim]
 
     long long q0, k0, o0; int nq, nk;
     attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
@@ -62,14 +62,13 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
     const int gq = lane >> 2, t = lane & 3;
     bool ovf = false;
 
-    // ---- stage Q (x 1/8) as hi/lo halves, head dim permuted; rows beyond nqt are zero (only up to the last active warp) ----
+    // ---- stage Q as hi/lo halves (the 1/8 score scale is applied after the MMAs: exact), head dim permuted; rows beyond nqt are zero (only up to the last active warp) ----
     const int q_rows = min(AF_BQ, (nqt + 15) & ~15);
     for (int idx = tid; idx < q_rows * 16; idx += 128) {
         const int r = idx >> 4, d4 = idx & 15;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nqt) {
             v = *reinterpret_cast<const float4*>(Q + (size_t)(q0 + qt0 + r) * ldq + head * 64 + d4 * 4);
-            v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
         }
         ovf |= !(fabsf(v.x) <= 65504.f) | !(fabsf(v.y) <= 65504.f) | !(fabsf(v.z) <= 65504.f) | !(fabsf(v.w) <= 65504.f);
         uint32_t h0, l0, h1, l1;
@@ -121,15 +120,9 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
             const int c0 = af_perm(d4 * 4), c1 = af_perm(d4 * 4 + 2);
             *reinterpret_cast<uint32_t*>(Kh + r * AF_S + c0) = h0; *reinterpret_cast<uint32_t*>(Kl + r * AF_S + c0) = l0;
             *reinterpret_cast<uint32_t*>(Kh + r * AF_S + c1) = h1; *reinterpret_cast<uint32_t*>(Kl + r * AF_S + c1) = l1;
-            // V transposed: element (key r, head dim d) -> Vt[d][perm(r)]
-            const int kc = af_perm(r);
-            const float ve[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const __half hh = __float2half_rn(ve[i]);
-                Vh[(d4 * 4 + i) * AF_S + kc] = __half_as_ushort(hh);
-                Vl[(d4 * 4 + i) * AF_S + kc] = __half_as_ushort(__float2half_rn(ve[i] - __half2float(hh)));
-            }
+            split_pair(vv.x, vv.y, h0, l0); split_pair(vv.z, vv.w, h1, l1);          // V row-major, natural head-dim order
+            *reinterpret_cast<uint2*>(Vh + r * AF_S + d4 * 4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Vl + r * AF_S + d4 * 4) = make_uint2(l0, l1);
         }
         __syncthreads();
         if (!warp_active) continue;
@@ -150,8 +143,8 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
                     mma_f16(sc, ql[2 * half + 1], kh.z, kh.w); mma_f16(sc, qh[2 * half + 1], kl.z, kl.w); mma_f16(sm, qh[2 * half + 1], kh.z, kh.w);
                 }
                 const int key = kt + 8 * j + 2 * t;
-                s[j][0] = (key < nk) ? sm[0] + sc[0] : -INFINITY; s[j][1] = (key + 1 < nk) ? sm[1] + sc[1] : -INFINITY;
-                s[j][2] = (key < nk) ? sm[2] + sc[2] : -INFINITY; s[j][3] = (key + 1 < nk) ? sm[3] + sc[3] : -INFINITY;
+                s[j][0] = (key < nk) ? (sm[0] + sc[0]) * 0.125f : -INFINITY; s[j][1] = (key + 1 < nk) ? (sm[1] + sc[1]) * 0.125f : -INFINITY;
+                s[j][2] = (key < nk) ? (sm[2] + sc[2]) * 0.125f : -INFINITY; s[j][3] = (key + 1 < nk) ? (sm[3] + sc[3]) * 0.125f : -INFINITY;
             } else {
                 s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY;
             }
@@ -180,23 +173,26 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
         float om[8][4];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { om[u][0] = om[u][1] = om[u][2] = om[u][3] = 0.f; }
+        // ldmatrix.x4.trans lane addressing: matrices (m0,m1) = keys 16ks + {0..7, 8..15} of head-dim block 8*(2up), (m2,m3) = same keys of
+        // block 8*(2up+1); lane l supplies row (l & 7) of matrix (l >> 3).  Transposed, matrix m0/m1 are (b0, b1) of tile 2up, m2/m3 of tile 2up+1.
+        const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_col = (lane >> 4) * 8;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {                           // one LDS.128 per operand covers k-steps 2*half, 2*half+1
-            if (2 * half < smax) {
-                const bool second = (2 * half + 1) < smax;
-                uint32_t pa0[4], pl0[4], pa1[4], pl1[4];                 // A fragment of k-step ks = S accumulators of key blocks 2ks, 2ks+1
-                split_pair(s[4 * half][0], s[4 * half][1], pa0[0], pl0[0]); split_pair(s[4 * half][2], s[4 * half][3], pa0[1], pl0[1]);
-                split_pair(s[4 * half + 1][0], s[4 * half + 1][1], pa0[2], pl0[2]); split_pair(s[4 * half + 1][2], s[4 * half + 1][3], pa0[3], pl0[3]);
-                split_pair(s[4 * half + 2][0], s[4 * half + 2][1], pa1[0], pl1[0]); split_pair(s[4 * half + 2][2], s[4 * half + 2][3], pa1[1], pl1[1]);
-                split_pair(s[4 * half + 3][0], s[4 * half + 3][1], pa1[2], pl1[2]); split_pair(s[4 * half + 3][2], s[4 * half + 3][3], pa1[3], pl1[3]);
+        for (int ks = 0; ks < 4; ++ks) {
+            if (ks < smax) {
+                uint32_t pa[4], pl[4];                                   // A fragment = S accumulators of key blocks 2ks, 2ks+1
+                split_pair(s[2 * ks][0], s[2 * ks][1], pa[0], pl[0]); split_pair(s[2 * ks][2], s[2 * ks][3], pa[1], pl[1]);
+                split_pair(s[2 * ks + 1][0], s[2 * ks + 1][1], pa[2], pl[2]); split_pair(s[2 * ks + 1][2], s[2 * ks + 1][3], pa[3], pl[3]);
+                const uint32_t vh_addr = (uint32_t)__cvta_generic_to_shared(Vh + (16 * ks + lm_row) * AF_S + lm_col);
+                const uint32_t vl_addr = (uint32_t)__cvta_generic_to_shared(Vl + (16 * ks + lm_row) * AF_S + lm_col);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    // output tile u, fragment column n = gq <-> head dim 8u + gq.  This thread's run of permuted keys [16t, 16t+16):
-                    // word 2ks = slots (2t, 2t+1) of k-step ks, word 2ks+1 = slots (2t+8, 2t+9).
-                    const uint4 vh = *reinterpret_cast<const uint4*>(Vh + (8 * u + gq) * AF_S + 16 * t + 8 * half);
-                    const uint4 vl = *reinterpret_cast<const uint4*>(Vl + (8 * u + gq) * AF_S + 16 * t + 8 * half);
-                    mma_f16(om[u], pl0, vh.x, vh.y); mma_f16(om[u], pa0, vl.x, vl.y); mma_f16(om[u], pa0, vh.x, vh.y);
-                    if (second) { mma_f16(om[u], pl1, vh.z, vh.w); mma_f16(om[u], pa1, vl.z, vl.w); mma_f16(om[u], pa1, vh.z, vh.w); }
+                for (int up = 0; up < 4; ++up) {                         // output tiles 2up, 2up+1 (head dims 16up .. 16up+15)
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(vh_addr + up * 32));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(vl_addr + up * 32));
+                    mma_f16(om[2 * up], pl, h0, h1); mma_f16(om[2 * up], pa, l0, l1); mma_f16(om[2 * up], pa, h0, h1);
+                    mma_f16(om[2 * up + 1], pl, h2, h3); mma_f16(om[2 * up + 1], pa, l2, l3); mma_f16(om[2 * up + 1], pa, h2, h3);
                 }
             }
         }
