@@ -179,9 +179,13 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             if (ks < smax) {
-                uint32_t pa[4], pl[4];                                   // A fragment = S accumulators of key blocks 2ks, 2ks+1
-                split_pair(s[2 * ks][0], s[2 * ks][1], pa[0], pl[0]); split_pair(s[2 * ks][2], s[2 * ks][3], pa[1], pl[1]);
-                split_pair(s[2 * ks + 1][0], s[2 * ks + 1][1], pa[2], pl[2]); split_pair(s[2 * ks + 1][2], s[2 * ks + 1][3], pa[3], pl[3]);
+                // A fragment = S accumulators of key blocks 2ks, 2ks+1.  Probabilities are mostly << 1/8, where the low half of the
+                // split would be subnormal in fp16: split 4096*p instead (exact power of two, undone on O_tile below).
+                uint32_t pa[4], pl[4];
+                split_pair(s[2 * ks][0] * 4096.f, s[2 * ks][1] * 4096.f, pa[0], pl[0]);
+                split_pair(s[2 * ks][2] * 4096.f, s[2 * ks][3] * 4096.f, pa[1], pl[1]);
+                split_pair(s[2 * ks + 1][0] * 4096.f, s[2 * ks + 1][1] * 4096.f, pa[2], pl[2]);
+                split_pair(s[2 * ks + 1][2] * 4096.f, s[2 * ks + 1][3] * 4096.f, pa[3], pl[3]);
                 const uint32_t vh_addr = (uint32_t)__cvta_generic_to_shared(Vh + (16 * ks + lm_row) * AF_S + lm_col);
                 const uint32_t vl_addr = (uint32_t)__cvta_generic_to_shared(Vl + (16 * ks + lm_row) * AF_S + lm_col);
 #pragma unroll
@@ -198,8 +202,9 @@ __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restric
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            o[u][0] = o[u][0] * corr0 + om[u][0]; o[u][1] = o[u][1] * corr0 + om[u][1];
-            o[u][2] = o[u][2] * corr1 + om[u][2]; o[u][3] = o[u][3] * corr1 + om[u][3];
+            constexpr float kInvP = 1.0f / 4096.f;
+            o[u][0] = o[u][0] * corr0 + om[u][0] * kInvP; o[u][1] = o[u][1] * corr0 + om[u][1] * kInvP;
+            o[u][2] = o[u][2] * corr1 + om[u][2] * kInvP; o[u][3] = o[u][3] * corr1 + om[u][3] * kInvP;
         }
     }
     if (ovf && g.overflow) *g.overflow = 1;

@@ -1,0 +1,191 @@
+// attn_h.cuh -- attention core whose inputs ARRIVE as fp16x2 splits (the tensor-core GEMM epilogue writes q, k, v that way;
+// the cross-attention K/V cache is split once per wireframe at encode time).
+//
+// Same arithmetic as attn_f16.cuh (hi*hi + lo*hi + hi*lo on mma.sync m16n8k16, fp32 accumulate, online softmax, P scaled
+// by 4096 before its split, O_tile merged in fp32), but with ZERO operand-formatting work in the kernel:
+//   * staging is a straight 16-byte cp.async copy of the hi and lo rows into natural row-major tiles (zero-filled past the end);
+//   * all fragments come from ldmatrix (A of Q K^T: x4; B of Q K^T: x4 covering two key blocks; B of P V: x4.trans).
+// Row stride 72 halves (144 B) makes every ldmatrix / cp.async conflict-free.
+#pragma once
+#include "attn_f16.cuh"
+
+namespace ffb {
+
+struct AttnHalfIn {
+    const uint16_t* Qh; long long q_split; int ldq;          // lo part at Qh + q_split; row stride ldq halves
+    const uint16_t* Kh; long long k_split;                   // keys
+    const uint16_t* Vh; long long v_split; int ldk;          // values (same row stride as the keys)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;                           // src-size 0: nothing is read, 16 zero bytes are written
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
+                                                        long long os_stride, const AttnGroups g, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    extern __shared__ __align__(16) uint16_t smem_h[];
+    const uint32_t sQh = (uint32_t)__cvta_generic_to_shared(smem_h), sQl = sQh + AF_TILE * 2;
+    const uint32_t sKh = sQh + 2 * AF_TILE * 2, sKl = sQh + 3 * AF_TILE * 2, sVh = sQh + 4 * AF_TILE * 2, sVl = sQh + 5 * AF_TILE * 2;
+
+    long long q0, k0, o0; int nq, nk;
+    attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
+    const int head = blockIdx.y;
+    const int qt0 = blockIdx.z * AF_BQ;
+    if (qt0 >= nq) return;
+    const int nqt = min(AF_BQ, nq - qt0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+
+    // ---- stage Q (hi, lo): 8 chunks of 16 B per row and part ----
+    const int q_rows = min(AF_BQ, (nqt + 15) & ~15);
+    for (int idx = tid; idx < q_rows * 16; idx += 128) {
+        const int r = idx >> 4, c = idx & 7, part = (idx >> 3) & 1;
+        const uint16_t* src = in.Qh + (part ? in.q_split : 0) + (size_t)(q0 + qt0 + min(r, nqt - 1)) * in.ldq + head * 64 + c * 8;
+        cp_async16((part ? sQl : sQh) + (uint32_t)(r * AF_S + c * 8) * 2u, src, r < nqt);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const bool warp_active = (w * 16) < nqt;
+    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_col = (lane >> 4) * 8;       // A-operand / V (trans) lane addressing
+    const int lk_row = (lane & 7) + (lane >> 4) * 8, lk_col = ((lane >> 3) & 1) * 8;       // K (B of Q K^T) lane addressing
+
+    float m0 = -INFINITY, m1 = -INFINITY, l0s = 0.f, l1s = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.f; }
+    uint32_t qh[4][4], ql[4][4];
+
+    for (int kt = 0; kt < nk; kt += AF_BK) {
+        const int nkt = min(AF_BK, nk - kt);
+        const int k_rows = (nkt + 15) & ~15;
+        if (kt > 0) __syncthreads();                                     // previous K/V tile fully consumed
+        for (int idx = tid; idx < k_rows * 32; idx += 128) {
+            const int r = idx >> 5, c = idx & 7, which = (idx >> 3) & 3;    // which: 0 Kh, 1 Kl, 2 Vh, 3 Vl
+            const size_t row = (size_t)(k0 + kt + min(r, nkt - 1)) * in.ldk + head * 64 + c * 8;
+            const uint16_t* src = (which < 2) ? in.Kh + (which & 1 ? in.k_split : 0) + row : in.Vh + (which & 1 ? in.v_split : 0) + row;
+            const uint32_t dst = (which == 0 ? sKh : which == 1 ? sKl : which == 2 ? sVh : sVl) + (uint32_t)(r * AF_S + c * 8) * 2u;
+            cp_async16(dst, src, r < nkt);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (!warp_active) continue;
+        if (kt == 0) {                                                   // A fragments of this warp's 16 query rows, 4 k-steps
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t off = (uint32_t)((w * 16 + lm_row) * AF_S + 16 * ks + lm_col) * 2u;
+                ldsm_x4(sQh + off, qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3]);
+                ldsm_x4(sQl + off, ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
+            }
+        }
+        const int jmax = (nkt + 7) >> 3, smax = (nkt + 15) >> 4;
+
+        // ---- S = Q K^T / 8 ----
+        float s[8][4];
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {                                 // key blocks 2jp, 2jp+1
+            if (2 * jp < jmax) {
+                float sm0[4] = {0.f, 0.f, 0.f, 0.f}, sc0[4] = {0.f, 0.f, 0.f, 0.f}, sm1[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t off = (uint32_t)((16 * jp + lk_row) * AF_S + 16 * ks + lk_col) * 2u;
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;              // (b0,b1) of block 2jp, (b0,b1) of block 2jp+1
+                    ldsm_x4(sKh + off, h0, h1, h2, h3);
+                    ldsm_x4(sKl + off, l0, l1, l2, l3);
+                    mma_f16(sc0, ql[ks], h0, h1); mma_f16(sc0, qh[ks], l0, l1); mma_f16(sm0, qh[ks], h0, h1);
+                    mma_f16(sc1, ql[ks], h2, h3); mma_f16(sc1, qh[ks], l2, l3); mma_f16(sm1, qh[ks], h2, h3);
+                }
+                const int key = kt + 16 * jp + 2 * t;
+                s[2 * jp][0] = (key < nk) ? (sm0[0] + sc0[0]) * 0.125f : -INFINITY; s[2 * jp][1] = (key + 1 < nk) ? (sm0[1] + sc0[1]) * 0.125f : -INFINITY;
+                s[2 * jp][2] = (key < nk) ? (sm0[2] + sc0[2]) * 0.125f : -INFINITY; s[2 * jp][3] = (key + 1 < nk) ? (sm0[3] + sc0[3]) * 0.125f : -INFINITY;
+                s[2 * jp + 1][0] = (key + 8 < nk) ? (sm1[0] + sc1[0]) * 0.125f : -INFINITY; s[2 * jp + 1][1] = (key + 9 < nk) ? (sm1[1] + sc1[1]) * 0.125f : -INFINITY;
+                s[2 * jp + 1][2] = (key + 8 < nk) ? (sm1[2] + sc1[2]) * 0.125f : -INFINITY; s[2 * jp + 1][3] = (key + 9 < nk) ? (sm1[3] + sc1[3]) * 0.125f : -INFINITY;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s[2 * jp][i] = -INFINITY; s[2 * jp + 1][i] = -INFINITY; }
+            }
+        }
+        // ---- online softmax ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3])); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = expf(s[j][0] - mn0); s[j][1] = expf(s[j][1] - mn0);
+            s[j][2] = expf(s[j][2] - mn1); s[j][3] = expf(s[j][3] - mn1);
+            ps0 += s[j][0] + s[j][1]; ps1 += s[j][2] + s[j][3];
+        }
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+        ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+        l0s = l0s * corr0 + ps0; l1s = l1s * corr1 + ps1;
+        m0 = mn0; m1 = mn1;
+
+        // ---- O_tile = (4096 P) V from zero, then O = O * corr + O_tile / 4096 in fp32 ----
+        float om[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { om[u][0] = om[u][1] = om[u][2] = om[u][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            if (ks < smax) {
+                uint32_t pa[4], pl[4];
+                split_pair(s[2 * ks][0] * 4096.f, s[2 * ks][1] * 4096.f, pa[0], pl[0]);
+                split_pair(s[2 * ks][2] * 4096.f, s[2 * ks][3] * 4096.f, pa[1], pl[1]);
+                split_pair(s[2 * ks + 1][0] * 4096.f, s[2 * ks + 1][1] * 4096.f, pa[2], pl[2]);
+                split_pair(s[2 * ks + 1][2] * 4096.f, s[2 * ks + 1][3] * 4096.f, pa[3], pl[3]);
+                const uint32_t voff = (uint32_t)((16 * ks + lm_row) * AF_S + lm_col) * 2u;
+#pragma unroll
+                for (int up = 0; up < 4; ++up) {
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    ldsm_x4_t(sVh + voff + up * 32, h0, h1, h2, h3);
+                    ldsm_x4_t(sVl + voff + up * 32, l0, l1, l2, l3);
+                    mma_f16(om[2 * up], pl, h0, h1); mma_f16(om[2 * up], pa, l0, l1); mma_f16(om[2 * up], pa, h0, h1);
+                    mma_f16(om[2 * up + 1], pl, h2, h3); mma_f16(om[2 * up + 1], pa, l2, l3); mma_f16(om[2 * up + 1], pa, h2, h3);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            constexpr float kInvP = 1.0f / 4096.f;
+            o[u][0] = o[u][0] * corr0 + om[u][0] * kInvP; o[u][1] = o[u][1] * corr0 + om[u][1] * kInvP;
+            o[u][2] = o[u][2] * corr1 + om[u][2] * kInvP; o[u][3] = o[u][3] * corr1 + om[u][3] * kInvP;
+        }
+    }
+    if (!warp_active) return;
+
+    const float inv0 = 1.0f / l0s, inv1 = 1.0f / l1s;
+    const bool odd = (t & 1) != 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int r = w * 16 + gq + half * 8;
+        const float inv = half ? inv1 : inv0;
+        const int e = half * 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float a0 = o[2 * c][e] * inv, a1 = o[2 * c][e + 1] * inv, b0 = o[2 * c + 1][e] * inv, b1 = o[2 * c + 1][e + 1] * inv;
+            const float s0 = odd ? a0 : b0, s1 = odd ? a1 : b1;
+            const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            const float4 v = odd ? make_float4(r0, r1, b0, b1) : make_float4(a0, a1, r0, r1);
+            const int d = odd ? (8 * (2 * c + 1) + 2 * (t - 1)) : (8 * (2 * c) + 2 * t);
+            if (r < nqt) {
+                const size_t off = (size_t)(o0 + qt0 + r) * ldo + head * 64 + d;
+                if (Os == nullptr) *reinterpret_cast<float4*>(O + off) = v;
+                else store_split4(Os + off, os_stride, v, g.split_fmt, g.overflow);
+            }
+        }
+    }
+}
+
+}  // namespace ffb

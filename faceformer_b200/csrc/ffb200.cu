@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "attn_mma.cuh"
 #include "attn_f16.cuh"
+#include "attn_h.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -92,6 +93,11 @@ struct ffb_handle {
     int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
     int opt_tma_out = 1;                          // fp16x2 GEMM: asynchronous TMA store / reduce-add epilogue
     CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
+    CUtensorMap ms_h;                             // fp16x2 split STORE map of a_h (FFN hidden)
+    // "half pipeline" (fp16x2 GEMM + fp16x2 attention): q,k,v and the cross-attention query never exist in fp32
+    DevBuf a_qkv, a_qc, kc_h, vc_h;               // [2][cap][3E], [2][cap][E], [2][R][Ld*E] halves
+    CUtensorMap ms_qkv, ms_qc;
+    bool half_pipe = false;                       // set per batch at plan time
     int opt_attn_mma = 2;                         // attention core: 2 = mma.sync fp16x2 kernel (decode, while the GEMM format is fp16x2),
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
@@ -283,6 +289,21 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
     return FFB_OK;
 }
 
+int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long os_stride, AttnGroups g, int G, int max_q_rows,
+                  double qk_pairs, int prof_class, const int* stop, cudaStream_t s, float* O = nullptr) {
+    if (G <= 0 || max_q_rows <= 0) return FFB_OK;
+    const int qtiles = (max_q_rows + AF_BQ - 1) / AF_BQ;
+    if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
+    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
+    dim3 grid(G, h->H, qtiles);
+    prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
+    attn_h_kernel<<<grid, 128, AF_SMEM_BYTES, s>>>(in, O, h->E, Os, os_stride, g, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
 int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                       const AttnGroups& g_in, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
                       uint16_t* Os = nullptr, long long os_stride = 0) {
@@ -335,6 +356,19 @@ int encode_output_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, ui
     return FFB_OK;
 }
 
+// fp16x2 split buffer [2][rows][ld] -> 3-D STORE map (col, row, split), box 32 x 32 x 1 halves, SWIZZLE_64B
+int encode_split_store_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint64_t rows) {
+    if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {ld, rows, 2};
+    const cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(split store) failed with CUresult %d", (int)r);
+    return FFB_OK;
+}
+
 struct TcLin {
     const CUtensorMap* A0 = nullptr; const CUtensorMap* A1 = nullptr; int n_switch = 1 << 30;
     const CUtensorMap* W = nullptr; float w_scale = 1.f; const float* bias = nullptr;
@@ -359,7 +393,7 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     if (h->opt_stagger && tiles >= 4 * grid) p.stagger_ns = (unsigned)((l.K / tc::BK) * 130 * (h->tc_fmt == 2 ? 3 : 6) / 4);
     prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
     // TMA epilogue: only when the residual (if any) is the in-place form C += ..., which a reduce-add expresses exactly
-    p.tma_out = (h->opt_tma_out && h->tc_fmt == 2 && l.Cmap && l.C && (!l.R || (l.R == l.C && l.ldr == l.ldc))) ? 1 : 0;
+    p.tma_out = (h->opt_tma_out && h->tc_fmt == 2 && l.Cmap && ((l.C && (!l.R || (l.R == l.C && l.ldr == l.ldc))) || (!l.C && l.Cs))) ? 1 : 0;
     const CUtensorMap& mc = l.Cmap ? *l.Cmap : *l.W;
     if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
     else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
@@ -541,6 +575,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     }
     h->h_seq_off[N] = (int)seq_wf.size();
     h->B = (long long)seq_wf.size();
+    h->half_pipe = false;
     h->sum_seq_vlen = 0; h->sum_vlen2 = 0;
     for (int i = 0; i < N; ++i) {
         h->sum_seq_vlen += (double)(h->h_seq_off[i + 1] - h->h_seq_off[i]) * h->h_vlen[i];
@@ -592,6 +627,14 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         FFB_TRY(encode_output_map(h, &h->mc_qkv3, h->qkv.p, 3 * E, rows));
         FFB_TRY(encode_output_map(h, &h->mc_qkv1, h->qkv.p, E, rows));
         FFB_TRY(encode_output_map(h, &h->mc_att, h->att.p, E, rows));
+        FFB_TRY(encode_split_store_map(h, &h->ms_h, h->a_h.p, FF, cr));
+        h->half_pipe = (h->tc_fmt == 2 && h->opt_attn_mma == 2 && h->opt_tma_out);
+        if (h->half_pipe) {
+            CU(h, h->a_qkv.ensure(2 * cr * 3 * E * 2)); CU(h, h->a_qc.ensure(2 * cr * E * 2));
+            CU(h, h->kc_h.ensure(2 * (size_t)R * h->Ld * E * 2)); CU(h, h->vc_h.ensure(2 * (size_t)R * h->Ld * E * 2));
+            FFB_TRY(encode_split_store_map(h, &h->ms_qkv, h->a_qkv.p, 3 * E, cr));
+            FFB_TRY(encode_split_store_map(h, &h->ms_qc, h->a_qc.p, E, cr));
+        }
     }
     return FFB_OK;
 }
@@ -637,6 +680,13 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
       l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = LdE; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
     { Lin l; l.A = mem; l.lda = E; l.W = w.cvw; l.ldw = E; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
       l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    if (h->half_pipe) {      // fp16x2 copy of the cache for the half pipeline's cross-attention (overflow -> state[5], checked after the decode)
+        const long long n4 = (long long)R * LdE / 4;
+        CU(h, cudaMemsetAsync(h->state.as<int>() + 5, 0, sizeof(int), s));
+        split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
+        split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
+        h->launches += 2; CU(h, cudaGetLastError());
+    }
     return FFB_OK;
 }
 
@@ -665,6 +715,8 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     const bool tc = h->tc_ok && h->opt_tc && TS.ready && (int)TS.layers.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS);
     uint16_t* ax2 = h->a_x2.as<uint16_t>(); uint16_t* ax2p = h->a_x2p.as<uint16_t>();
     uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>();
+    uint16_t* aqkv = h->a_qkv.as<uint16_t>(); uint16_t* aqc = h->a_qc.as<uint16_t>();
+    const bool hp = h->half_pipe && h->tc_fmt == 2;      // q,k,v / cross-q produced and consumed as fp16x2 (no fp32 copy)
     const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the bf16x3 splits
     for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
         const DecLayerW& Lw = w.dec[li];
@@ -712,13 +764,25 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             const ffb_handle::DecTcW& Tw = TS.layers[li];
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
             { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
-              l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E; l.Cmap = &h->mc_qkv3; l.M = M; l.N = 3 * E; l.K = E;
+              l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = M; l.N = 3 * E; l.K = E;
+              if (hp) { l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv; }   // q,k,v straight to fp16x2
+              else { l.C = qkv; l.ldc = 3 * E; l.Cmap = &h->mc_qkv3; }
               FFB_TRY(launch_tc(h, l, stop, s)); }
             if (!last) {
+                if (hp) {
+                    AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
+                    AttnGroups g{}; g.ragged = 0; g.nq = P; g.nk = P; g.q_stride = P; g.q_off = 0; g.k_stride = P; g.o_stride = P;
+                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, P, (double)B * P * P, PC_ATTN_ROWS, stop, s));
+                } else
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
                 { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E; l.Cmap = &h->mc_x;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             } else {
+                if (hp) {
+                    AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
+                    AttnGroups g{}; g.ragged = 0; g.nq = 1; g.nk = P; g.q_stride = P; g.q_off = P - 1; g.k_stride = P; g.o_stride = 1;
+                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, 1, (double)B * P, PC_ATTN_ROWS, stop, s));
+                } else
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
                 copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
@@ -727,15 +791,22 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                 cur = xl; rows = B; Pq = 1;
             }
             FFB_TRY(launch_ln_split(h, cur, Lw.n2w, Lw.n2b, nullptr, ax2p, ssE, qpos_cross, qmod_cross, rows, E, stop, s));
-            { TcLin l; l.A0 = &TS.m_x2p; l.W = &Tw.ca_q; l.w_scale = Tw.s_ca_q; l.bias = Lw.ca.in_b; l.C = qkv; l.ldc = E; l.Cmap = &h->mc_qkv1; l.M = rows; l.N = E; l.K = E;
+            { TcLin l; l.A0 = &TS.m_x2p; l.W = &Tw.ca_q; l.w_scale = Tw.s_ca_q; l.bias = Lw.ca.in_b; l.M = rows; l.N = E; l.K = E;
+              if (hp) { l.Cs = aqc; l.cs_stride = h->cap_rows * E; l.ldcs = E; l.Cmap = &h->ms_qc; }
+              else { l.C = qkv; l.ldc = E; l.Cmap = &h->mc_qkv1; }
               FFB_TRY(launch_tc(h, l, stop, s)); }
             { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
+              if (hp) {
+                  const long long kvs = (long long)h->R * LdE;
+                  AttnHalfIn in{aqc, h->cap_rows * E, E, h->kc_h.as<uint16_t>() + (size_t)li * E, kvs, h->vc_h.as<uint16_t>() + (size_t)li * E, kvs, LdE};
+                  FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, PC_ATTN_TILED, stop, s));
+              } else
               FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
                                         att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s, aatt, ssE)); }
             { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.ca_out; l.w_scale = Tw.s_ca_out; l.bias = Lw.ca.out_b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E; l.Cmap = (cur == x) ? &h->mc_x : &h->mc_xl;
               l.M = rows; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             FFB_TRY(launch_ln_split(h, cur, Lw.n3w, Lw.n3b, ax2, nullptr, ssE, nullptr, 1, rows, E, stop, s));
-            { TcLin l; l.A0 = &TS.m_x2; l.W = &Tw.l1; l.w_scale = Tw.s_l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
+            { TcLin l; l.A0 = &TS.m_x2; l.W = &Tw.l1; l.w_scale = Tw.s_l1; l.bias = Lw.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF; l.Cmap = &h->ms_h;
               l.M = rows; l.N = FF; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             { TcLin l; l.A0 = &TS.m_h; l.W = &Tw.l2; l.w_scale = Tw.s_l2; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E; l.Cmap = (cur == x) ? &h->mc_x : &h->mc_xl;
               l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_tc(h, l, stop, s)); }
@@ -805,6 +876,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
         return fail(nullptr, FFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libffb200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
     e = cudaFuncSetAttribute(attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_tiled): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attn_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_h_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(attn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_f16_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES);
@@ -841,7 +914,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -970,19 +1043,19 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
     }
     const bool syncing = (steps_run != nullptr) || (loc == FFB_HOST);
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
+        CU(h, cudaMemsetAsync(st, 0, 5 * sizeof(int), s));          // [5] = overflow seen while encoding: survives
         init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
         h->launches++; CU(h, cudaGetLastError());
         for (int step = 0; step < T - 1; ++step) FFB_TRY(run_step(h, step + 1, true, s));   // no host sync inside the loop
         expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
         h->launches++; CU(h, cudaGetLastError());
         if (!syncing) break;                      // fully asynchronous call: the overflow flag is left for ffb_overflowed()
-        int host_state[2] = {0, 0};               // executed steps, fp16 overflow flag
+        int host_state[3] = {0, 0, 0};            // executed steps, fp16 overflow flag (decode), fp16 overflow flag (K/V cache split)
         CU(h, cudaMemcpyAsync(&host_state[0], st + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CU(h, cudaMemcpyAsync(&host_state[1], st + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(&host_state[1], st + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         if (steps_run) *steps_run = host_state[0];
-        if (host_state[1] == 0 || h->tc_fmt != 2) break;
+        if ((host_state[1] == 0 && !(h->half_pipe && host_state[2])) || h->tc_fmt != 2) break;
         // an activation left the fp16 range: switch this handle to the bf16x3 operand format (sticky) and decode again
         h->tc_fmt = 3; h->fp16_fallbacks++;
         FFB_TRY(prepare_tc(h, 3, s));
@@ -1080,18 +1153,18 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
             }
     }
     int* st = h->state.as<int>();
-    CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
+    CU(h, cudaMemsetAsync(st, 0, 5 * sizeof(int), s));
     load_prefix_kernel<<<grid1d((long long)P * h->B), 256, 0, s>>>(pdev, h->d_seq_slot.as<int>(), h->tok.as<int>(), P, (int)h->B_full, (int)h->B);
     h->launches++; CU(h, cudaGetLastError());
     for (int attempt = 0; attempt < 2; ++attempt) {
         FFB_TRY(run_step(h, P, false, s));
-        int ovf = 0;
-        CU(h, cudaMemcpyAsync(&ovf, st + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
+        int ovf[2] = {0, 0};
+        CU(h, cudaMemcpyAsync(ovf, st + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
-        if (ovf == 0 || h->tc_fmt != 2) break;
+        if ((ovf[0] == 0 && !(h->half_pipe && ovf[1])) || h->tc_fmt != 2) break;
         h->tc_fmt = 3; h->fp16_fallbacks++;
         FFB_TRY(prepare_tc(h, 3, s));
-        CU(h, cudaMemsetAsync(st, 0, 8 * sizeof(int), s));
+        CU(h, cudaMemsetAsync(st, 0, 5 * sizeof(int), s));
     }
     h->decoded = false;
     return emit_logits(h, logits, loc, s);
@@ -1164,6 +1237,7 @@ int ffb_op_linear_tc(ffb_handle* h, const float* A, const float* W, const float*
         else { l.C = C; l.ldc = N; l.R = R; l.ldr = N; }
         CUtensorMap mC;
         if (!via_split) { if ((rc = encode_output_map(h, &mC, C, N, M)) != FFB_OK) break; l.Cmap = &mC; }
+        else if (fmt == 2) { if ((rc = encode_split_store_map(h, &mC, cs.p, N, Mp)) != FFB_OK) break; l.Cmap = &mC; }
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;
         if (via_split) {
             sum_split_kernel<<<grid1d((long long)M * N), 256, 0, s>>>(cs.as<uint16_t>(), (long long)Mp * N, C, (long long)M * N, fmt);
@@ -1200,6 +1274,7 @@ int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t 
         else if (!(flags & 16)) { l.C = cf.as<float>(); l.ldc = N; if (flags & 2) { l.R = cf.as<float>(); l.ldr = N; } }
         CUtensorMap mC;
         if (l.C) { if ((rc = encode_output_map(h, &mC, cf.p, N, Mp)) != FFB_OK) break; l.Cmap = &mC; }
+        else if (l.Cs && h->tc_fmt == 2) { if ((rc = encode_split_store_map(h, &mC, cs.p, N, Mp)) != FFB_OK) break; l.Cmap = &mC; }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break;          // warm-up
         cudaEventRecord(e0, s);
@@ -1228,6 +1303,27 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
     if (H != h->H) return fail(h, FFB_ERR_ARG, "op_attention: H must equal the handle's num_head");
     FFB_TRY(set_device(h));
     cudaStream_t s = (cudaStream_t)stream;
+    if (kind == 4) {     // inputs converted to fp16x2 first, then the half-input kernel (k and v must share ldk; out is fp32)
+        const size_t nqe = (size_t)G * nq * ldq, nke = (size_t)G * nk * ldk;
+        if (ldq % 4 || ldk % 4) return fail(h, FFB_ERR_ARG, "op_attention kind 4: ldq/ldk must be multiples of 4");
+        DevBuf qh, kh, vh;
+        int rc = FFB_OK;
+        if (qh.ensure(2 * nqe * 2) != cudaSuccess || kh.ensure(2 * nke * 2) != cudaSuccess || vh.ensure(2 * nke * 2) != cudaSuccess)
+            rc = fail(h, FFB_ERR_CUDA, "op_attention: out of device memory");
+        if (rc == FFB_OK) {
+            split_array_kernel<<<grid1d((long long)nqe / 4), 256, 0, s>>>(q, qh.as<uint16_t>(), (long long)nqe / 4, 1.0f, 2);
+            split_array_kernel<<<grid1d((long long)nke / 4), 256, 0, s>>>(k, kh.as<uint16_t>(), (long long)nke / 4, 1.0f, 2);
+            split_array_kernel<<<grid1d((long long)nke / 4), 256, 0, s>>>(v, vh.as<uint16_t>(), (long long)nke / 4, 1.0f, 2);
+            AttnHalfIn in{qh.as<uint16_t>(), (long long)nqe, ldq, kh.as<uint16_t>(), (long long)nke, vh.as<uint16_t>(), (long long)nke, ldk};
+            AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
+            const int saved_fmt = h->tc_fmt; h->tc_fmt = 2;
+            rc = launch_attn_h(h, in, nullptr, 0, g, G, nq, (double)G * nq * nk, PC_ATTN_TILED, nullptr, s, out);
+            h->tc_fmt = saved_fmt;
+            if (cudaStreamSynchronize(s) != cudaSuccess && rc == FFB_OK) rc = fail(h, FFB_ERR_CUDA, "op_attention: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        qh.release(); kh.release(); vh.release();
+        return rc;
+    }
     const int saved = h->opt_attn_mma, saved_fmt = h->tc_fmt;
     h->opt_attn_mma = (kind == 2) ? 1 : (kind == 3) ? 2 : 0;
     if (kind == 3) h->tc_fmt = 2;

@@ -113,6 +113,10 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -297,9 +301,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             if constexpr (C_::STAGED_EPI) {
                 // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----
                 const bool tma_out = p.tma_out && (p.C != nullptr);
+                const bool tma_cs = p.tma_out && (p.C == nullptr) && (p.Cs != nullptr);
                 const uint32_t stg_s = epi_base + (uint32_t)e * 4096u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                 // (fully unrolled: acc[] must stay in registers)
+                    if (tma_cs) {
+                        // ---- asynchronous split output: the block goes out as two fp16 tiles (hi, lo) of 32 x 32 halves, laid out as the
+                        // SWIZZLE_64B boxes of mapC (3-D: col, row, split) expect: 64-byte rows, 16-byte chunk c stored at c ^ ((row >> 1) & 3)
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                        bool ovf = false;
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {                 // 8 values per 16-byte chunk
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float x0 = acc[j * 32 + 8 * cc + 2 * u] * p.out_scale, x1 = acc[j * 32 + 8 * cc + 2 * u + 1] * p.out_scale;
+                                if (p.bias) { x0 += __ldg(p.bias + col0 + j * 32 + 8 * cc + 2 * u); x1 += __ldg(p.bias + col0 + j * 32 + 8 * cc + 2 * u + 1); }
+                                if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                                ovf |= !(fabsf(x0) <= 65504.f) | !(fabsf(x1) <= 65504.f);
+                                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                                hw[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                lw[u] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            }
+                            uint8_t* base = reinterpret_cast<uint8_t*>(stg) + lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4*>(base) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(base + 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                        if (ovf && p.overflow) *p.overflow = 1;
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&mapC, stg_s, col0 + j * 32, row0, 0);
+                            tma_store_3d(&mapC, stg_s + 2048u, col0 + j * 32, row0, 1);
+                            tma_store_commit();
+                        }
+                        continue;
+                    }
                     if (tma_out) {
                         // ---- asynchronous path: the 32x32 block (value = acc*scale + bias, ReLU) is laid out exactly as the
                         // SWIZZLE_128B box of mapC expects and handed to the TMA engine: plain store, or reduce-add into C when the

@@ -87,11 +87,12 @@ __device__ __forceinline__ void store_split1(uint16_t* dst, long long stride, fl
 }
 
 // dst[fmt][n] 16-bit <- split(src[n] * scale)  (weights, once at load time; scale is a power of two)
-__global__ void split_array_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n4, float scale, int fmt) {
+__global__ void split_array_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n4, float scale, int fmt,
+                                   int* ovf = nullptr) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(src)[i];
         v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-        store_split4(dst + 4 * i, 4 * n4, v, fmt, nullptr);
+        store_split4(dst + 4 * i, 4 * n4, v, fmt, ovf);
     }
 }
 

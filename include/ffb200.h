@@ -190,7 +190,8 @@ int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const fl
                      float* y, int32_t M, int32_t E, void* stream);
 /* Multi-head attention core (softmax(q k^T / 8) v) for G equal-sized groups:
  * q [G*nq, ldq], k/v [G*nk, ldk] with head h in columns [64h, 64h+64); out [G*nq, H*64].
- * kind 0 = SIMT warp-per-row kernel, 1 = SIMT tiled kernel, 2 = 3xTF32 mma.sync kernel, 3 = fp16x2 mma.sync kernel.  */
+ * kind 0 = SIMT warp-per-row kernel, 1 = SIMT tiled kernel, 2 = 3xTF32 mma.sync kernel, 3 = fp16x2 mma.sync kernel, 4 = fp16x2 kernel
+ * with pre-split inputs (attn_h.cuh; the hook splits q/k/v first; q/k/v must be contiguous [rows, ld] arrays).  */
 int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k,
                      const float* v, int32_t ldk, float* out, int32_t G, int32_t nq, int32_t nk,
                      int32_t H, void* stream);

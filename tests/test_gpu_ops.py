@@ -91,3 +91,17 @@ def test_attention(eng, kind, G, nq, nk):
     got = eng.op_attention(kind, _t(q), kvt[:, :H * 64], kvt[:, H * 64:], G, nq, nk).cpu().numpy()
     want = _attn_ref(q, kv[:, :H * 64], kv[:, H * 64:], G, nq, nk, H)
     assert np.max(np.abs(got - want)) <= 2e-5
+
+
+@pytest.mark.parametrize("G,nq,nk", [(3, 1, 1), (5, 7, 7), (4, 36, 36), (2, 37, 37), (2, 70, 70), (3, 64, 220),
+                                     (2, 130, 65), (1, 258, 258), (2, 5, 516), (40, 1, 36)])
+def test_attention_half_inputs(eng, G, nq, nk):
+    """attn_h_kernel: q/k/v arrive as fp16x2 splits (the hook splits them), staged with cp.async, fragments from ldmatrix."""
+    H = OURS.num_head
+    rng = np.random.default_rng(G * 100 + nq + nk + 1)
+    q = (rng.normal(size=(G * nq, H * 64)) * 1.5).astype(np.float32)
+    k = (rng.normal(size=(G * nk, H * 64)) * 1.5).astype(np.float32)
+    v = (rng.normal(size=(G * nk, H * 64)) * 1.5).astype(np.float32)
+    got = eng.op_attention(4, _t(q), _t(k), _t(v), G, nq, nk).cpu().numpy()
+    want = _attn_ref(q, k, v, G, nq, nk, H)
+    assert np.max(np.abs(got - want)) <= 2e-5
