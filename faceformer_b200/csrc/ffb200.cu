@@ -279,7 +279,8 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
     const int qtiles = (max_q_rows + AM_BQ - 1) / AM_BQ;
     if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
     dim3 grid(G, h->H, qtiles);
-    const bool f16 = h->opt_attn_mma == 2 && h->tc_fmt == 2 && h->attn_allow_f16;
+    // fp16x2 attention only as part of the tensor-core pipeline; geometries that stay on the fp32 SIMT GEMMs keep the 3xTF32 kernel
+    const bool f16 = h->opt_attn_mma == 2 && h->tc_fmt == 2 && h->attn_allow_f16 && h->tc_ok && h->opt_tc;
     prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
     if (f16) attn_f16_kernel<<<grid, 128, AF_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
     else attn_mma_kernel<<<grid, 128, AM_SMEM_BYTES, s>>>(Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g, stop);
