@@ -35,12 +35,16 @@ __device__ __forceinline__ int af_perm(int i) {                         // i in 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
-// split two fp32 values into packed hi / lo half2 words
+// split two fp32 values into packed hi / lo half2 words (packed conversions: one F2FP per pair)
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-    const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
-    hi = pack_h2(hx, hy);
-    lo = pack_h2(__float2half_rn(x - __half2float(hx)), __float2half_rn(y - __half2float(hy)));
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// exp(x) for x <= 0 on the SFU: ex2.approx(x * log2 e), relative error ~2^-22 (the softmax weights are split to 22 bits anyway)
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
 
 __global__ void __launch_bounds__(128, 3) attn_f16_kernel(const float* __restrict__ Q, int ldq,
                                                           const float* __restrict__ K, const float* __restrict__ V, int ldk,

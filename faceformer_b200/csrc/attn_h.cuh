@@ -103,11 +103,15 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
                     mma_f16(sc0, ql[ks], h0, h1); mma_f16(sc0, qh[ks], l0, l1); mma_f16(sm0, qh[ks], h0, h1);
                     mma_f16(sc1, ql[ks], h2, h3); mma_f16(sc1, qh[ks], l2, l3); mma_f16(sm1, qh[ks], h2, h3);
                 }
-                const int key = kt + 16 * jp + 2 * t;
-                s[2 * jp][0] = (key < nk) ? (sm0[0] + sc0[0]) * 0.125f : -INFINITY; s[2 * jp][1] = (key + 1 < nk) ? (sm0[1] + sc0[1]) * 0.125f : -INFINITY;
-                s[2 * jp][2] = (key < nk) ? (sm0[2] + sc0[2]) * 0.125f : -INFINITY; s[2 * jp][3] = (key + 1 < nk) ? (sm0[3] + sc0[3]) * 0.125f : -INFINITY;
-                s[2 * jp + 1][0] = (key + 8 < nk) ? (sm1[0] + sc1[0]) * 0.125f : -INFINITY; s[2 * jp + 1][1] = (key + 9 < nk) ? (sm1[1] + sc1[1]) * 0.125f : -INFINITY;
-                s[2 * jp + 1][2] = (key + 8 < nk) ? (sm1[2] + sc1[2]) * 0.125f : -INFINITY; s[2 * jp + 1][3] = (key + 9 < nk) ? (sm1[3] + sc1[3]) * 0.125f : -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s[2 * jp][i] = (sm0[i] + sc0[i]) * 0.125f; s[2 * jp + 1][i] = (sm1[i] + sc1[i]) * 0.125f; }
+                if (nkt < AF_BK) {                                       // only the last, partial tile has keys to mask
+                    const int key = 16 * jp + 2 * t;
+                    if (key >= nkt) { s[2 * jp][0] = -INFINITY; s[2 * jp][2] = -INFINITY; }
+                    if (key + 1 >= nkt) { s[2 * jp][1] = -INFINITY; s[2 * jp][3] = -INFINITY; }
+                    if (key + 8 >= nkt) { s[2 * jp + 1][0] = -INFINITY; s[2 * jp + 1][2] = -INFINITY; }
+                    if (key + 9 >= nkt) { s[2 * jp + 1][1] = -INFINITY; s[2 * jp + 1][3] = -INFINITY; }
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { s[2 * jp][i] = -INFINITY; s[2 * jp + 1][i] = -INFINITY; }
@@ -120,12 +124,12 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
+        const float corr0 = fast_exp(m0 - mn0), corr1 = fast_exp(m1 - mn1);
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = expf(s[j][0] - mn0); s[j][1] = expf(s[j][1] - mn0);
-            s[j][2] = expf(s[j][2] - mn1); s[j][3] = expf(s[j][3] - mn1);
+            s[j][0] = fast_exp(s[j][0] - mn0); s[j][1] = fast_exp(s[j][1] - mn0);
+            s[j][2] = fast_exp(s[j][2] - mn1); s[j][3] = fast_exp(s[j][3] - mn1);
             ps0 += s[j][0] + s[j][1]; ps1 += s[j][2] + s[j][3];
         }
         ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
