@@ -91,8 +91,30 @@ def cpu_sample(seed):
     return cfg, batch
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core (BLAS thread pool raised at run time)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
+def load_traffic(kernel_tag):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(kernel_tag)
+        return (ent["dram_bytes_per_launch"], ent.get("note")) if ent else (None, None)
+    except Exception:
+        return (None, None)
+
+
 def time_oracle(sd, seed, repeats=1):
     from oracle import faceformer_oracle as orc
+    use_all_cores()
     cfg, batch = cpu_sample(seed)
     best = None
     for _ in range(repeats):
@@ -167,7 +189,8 @@ def run_ours(args):
     eng.set_option(FFB_OPT_TENSOR_CORE, args.tc)
 
     # one batch per rank (weak scaling: fixed work per GPU)
-    batch = synth.synth_batch(cfg, mode, args.batch, seed=args.seed + 1000 * rank)
+    # identical batch content on every rank: weak scaling with exactly the same work per GPU
+    batch = synth.synth_batch(cfg, mode, args.batch, seed=args.seed)
     N = args.batch
     coords_h = torch.from_numpy(batch["input"].reshape(N, cfg.num_lines, -1)).pin_memory()
     mask_h = torch.from_numpy(batch["input_mask"].astype(np.uint8)).pin_memory()
@@ -256,10 +279,11 @@ def run_ours(args):
         fmt = 3 if eng.fp16_fallbacks() else args.tc_format
         passes = (3 if fmt == 2 else 6) if use_tc else 1
         peak = peaks["bf16_sustained"] / passes
+        traffic, traffic_note = load_traffic(f"gemm_kernel<{fmt}>" if use_tc else "linear_kernel")
         kname = (f"tc::gemm_kernel<{fmt}> (tcgen05 {'fp16x2' if fmt == 2 else 'bf16x3'} split, {passes} MMA passes)" if use_tc
                  else "linear_kernel (fp32 SIMT FFMA)")
         roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "mma_passes": passes,
-                    "frac": ach / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / {passes} ({peaks['source']})",
+                    "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained / {passes} ({peaks['source']})",
                     "avg_launch_ms": lin["ms"] / max(1, lin["launches"]), "launches_per_step": lin["launches"],
                     "share_of_step": lin["ms"] / tot_ms if tot_ms else None,
                     "fp32_ffma_peak_tflops": 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
