@@ -111,3 +111,62 @@ def test_full_size_properties():
         n, s = int(batch["num_input"][i]), min(sb, sa)
         assert np.array_equal(pa[0, :n, :s + 1], pb[i, :n, :s + 1])
     eng.close()
+
+
+@pytest.mark.timeout(300)
+def test_bench_workload_properties_and_seq2seq_latency():
+    """BASELINE.json configs[1] at full size (32 wireframes, 6912 sequences, 36 steps): size-independent properties only
+    (the oracle would need hours).  Also times configs[0] (seq2seq, one 64-edge wireframe, 258 steps) for the record."""
+    import time
+    from faceformer_b200.engine import Engine
+    from faceformer_b200.lib import FFB_OPT_DEDUP_PAD
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 32, seed=0)
+    eng = Engine(cfg, MODE_PARALLEL, 0)
+    eng.load_state_dict(sd)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    p1, s1 = eng.forward_eval(coords, mask, ni)
+    p1 = p1.cpu().numpy()
+    info = eng.batch_info()
+    assert info["B"] == 32 * int(batch["num_input"].max()) and info["B_eff"] < info["B"]
+    p2, s2 = eng.forward_eval(coords, mask, ni)
+    assert s1 == s2 and np.array_equal(p1, p2.cpu().numpy())                              # deterministic
+    assert eng.fp16_fallbacks() == 0
+    nvalid = batch["num_input"] + cfg.num_token
+    for i, n in enumerate(batch["num_input"]):
+        assert np.array_equal(p1[i, :n, 0], np.arange(n)) and np.all(p1[i, n:, 0] == 3)
+        assert np.all(p1[i, n:] == p1[i, n:n + 1])
+        assert p1[i, :, :s1 + 1].max() < nvalid[i] and p1[i].min() >= 0
+    assert np.all(p1[:, :, s1 + 1:] == 0)
+    # two half-batches decoded separately agree with the full batch on the common steps (whole-batch sharding is exact when
+    # the batch composition is kept; here it is NOT kept, so only per-sequence tokens of real anchors are compared)
+    pa, sa = eng.forward_eval(coords[:16], mask[:16], ni[:16])
+    pa = pa.cpu().numpy()
+    s = min(s1, sa)
+    for i in range(16):
+        n = int(batch["num_input"][i])
+        assert np.array_equal(pa[i, :n, :s + 1], p1[i, :n, :s + 1])
+    # un-deduplicated decode (all 6912 sequences) gives the same tensor
+    eng.set_option(FFB_OPT_DEDUP_PAD, 0)
+    p3, s3 = eng.forward_eval(coords, mask, ni)
+    assert s3 == s1 and np.array_equal(p3.cpu().numpy(), p1)
+    eng.close()
+
+    g = load_case("seq2seq_single64")
+    e2 = Engine(g["cfg"], g["mode"], 0)
+    e2.load_state_dict(g["sd"])
+    b = g["batch"]
+    c2 = torch.from_numpy(b["input"]).cuda().flatten(2)
+    m2 = torch.from_numpy(b["input_mask"]).cuda()
+    e2.forward_eval(c2, m2, None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pred, steps = e2.forward_eval(c2, m2, None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert np.array_equal(pred.cpu().numpy(), g["predict"]) and steps == 258
+    print(f"seq2seq config[0]: 1 wireframe x 64 edges, 258 steps in {dt * 1e3:.1f} ms ({258 / dt:.0f} edges/s); "
+          f"reference CPU run took {g['meta']['ref_seconds']} s when the golden was generated")
+    e2.close()
