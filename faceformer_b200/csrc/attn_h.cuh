@@ -28,12 +28,22 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 
-__global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
-                                                        long long os_stride, const AttnGroups g, const int* stop) {
+__device__ __forceinline__ float ex2_approx(float x) {          // 2^x on the SFU, one instruction; 2^-inf = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Launch: blockDim.x = 32 * (number of 16-row query slabs of the largest tile, <= 4); dynamic smem = (2*qr_cap + 4*kr_cap) * 144 B
+// where qr_cap / kr_cap = rows per Q / K,V tile buffer (multiples of 16, <= 64): short prefixes (decoder self-attention early in the
+// decode) get small CTAs and many of them per SM.
+__global__ void __launch_bounds__(128) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
+                                                     long long os_stride, const AttnGroups g, int qr_cap, int kr_cap, const int* stop) {
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) uint16_t smem_h[];
-    const uint32_t sQh = (uint32_t)__cvta_generic_to_shared(smem_h), sQl = sQh + AF_TILE * 2;
-    const uint32_t sKh = sQh + 2 * AF_TILE * 2, sKl = sQh + 3 * AF_TILE * 2, sVh = sQh + 4 * AF_TILE * 2, sVl = sQh + 5 * AF_TILE * 2;
+    const uint32_t qbytes = (uint32_t)qr_cap * AF_S * 2u, kbytes = (uint32_t)kr_cap * AF_S * 2u;
+    const uint32_t sQh = (uint32_t)__cvta_generic_to_shared(smem_h), sQl = sQh + qbytes;
+    const uint32_t sKh = sQl + qbytes, sKl = sKh + kbytes, sVh = sKl + kbytes, sVl = sVh + kbytes;
 
     long long q0, k0, o0; int nq, nk;
     attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
@@ -41,12 +51,12 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
     const int qt0 = blockIdx.z * AF_BQ;
     if (qt0 >= nq) return;
     const int nqt = min(AF_BQ, nq - qt0);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5;
     const int gq = lane >> 2, t = lane & 3;
 
     // ---- stage Q (hi, lo): 8 chunks of 16 B per row and part ----
-    const int q_rows = min(AF_BQ, (nqt + 15) & ~15);
-    for (int idx = tid; idx < q_rows * 16; idx += 128) {
+    const int q_rows = min(qr_cap, (nqt + 15) & ~15);
+    for (int idx = tid; idx < q_rows * 16; idx += nthr) {
         const int r = idx >> 4, c = idx & 7, part = (idx >> 3) & 1;
         const uint16_t* src = in.Qh + (part ? in.q_split : 0) + (size_t)(q0 + qt0 + min(r, nqt - 1)) * in.ldq + head * 64 + c * 8;
         cp_async16((part ? sQl : sQh) + (uint32_t)(r * AF_S + c * 8) * 2u, src, r < nqt);
@@ -57,17 +67,20 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
     const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_col = (lane >> 4) * 8;       // A-operand / V (trans) lane addressing
     const int lk_row = (lane & 7) + (lane >> 4) * 8, lk_col = ((lane >> 3) & 1) * 8;       // K (B of Q K^T) lane addressing
 
+    // Softmax state in the log2 domain, with the 4096x probability scale folded in:
+    //   s' = s * log2(e)/8,  p' = 2^(s' - m' + 12) = 4096 * exp(s - m),  l' = sum p',  o' = sum p' v  ->  out = o' / l'
     float m0 = -INFINITY, m1 = -INFINITY, l0s = 0.f, l1s = 0.f;
     float o[8][4];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.f; }
     uint32_t qh[4][4], ql[4][4];
+    constexpr float kScale = 0.125f * 1.4426950408889634f;
 
     for (int kt = 0; kt < nk; kt += AF_BK) {
         const int nkt = min(AF_BK, nk - kt);
-        const int k_rows = (nkt + 15) & ~15;
+        const int k_rows = min(kr_cap, (nkt + 15) & ~15);
         if (kt > 0) __syncthreads();                                     // previous K/V tile fully consumed
-        for (int idx = tid; idx < k_rows * 32; idx += 128) {
+        for (int idx = tid; idx < k_rows * 32; idx += nthr) {
             const int r = idx >> 5, c = idx & 7, which = (idx >> 3) & 3;    // which: 0 Kh, 1 Kl, 2 Vh, 3 Vl
             const size_t row = (size_t)(k0 + kt + min(r, nkt - 1)) * in.ldk + head * 64 + c * 8;
             const uint16_t* src = (which < 2) ? in.Kh + (which & 1 ? in.k_split : 0) + row : in.Vh + (which & 1 ? in.v_split : 0) + row;
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
         }
         const int jmax = (nkt + 7) >> 3, smax = (nkt + 15) >> 4;
 
-        // ---- S = Q K^T / 8 ----
+        // ---- S' = Q K^T * log2(e)/8 ----
         float s[8][4];
 #pragma unroll
         for (int jp = 0; jp < 4; ++jp) {                                 // key blocks 2jp, 2jp+1
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
                     mma_f16(sc1, ql[ks], h2, h3); mma_f16(sc1, qh[ks], l2, l3); mma_f16(sm1, qh[ks], h2, h3);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { s[2 * jp][i] = (sm0[i] + sc0[i]) * 0.125f; s[2 * jp + 1][i] = (sm1[i] + sc1[i]) * 0.125f; }
+                for (int i = 0; i < 4; ++i) { s[2 * jp][i] = (sm0[i] + sc0[i]) * kScale; s[2 * jp + 1][i] = (sm1[i] + sc1[i]) * kScale; }
                 if (nkt < AF_BK) {                                       // only the last, partial tile has keys to mask
                     const int key = 16 * jp + 2 * t;
                     if (key >= nkt) { s[2 * jp][0] = -INFINITY; s[2 * jp][2] = -INFINITY; }
@@ -123,48 +136,42 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
         for (int j = 0; j < 8; ++j) { mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1])); mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3])); }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float corr0 = fast_exp(m0 - mn0), corr1 = fast_exp(m1 - mn1);
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);          // finite: every tile has >= 1 valid key
+        const float corr0 = ex2_approx(m0 - mn0), corr1 = ex2_approx(m1 - mn1);
+        const float b0 = 12.0f - mn0, b1 = 12.0f - mn1;
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = fast_exp(s[j][0] - mn0); s[j][1] = fast_exp(s[j][1] - mn0);
-            s[j][2] = fast_exp(s[j][2] - mn1); s[j][3] = fast_exp(s[j][3] - mn1);
+            s[j][0] = ex2_approx(s[j][0] + b0); s[j][1] = ex2_approx(s[j][1] + b0);
+            s[j][2] = ex2_approx(s[j][2] + b1); s[j][3] = ex2_approx(s[j][3] + b1);
             ps0 += s[j][0] + s[j][1]; ps1 += s[j][2] + s[j][3];
         }
         ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
         ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
         l0s = l0s * corr0 + ps0; l1s = l1s * corr1 + ps1;
         m0 = mn0; m1 = mn1;
-
-        // ---- O_tile = (4096 P) V from zero, then O = O * corr + O_tile / 4096 in fp32 ----
-        float om[8][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { om[u][0] = om[u][1] = om[u][2] = om[u][3] = 0.f; }
+        for (int u = 0; u < 8; ++u) { o[u][0] *= corr0; o[u][1] *= corr0; o[u][2] *= corr1; o[u][3] *= corr1; }
+
+        // ---- O' += P' V (accumulated straight into the rescaled running output) ----
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             if (ks < smax) {
-                uint32_t pa[4], pl[4];
-                split_pair(s[2 * ks][0] * 4096.f, s[2 * ks][1] * 4096.f, pa[0], pl[0]);
-                split_pair(s[2 * ks][2] * 4096.f, s[2 * ks][3] * 4096.f, pa[1], pl[1]);
-                split_pair(s[2 * ks + 1][0] * 4096.f, s[2 * ks + 1][1] * 4096.f, pa[2], pl[2]);
-                split_pair(s[2 * ks + 1][2] * 4096.f, s[2 * ks + 1][3] * 4096.f, pa[3], pl[3]);
+                uint32_t pa[4], pl[4];                                   // A fragment = S accumulators of key blocks 2ks, 2ks+1
+                split_pair(s[2 * ks][0], s[2 * ks][1], pa[0], pl[0]);
+                split_pair(s[2 * ks][2], s[2 * ks][3], pa[1], pl[1]);
+                split_pair(s[2 * ks + 1][0], s[2 * ks + 1][1], pa[2], pl[2]);
+                split_pair(s[2 * ks + 1][2], s[2 * ks + 1][3], pa[3], pl[3]);
                 const uint32_t voff = (uint32_t)((16 * ks + lm_row) * AF_S + lm_col) * 2u;
 #pragma unroll
                 for (int up = 0; up < 4; ++up) {
                     uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
                     ldsm_x4_t(sVh + voff + up * 32, h0, h1, h2, h3);
                     ldsm_x4_t(sVl + voff + up * 32, l0, l1, l2, l3);
-                    mma_f16(om[2 * up], pl, h0, h1); mma_f16(om[2 * up], pa, l0, l1); mma_f16(om[2 * up], pa, h0, h1);
-                    mma_f16(om[2 * up + 1], pl, h2, h3); mma_f16(om[2 * up + 1], pa, l2, l3); mma_f16(om[2 * up + 1], pa, h2, h3);
+                    mma_f16(o[2 * up], pl, h0, h1); mma_f16(o[2 * up], pa, l0, l1); mma_f16(o[2 * up], pa, h0, h1);
+                    mma_f16(o[2 * up + 1], pl, h2, h3); mma_f16(o[2 * up + 1], pa, l2, l3); mma_f16(o[2 * up + 1], pa, h2, h3);
                 }
             }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            constexpr float kInvP = 1.0f / 4096.f;
-            o[u][0] = o[u][0] * corr0 + om[u][0] * kInvP; o[u][1] = o[u][1] * corr0 + om[u][1] * kInvP;
-            o[u][2] = o[u][2] * corr1 + om[u][2] * kInvP; o[u][3] = o[u][3] * corr1 + om[u][3] * kInvP;
         }
     }
     if (!warp_active) return;

@@ -290,7 +290,7 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
     return FFB_OK;
 }
 
-int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long os_stride, AttnGroups g, int G, int max_q_rows,
+int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long os_stride, AttnGroups g, int G, int max_q_rows, int max_nk,
                   double qk_pairs, int prof_class, const int* stop, cudaStream_t s, float* O = nullptr) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
     const int qtiles = (max_q_rows + AF_BQ - 1) / AF_BQ;
@@ -298,7 +298,10 @@ int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long o
     g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
     dim3 grid(G, h->H, qtiles);
     prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
-    attn_h_kernel<<<grid, 128, AF_SMEM_BYTES, s>>>(in, O, h->E, Os, os_stride, g, stop);
+    const int qr_cap = std::min(AF_BQ, (std::min(max_q_rows, AF_BQ) + 15) & ~15);      // rows per Q tile buffer
+    const int kr_cap = std::min(AF_BK, (std::min(std::max(max_nk, 1), AF_BK) + 15) & ~15);   // rows per K / V tile buffer
+    const int smem = (2 * qr_cap + 4 * kr_cap) * AF_S * 2;
+    attn_h_kernel<<<grid, 32 * (qr_cap / 16), smem, s>>>(in, O, h->E, Os, os_stride, g, qr_cap, kr_cap, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -773,7 +776,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                 if (hp) {
                     AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
                     AttnGroups g{}; g.ragged = 0; g.nq = P; g.nk = P; g.q_stride = P; g.q_off = 0; g.k_stride = P; g.o_stride = P;
-                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, P, (double)B * P * P, PC_ATTN_ROWS, stop, s));
+                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, P, P, (double)B * P * P, PC_ATTN_ROWS, stop, s));
                 } else
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
                 { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E; l.Cmap = &h->mc_x;
@@ -782,7 +785,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                 if (hp) {
                     AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
                     AttnGroups g{}; g.ragged = 0; g.nq = 1; g.nk = P; g.q_stride = P; g.q_off = P - 1; g.k_stride = P; g.o_stride = 1;
-                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, 1, (double)B * P, PC_ATTN_ROWS, stop, s));
+                    FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, 1, P, (double)B * P, PC_ATTN_ROWS, stop, s));
                 } else
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
                 copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
@@ -800,7 +803,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               if (hp) {
                   const long long kvs = (long long)h->R * LdE;
                   AttnHalfIn in{aqc, h->cap_rows * E, E, h->kc_h.as<uint16_t>() + (size_t)li * E, kvs, h->vc_h.as<uint16_t>() + (size_t)li * E, kvs, LdE};
-                  FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, PC_ATTN_TILED, stop, s));
+                  FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, N, h->max_seq_per_wf * Pq, h->max_vlen, h->sum_seq_vlen * Pq, PC_ATTN_TILED, stop, s));
               } else
               FFB_TRY(launch_attn_tiled(h, qkv, E, h->Kc.as<float>() + (size_t)li * E, h->Vc.as<float>() + (size_t)li * E, LdE,
                                         att, E, g, N, h->max_seq_per_wf * Pq, h->sum_seq_vlen * Pq, stop, s, aatt, ssE)); }
@@ -1318,7 +1321,7 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
             AttnHalfIn in{qh.as<uint16_t>(), (long long)nqe, ldq, kh.as<uint16_t>(), (long long)nke, vh.as<uint16_t>(), (long long)nke, ldk};
             AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = nq; g.q_off = 0; g.k_stride = nk; g.o_stride = nq;
             const int saved_fmt = h->tc_fmt; h->tc_fmt = 2;
-            rc = launch_attn_h(h, in, nullptr, 0, g, G, nq, (double)G * nq * nk, PC_ATTN_TILED, nullptr, s, out);
+            rc = launch_attn_h(h, in, nullptr, 0, g, G, nq, nk, (double)G * nq * nk, PC_ATTN_TILED, nullptr, s, out);
             h->tc_fmt = saved_fmt;
             if (cudaStreamSynchronize(s) != cudaSuccess && rc == FFB_OK) rc = fail(h, FFB_ERR_CUDA, "op_attention: %s", cudaGetErrorString(cudaGetLastError()));
         }
