@@ -37,7 +37,7 @@ __device__ __forceinline__ float ex2_approx(float x) {          // 2^x on the SF
 // Launch: blockDim.x = 32 * (number of 16-row query slabs of the largest tile, <= 4); dynamic smem = (2*qr_cap + 4*kr_cap) * 144 B
 // where qr_cap / kr_cap = rows per Q / K,V tile buffer (multiples of 16, <= 64): short prefixes (decoder self-attention early in the
 // decode) get small CTAs and many of them per SM.
-__global__ void __launch_bounds__(128) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
+__global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
                                                      long long os_stride, const AttnGroups g, int qr_cap, int kr_cap, const int* stop) {
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) uint16_t smem_h[];
@@ -101,23 +101,38 @@ __global__ void __launch_bounds__(128) attn_h_kernel(const AttnHalfIn in, float*
         }
         const int jmax = (nkt + 7) >> 3, smax = (nkt + 15) >> 4;
 
-        // ---- S' = Q K^T * log2(e)/8 ----
+        // ---- S' = Q K^T * log2(e)/8.  One accumulator per 8-key block; per k-step the three passes (lo*hi, hi*lo, hi*hi) are issued
+        // pass-major across all key blocks, so consecutive MMAs never depend on each other (8 independent chains). ----
         float s[8][4];
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {                                 // key blocks 2jp, 2jp+1
-            if (2 * jp < jmax) {
-                float sm0[4] = {0.f, 0.f, 0.f, 0.f}, sc0[4] = {0.f, 0.f, 0.f, 0.f}, sm1[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t off = (uint32_t)((16 * jp + lk_row) * AF_S + 16 * ks + lk_col) * 2u;
-                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;              // (b0,b1) of block 2jp, (b0,b1) of block 2jp+1
-                    ldsm_x4(sKh + off, h0, h1, h2, h3);
-                    ldsm_x4(sKl + off, l0, l1, l2, l3);
-                    mma_f16(sc0, ql[ks], h0, h1); mma_f16(sc0, qh[ks], l0, l1); mma_f16(sm0, qh[ks], h0, h1);
-                    mma_f16(sc1, ql[ks], h2, h3); mma_f16(sc1, qh[ks], l2, l3); mma_f16(sm1, qh[ks], h2, h3);
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {                             // key-block pairs (2jh, 2jh+1): 4 independent chains per pass
+                if (4 * jh < jmax) {
+                    uint32_t kh[2][4], kl[2][4];                         // (b0,b1) of block 2jp, (b0,b1) of block 2jp+1
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int jp = 2 * jh + q2;
+                        const uint32_t off = (uint32_t)((16 * jp + lk_row) * AF_S + 16 * ks + lk_col) * 2u;
+                        ldsm_x4(sKh + off, kh[q2][0], kh[q2][1], kh[q2][2], kh[q2][3]);
+                        ldsm_x4(sKl + off, kl[q2][0], kl[q2][1], kl[q2][2], kl[q2][3]);
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int jp = 2 * jh + q2; mma_f16(s[2 * jp], ql[ks], kh[q2][0], kh[q2][1]); mma_f16(s[2 * jp + 1], ql[ks], kh[q2][2], kh[q2][3]); }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int jp = 2 * jh + q2; mma_f16(s[2 * jp], qh[ks], kl[q2][0], kl[q2][1]); mma_f16(s[2 * jp + 1], qh[ks], kl[q2][2], kl[q2][3]); }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int jp = 2 * jh + q2; mma_f16(s[2 * jp], qh[ks], kh[q2][0], kh[q2][1]); mma_f16(s[2 * jp + 1], qh[ks], kh[q2][2], kh[q2][3]); }
                 }
+            }
+        }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { s[2 * jp][i] = (sm0[i] + sc0[i]) * kScale; s[2 * jp + 1][i] = (sm1[i] + sc1[i]) * kScale; }
+        for (int jp = 0; jp < 4; ++jp) {
+            if (2 * jp < jmax) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s[2 * jp][i] *= kScale; s[2 * jp + 1][i] *= kScale; }
                 if (nkt < AF_BK) {                                       // only the last, partial tile has keys to mask
                     const int key = 16 * jp + 2 * t;
                     if (key >= nkt) { s[2 * jp][0] = -INFINITY; s[2 * jp][2] = -INFINITY; }
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(128) attn_h_kernel(const AttnHalfIn in, float*
 #pragma unroll
         for (int u = 0; u < 8; ++u) { o[u][0] *= corr0; o[u][1] *= corr0; o[u][2] *= corr1; o[u][3] *= corr1; }
 
-        // ---- O' += P' V (accumulated straight into the rescaled running output) ----
+        // ---- O' += P' V (accumulated straight into the rescaled running output), pass-major across the 8 output tiles ----
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             if (ks < smax) {
@@ -164,12 +179,19 @@ __global__ void __launch_bounds__(128) attn_h_kernel(const AttnHalfIn in, float*
                 split_pair(s[2 * ks + 1][2], s[2 * ks + 1][3], pa[3], pl[3]);
                 const uint32_t voff = (uint32_t)((16 * ks + lm_row) * AF_S + lm_col) * 2u;
 #pragma unroll
-                for (int up = 0; up < 4; ++up) {
-                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                    ldsm_x4_t(sVh + voff + up * 32, h0, h1, h2, h3);
-                    ldsm_x4_t(sVl + voff + up * 32, l0, l1, l2, l3);
-                    mma_f16(o[2 * up], pl, h0, h1); mma_f16(o[2 * up], pa, l0, l1); mma_f16(o[2 * up], pa, h0, h1);
-                    mma_f16(o[2 * up + 1], pl, h2, h3); mma_f16(o[2 * up + 1], pa, l2, l3); mma_f16(o[2 * up + 1], pa, h2, h3);
+                for (int uh = 0; uh < 2; ++uh) {                         // output tiles 4uh .. 4uh+3: 4 independent chains per pass
+                    uint32_t vh[2][4], vl[2][4];
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        ldsm_x4_t(sVh + voff + (2 * uh + q2) * 32, vh[q2][0], vh[q2][1], vh[q2][2], vh[q2][3]);
+                        ldsm_x4_t(sVl + voff + (2 * uh + q2) * 32, vl[q2][0], vl[q2][1], vl[q2][2], vl[q2][3]);
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int up = 2 * uh + q2; mma_f16(o[2 * up], pl, vh[q2][0], vh[q2][1]); mma_f16(o[2 * up + 1], pl, vh[q2][2], vh[q2][3]); }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int up = 2 * uh + q2; mma_f16(o[2 * up], pa, vl[q2][0], vl[q2][1]); mma_f16(o[2 * up + 1], pa, vl[q2][2], vl[q2][3]); }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) { const int up = 2 * uh + q2; mma_f16(o[2 * up], pa, vh[q2][0], vh[q2][1]); mma_f16(o[2 * up + 1], pa, vh[q2][2], vh[q2][3]); }
                 }
             }
         }
