@@ -16,6 +16,7 @@
 #include "attn_mma.cuh"
 #include "attn_f16.cuh"
 #include "attn_h.cuh"
+#include "attn_x.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -98,6 +99,12 @@ struct ffb_handle {
     DevBuf a_qkv, a_qc, kc_h, vc_h;               // [2][cap][3E], [2][cap][E], [2][R][Ld*E] halves
     CUtensorMap ms_qkv, ms_qc;
     bool half_pipe = false;                       // set per batch at plan time
+    // tcgen05 cross-attention (attn_x.cuh): transposed fp16x2 value cache [2][Ld*E][Rp] + TMA load maps of Q, K, Vt
+    DevBuf vt_h, d_colp_off;
+    long long Rp = 0;
+    CUtensorMap mx_q, mx_k, mx_vt;
+    bool attn_x_ok = false;                       // set per batch: half pipeline, <= 256 keys per wireframe, <= 1023 wireframes
+    int opt_attn_x = 1;
     int opt_attn_mma = 2;                         // attention core: 2 = mma.sync fp16x2 kernel (decode, while the GEMM format is fp16x2),
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
@@ -302,6 +309,28 @@ int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long o
     const int kr_cap = std::min(AF_BK, (std::min(std::max(max_nk, 1), AF_BK) + 15) & ~15);   // rows per K / V tile buffer
     const int smem = (2 * qr_cap + 4 * kr_cap) * AF_S * 2;
     attn_h_kernel<<<grid, 32 * (qr_cap / 16), smem, s>>>(in, O, h->E, Os, os_stride, g, qr_cap, kr_cap, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+// tcgen05 cross-attention: queries of wireframe i are rows [seq_off[i]*Pq, seq_off[i+1]*Pq) of Q, keys its rows of the cache
+int launch_attn_x(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const int* seq_off_dev,
+                  const std::vector<int>& seq_off_host, int Pq, const int* row_off, const int* vlen, const int* colp_off, int G,
+                  int layer_col, uint16_t* Os, long long os_stride, int ldo, double qk_pairs, const int* stop, cudaStream_t s) {
+    long long tiles = 0;
+    for (int i = 0; i < G; ++i) tiles += ((long long)(seq_off_host[i + 1] - seq_off_host[i]) * Pq + ax::BQ - 1) / ax::BQ;
+    const long long items = tiles * h->H;
+    if (items <= 0) return FFB_OK;
+    if (items > 0x7fffffffLL) return fail(h, FFB_ERR_ARG, "cross-attention: too many work items");
+    ax::Params p{};
+    p.seq_off = seq_off_dev; p.q_mul = Pq; p.row_off = row_off; p.vlen = vlen; p.colp_off = colp_off;
+    p.n_groups = G; p.n_heads = h->H; p.layer_col = layer_col; p.total_items = (int)items;
+    p.Os = Os; p.os_stride = os_stride; p.ldo = ldo; p.stop = stop;
+    const int grid = (int)std::min<long long>(items, h->num_sms);
+    prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * qk_pairs, s);
+    ax::attn_x_kernel<<<grid, ax::NUM_THREADS, ax::SMEM_BYTES, s>>>(mq, mk, mvt, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -519,6 +548,9 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     if (R > 0x7fffffffLL / std::max(h->E * 3, h->Ld * h->E)) return fail(h, FFB_ERR_ARG, "batch too large (memory rows)");
     h->h_row_off[N] = (int)R;
     h->R = R; h->Re = Re; h->max_vlen = max_vlen;
+    std::vector<int> colp_off(N + 1, 0);                                  // key columns of the transposed value cache, 32-aligned per wireframe
+    for (int i = 0; i < N; ++i) colp_off[i + 1] = colp_off[i] + (h->h_vlen[i] + 31) / 32 * 32;
+    h->Rp = std::max(colp_off[N], 32);
     pos_idx.resize(R); edge_src.resize(Re); edge_dst.resize(Re);
     long long e = 0;
     for (int i = 0; i < N; ++i) {
@@ -579,7 +611,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     }
     h->h_seq_off[N] = (int)seq_wf.size();
     h->B = (long long)seq_wf.size();
-    h->half_pipe = false;
+    h->half_pipe = false; h->attn_x_ok = false;
     h->sum_seq_vlen = 0; h->sum_vlen2 = 0;
     for (int i = 0; i < N; ++i) {
         h->sum_seq_vlen += (double)(h->h_seq_off[i + 1] - h->h_seq_off[i]) * h->h_vlen[i];
@@ -600,6 +632,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     FFB_TRY(upload(h, h->d_seq_off, h->h_seq_off, s));
     FFB_TRY(upload(h, h->d_slot_seq, slot_seq, s));
     FFB_TRY(upload(h, h->d_seq_slot, seq_slot, s));
+    FFB_TRY(upload(h, h->d_colp_off, colp_off, s));
     // the std::vectors above are pageable: make sure the copies are done before they go out of scope
     CU(h, cudaStreamSynchronize(s));
 
@@ -638,6 +671,14 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             CU(h, h->kc_h.ensure(2 * (size_t)R * h->Ld * E * 2)); CU(h, h->vc_h.ensure(2 * (size_t)R * h->Ld * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_qkv, h->a_qkv.p, 3 * E, cr));
             FFB_TRY(encode_split_store_map(h, &h->ms_qc, h->a_qc.p, E, cr));
+            h->attn_x_ok = (h->max_vlen <= ax::KMAX && N <= ax::MAX_GROUPS);
+            if (h->attn_x_ok) {
+                const size_t LdE = (size_t)h->Ld * E;
+                CU(h, h->vt_h.ensure(2 * LdE * (size_t)h->Rp * 2));
+                FFB_TRY(encode_operand_map(h, &h->mx_q, h->a_qc.p, E, cr, ax::BQ, 2));
+                FFB_TRY(encode_operand_map(h, &h->mx_k, h->kc_h.p, LdE, (uint64_t)R, ax::KC, 2));
+                FFB_TRY(encode_operand_map(h, &h->mx_vt, h->vt_h.p, (uint64_t)h->Rp, LdE, 64, 2));
+            }
         }
     }
     return FFB_OK;
@@ -690,6 +731,12 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
         split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
         split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
         h->launches += 2; CU(h, cudaGetLastError());
+        if (h->attn_x_ok) {  // transposed copy of the value cache for the tcgen05 cross-attention (B operand of O = P V, keys contiguous)
+            CU(h, cudaMemsetAsync(h->vt_h.p, 0, 2 * (size_t)LdE * (size_t)h->Rp * 2, s));
+            ax::build_vt_kernel<<<dim3((LdE + 31) / 32, N), dim3(32, 8), 0, s>>>(h->Vc.as<float>(), LdE, row_off, vlen, h->d_colp_off.as<int>(),
+                                                                              h->vt_h.as<uint16_t>(), h->Rp, h->state.as<int>() + 5);
+            h->launches++; CU(h, cudaGetLastError());
+        }
     }
     return FFB_OK;
 }
@@ -800,7 +847,10 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               else { l.C = qkv; l.ldc = E; l.Cmap = &h->mc_qkv1; }
               FFB_TRY(launch_tc(h, l, stop, s)); }
             { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
-              if (hp) {
+              if (hp && h->attn_x_ok && h->opt_attn_x) {
+                  FFB_TRY(launch_attn_x(h, h->mx_q, h->mx_k, h->mx_vt, seq_off, h->h_seq_off, Pq, row_off, vlen, h->d_colp_off.as<int>(), N,
+                                        li * E, aatt, ssE, E, h->sum_seq_vlen * Pq, stop, s));
+              } else if (hp) {
                   const long long kvs = (long long)h->R * LdE;
                   AttnHalfIn in{aqc, h->cap_rows * E, E, h->kc_h.as<uint16_t>() + (size_t)li * E, kvs, h->vc_h.as<uint16_t>() + (size_t)li * E, kvs, LdE};
                   FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, N, h->max_seq_per_wf * Pq, h->max_vlen, h->sum_seq_vlen * Pq, PC_ATTN_TILED, stop, s));
@@ -889,6 +939,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(ax::attn_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ax::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_x_kernel): %s", cudaGetErrorString(e));
     if (!g_encode_tiled) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -918,7 +970,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->vt_h, &h->d_colp_off};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -943,6 +995,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_ATTN_MMA:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
             h->opt_attn_mma = value; return FFB_OK;
+        case FFB_OPT_ATTN_X: h->opt_attn_x = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -1326,6 +1379,47 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
             if (cudaStreamSynchronize(s) != cudaSuccess && rc == FFB_OK) rc = fail(h, FFB_ERR_CUDA, "op_attention: %s", cudaGetErrorString(cudaGetLastError()));
         }
         qh.release(); kh.release(); vh.release();
+        return rc;
+    }
+    if (kind == 5) {     // tcgen05 cross-attention kernel: group g = "wireframe" g with nq queries and nk (<= 256) keys
+        if (nk > ax::KMAX || G > ax::MAX_GROUPS) return fail(h, FFB_ERR_UNSUPPORTED, "op_attention kind 5: needs nk <= 256 and G <= 1023");
+        if (ldq != H * 64 || ldk % 32 || ldk < H * 64) return fail(h, FFB_ERR_ARG, "op_attention kind 5: ldq must be H*64, ldk a multiple of 32");
+        const size_t Mq = (size_t)G * nq, Mp = (Mq + 127) / 128 * 128, Rk = (size_t)G * nk;
+        const int nkp = (nk + 31) / 32 * 32;
+        const size_t Rp = (size_t)G * nkp;
+        std::vector<int> seq_off(G + 1), row_off(G), vlen(G), colp(G);
+        for (int g = 0; g <= G; ++g) seq_off[g] = g;
+        for (int g = 0; g < G; ++g) { row_off[g] = g * nk; vlen[g] = nk; colp[g] = g * nkp; }
+        DevBuf qh, kh, vt, os, meta;
+        int rc = FFB_OK;
+        do {
+            if (qh.ensure(2 * Mp * ldq * 2) != cudaSuccess || kh.ensure(2 * Rk * ldk * 2) != cudaSuccess || vt.ensure(2 * (size_t)ldk * Rp * 2) != cudaSuccess ||
+                os.ensure(2 * Mp * ldq * 2) != cudaSuccess || meta.ensure((4 * (size_t)G + 1) * sizeof(int)) != cudaSuccess) {
+                rc = fail(h, FFB_ERR_CUDA, "op_attention: out of device memory"); break; }
+            int* m = meta.as<int>();
+            cudaMemcpyAsync(m, seq_off.data(), (G + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(m + G + 1, row_off.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(m + 2 * G + 1, vlen.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(m + 3 * G + 1, colp.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemsetAsync(qh.p, 0, 2 * Mp * ldq * 2, s); cudaMemsetAsync(vt.p, 0, 2 * (size_t)ldk * Rp * 2, s);
+            cudaMemsetAsync(os.p, 0, 2 * Mp * ldq * 2, s);
+            // q is [Mq, ldq] contiguous: split as one array, the parts are then Mq*ldq elements apart (the map below says so)
+            split_array_kernel<<<grid1d((long long)Mq * ldq / 4), 256, 0, s>>>(q, qh.as<uint16_t>(), (long long)Mq * ldq / 4, 1.0f, 2);
+            split_array_kernel<<<grid1d((long long)Rk * ldk / 4), 256, 0, s>>>(k, kh.as<uint16_t>(), (long long)Rk * ldk / 4, 1.0f, 2);
+            ax::build_vt_kernel<<<dim3((ldk + 31) / 32, G), dim3(32, 8), 0, s>>>(v, ldk, m + G + 1, m + 2 * G + 1, m + 3 * G + 1, vt.as<uint16_t>(),
+                                                                              (long long)Rp, nullptr);
+            h->launches += 3;
+            CUtensorMap mq, mk, mvt;
+            if ((rc = encode_operand_map(h, &mq, qh.p, ldq, Mq, ax::BQ, 2)) != FFB_OK) break;
+            if ((rc = encode_operand_map(h, &mk, kh.p, ldk, Rk, ax::KC, 2)) != FFB_OK) break;
+            if ((rc = encode_operand_map(h, &mvt, vt.p, Rp, ldk, 64, 2)) != FFB_OK) break;
+            if ((rc = launch_attn_x(h, mq, mk, mvt, m, seq_off, nq, m + G + 1, m + 2 * G + 1, m + 3 * G + 1, G, 0, os.as<uint16_t>(),
+                                    (long long)Mp * ldq, ldq, (double)G * nq * nk, nullptr, s)) != FFB_OK) break;
+            sum_split_kernel<<<grid1d((long long)Mq * ldq), 256, 0, s>>>(os.as<uint16_t>(), (long long)Mp * ldq, out, (long long)Mq * ldq, 2);
+            h->launches++;
+            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention kind 5: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        } while (0);
+        qh.release(); kh.release(); vt.release(); os.release(); meta.release();
         return rc;
     }
     const int saved = h->opt_attn_mma, saved_fmt = h->tc_fmt;

@@ -146,6 +146,32 @@ def test_tensor_core_and_simt_paths_agree_on_a_real_batch():
     assert ok, d
 
 
+def test_tcgen05_cross_attention_agrees_with_mma_sync_on_a_real_batch():
+    """Same batch decoded with the cross-attention core on tcgen05 (attn_x_kernel, default) and on mma.sync (attn_h_kernel):
+    identical tokens, logits within tolerance; ragged wireframes (different key counts, tiles straddling wireframes)."""
+    from faceformer_b200 import synth
+    from faceformer_b200.lib import FFB_OPT_ATTN_X
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 9, seed=5, lo=24, hi=216)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    out = []
+    for mode in (0, 1):
+        e = Engine(cfg, MODE_PARALLEL, 0)
+        e.load_state_dict(sd)
+        e.set_option(FFB_OPT_TENSOR_CORE, 2)
+        e.set_option(FFB_OPT_ATTN_X, mode)
+        pred, steps = e.forward_eval(coords, mask, ni)
+        out.append((pred.cpu().numpy(), steps, e.get_last_logits().cpu().numpy(), e.fp16_fallbacks()))
+        e.close()
+    assert out[0][3] == 0 and out[1][3] == 0
+    assert out[0][1] == out[1][1]
+    assert np.array_equal(out[0][0], out[1][0]), f"{(out[0][0] != out[1][0]).sum()} token mismatches"
+    ok, d = logits_close(out[1][2], out[0][2])
+    assert ok, d
+
+
 def test_fp16_overflow_falls_back_to_bf16x3():
     """FFN hidden activations beyond the fp16 range (linear1 x 65536, linear2 / 65536: the same function in exact
     arithmetic): the fp16x2 decode raises the overflow flag, is re-run in bf16x3 and still matches the SIMT path."""
