@@ -1,26 +1,33 @@
-// attn_x.cuh -- decoder CROSS-attention core on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+// attn_x.cuh -- decoder attention cores on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
 //
-//   O = softmax(Q K^T / 8) V   per (wireframe, head): the queries are all prefix positions of all sequences of one
-//   wireframe (transformer.py:247-251 with memory_key_padding_mask realised as "only valid rows exist"), the keys /
-//   values are the wireframe's rows of the cross-attention cache (computed once per wireframe).
+//   O = softmax(Q K^T / 8) V   per (group, head), head dim 64, <= 256 keys per group, in two flavours:
+//   CROSS  group = wireframe: queries are all prefix positions of all its sequences, keys / values its rows of the
+//          cross-attention cache (transformer.py:247-251; memory_key_padding_mask realised as "only valid rows exist";
+//          the cache is computed once per wireframe).  K / V stay in shared memory while consecutive
+//          work items share (wireframe, head).
+//   SELF   decoder self-attention over the prefix, NO causal mask (transformer.py:242-246, model_para.py:222-223):
+//          a work item is a tile of floor(128 / P) whole sequences; S = Q K^T is computed for the whole tile and the
+//          softmax keeps only the block diagonal (row r attends to the keys of its own sequence).
 //
 // Operands are fp16x2 splits (x = h + l), every product is  l*h + h*l + h*h  (3 MMAs, fp32 accumulate in TMEM):
-//   Q   a_qc  [2][rows][E]            written by the query-projection GEMM epilogue       -> A of  S = Q K^T
-//   K   kc_h  [2][R][Ld*E]            split once per wireframe at encode time             -> B of  S   (K-major: head dim)
-//   Vt  vt_h  [2][Ld*E][Rp]           TRANSPOSED value cache, keys contiguous, every      -> B of  O = P V (K-major: keys)
-//                                     wireframe's key range padded with zeros to 32 keys
-//   P   softmax weights, written by the softmax warps into shared memory as fp16x2      -> A of  O
-// All smem operand tiles are 64-byte rows with SWIZZLE_64B (the layout gemm_tc.cuh uses), 32 contraction elements per tile.
+//   Q, K   rows of fp16x2 buffers [2][rows][ld] (written by GEMM epilogues / split once per wireframe), K-major smem
+//          tiles of 64-byte rows with SWIZZLE_64B (the layout gemm_tc.cuh uses), 32 contraction elements per tile
+//   V      the row-major rows themselves ([keys][head dim]), loaded as 128-byte rows with SWIZZLE_128B and consumed
+//          through an MN-major B descriptor (no transposed copy of V exists anywhere)
+//   P      softmax weights, written by the softmax warps into shared memory as fp16x2 (A operand of O += P V)
 //
-// One persistent CTA per SM walks a contiguous range of work items (wireframe, head, 128-query tile); K / Vt stay in
-// shared memory while consecutive items share (wireframe, head).  Roles (192 threads):
-//   warp 0      TMA producer (Q per item, K / Vt per (wireframe, head))
-//   warp 1      TMEM allocator + MMA issuer (one thread): S = Q K^T (N = keys rounded to 16, <= 256), then O += P_c Vt_c per
-//               32-key chunk as the softmax warps publish P_c
-//   warps 2-5   softmax + epilogue, one query row per thread (TMEM lane = row): pass 1 row max over S, pass 2
-//               p = 2^(s*log2e/8 - m + 12) per 32-key chunk -> fp16x2 -> smem (double-buffered), finally O / l -> fp16x2 ->
-//               coalesced global stores through a per-warp staging area.
-// Keys <= 256 per wireframe (ours.yml: 220); larger geometries use attn_h_kernel.
+// One persistent CTA per SM walks a contiguous range of work items.  Roles (384 threads):
+//   warp 0      TMA producer (Q per item, K / V per (group, head))
+//   warp 1      TMEM allocator + S issuer (one thread): S_j = Q_j K^T into the TMEM buffer of warpgroup j & 1
+//   warps 2, 3  P V issuers of warpgroup 0 / 1 (one thread each): O_j += P_c V_c as the softmax warpgroup publishes chunk c.
+//               Three independent issuers keep every hand-off a plain mbarrier wait (no polling loop between a softmax
+//               arrive and the MMA it unlocks), so the tensor pipe, both softmax warpgroups and the TMA loads overlap.
+//   warps 4-7   softmax warpgroup 0 (items 0, 2, 4, ... of the CTA), warps 8-11 softmax warpgroup 1 (items 1, 3, ...):
+//               one query row per thread (TMEM lane = row): pass 1 row max over S, pass 2 p = 2^(s*log2e/8 - m + 12)
+//               per 32-key chunk -> fp16x2 -> smem (double-buffered per warpgroup), finally O / l -> fp16x2 -> coalesced
+//               global stores through a per-warp staging area.
+// TMEM: two S buffers of 256 columns; O (64 columns) aliases columns [0,64) of its S buffer: the first P V product is
+// issued only after the softmax has read S chunks 0 and 1.
 #pragma once
 #include "gemm_tc.cuh"
 #include "attn_h.cuh"   // split_pair, ex2_approx
@@ -28,53 +35,88 @@
 namespace ffb {
 namespace ax {
 
-constexpr int BQ = 128, KMAX = 256, KC = 32, NUM_THREADS = 192, MAX_GROUPS = 1023;
+constexpr int BQ = 128, KMAX = 256, KC = 32, NUM_THREADS = 384, MAX_GROUPS = 255;
 constexpr int Q_TILE = BQ * 64;                  // bytes of one (part, k-chunk) Q tile: 128 rows x 64 B
-constexpr int K_TILE = KMAX * 64;                // 256 rows x 64 B
-constexpr int V_TILE = 64 * 64;                  // one 32-key chunk of Vt: 64 head-dim rows x 64 B
+constexpr int V_TILE = KC * 128;                 // one 32-key chunk of V: 32 rows x 128 B
 constexpr int P_TILE = BQ * 64;                  // one (buffer, part) P chunk: 128 rows x 32 keys
-constexpr int Q_BYTES = 4 * Q_TILE, K_BYTES = 4 * K_TILE, V_BYTES = 2 * (KMAX / KC) * V_TILE, P_BYTES = 4 * P_TILE;
+constexpr int Q_BYTES = 4 * Q_TILE, K_BYTES = 4 * KMAX * 64, V_BYTES = 2 * (KMAX / KC) * V_TILE, P_BYTES = 2 * 4 * P_TILE;
 constexpr int BAR_BYTES = 256, TOFF_BYTES = (MAX_GROUPS + 1) * 4;
 constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + P_BYTES + BAR_BYTES + TOFF_BYTES + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-constexpr int TMEM_COLS = 512, S_COL = 0, O_COL = 256;
+constexpr int TMEM_COLS = 512;
 
 struct Params {
-    const int* seq_off; int q_mul;             // queries of wireframe i: rows [seq_off[i]*q_mul, seq_off[i+1]*q_mul)
-    const int* row_off; const int* vlen;       // keys of wireframe i: cache rows [row_off[i], +vlen[i])
-    const int* colp_off;                       // first column of wireframe i in the transposed value cache (multiple of 32)
-    int n_groups, n_heads;
-    int layer_col;                             // first column of this layer in the cache rows (layer * E)
-    int total_items;                           // n_heads * sum_i ceil(queries_i / 128)
+    int mode;                                  // 0 = CROSS, 1 = SELF
+    // CROSS: queries of group i are rows [seq_off[i]*q_mul, seq_off[i+1]*q_mul); keys rows [row_off[i], +vlen[i])
+    const int* seq_off; int q_mul; const int* row_off; const int* vlen;
+    int n_groups;
+    // SELF: n_seqs sequences of P rows each; a tile holds seqs_per_tile = floor(128 / P) whole sequences
+    int P, seqs_per_tile, n_seqs;
+    int n_heads;
+    int q_col, k_col, v_col;                   // first column of head 0 in the Q / K / V rows
+    int total_items;
     uint16_t* Os; long long os_stride; int ldo;   // fp16x2 output [2][rows][ldo]
     const int* stop;
 };
 
-__device__ __forceinline__ uint32_t idesc_f16(int n) {     // kind::f16, fp16 A/B, fp32 D, K-major A and B, M = 128
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+struct Item {
+    int q_row0, q_rows;                        // first query row, valid rows of the tile (<= 128)
+    int k_row0, nk;                            // first key row, keys (<= 256)
+    int v0;                                    // first value row
+    int head, key;                             // key identifies the (group, head) whose K / V are in shared memory
+    int P;                                     // SELF: sequence length (band width); 0 = CROSS (every key is valid)
+};
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {       // non-blocking: has the phase with this parity completed?
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint32_t idesc_f16(int n, int b_mn) {     // kind::f16, fp16 A/B, fp32 D, K-major A, M = 128
+    return (1u << 4) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+}
+// MN-major B tile: rows = 32 keys of 128 bytes (64 head dims), SWIZZLE_128B; 8-key groups are 1024 B apart
+// (stride byte offset; the leading byte offset is unused because the 64 head dims are exactly one swizzle atom wide).
+// Verified on B200 against the transposed-cache path (tests/test_gpu_ops.py::test_attention_tcgen05_cross kind 6).
+__device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
 }
 
-struct Cursor {                                 // position in the item order (wireframe, head, tile), tile fastest
-    int wf, head, tile, tiles;
-    __device__ __forceinline__ void seek(const int* toff, int n_groups, int n_heads, int idx) {
-        wf = 0;
-        while (wf + 1 < n_groups && idx >= n_heads * toff[wf + 1]) ++wf;
-        tiles = toff[wf + 1] - toff[wf];
-        const int rem = idx - n_heads * toff[wf];
-        head = rem / tiles; tile = rem - head * tiles;
+// idx -> work item.  `hint` carries the group of the previous lookup (CROSS, items are visited in increasing order).
+__device__ __forceinline__ void get_item(const Params& p, const int* toff, int idx, int& hint, Item& it) {
+    const int H = p.n_heads;
+    if (p.mode == 0) {
+        int wf = hint;
+        while (wf + 1 < p.n_groups && idx >= H * toff[wf + 1]) ++wf;
+        hint = wf;
+        const int tiles = toff[wf + 1] - toff[wf];
+        const int rem = idx - H * toff[wf];
+        const int head = rem / tiles, tile = rem - head * tiles;
+        const long long q0 = (long long)p.seq_off[wf] * p.q_mul, q1 = (long long)p.seq_off[wf + 1] * p.q_mul;
+        it.q_row0 = (int)(q0 + (long long)tile * BQ);
+        it.q_rows = (int)min((long long)BQ, q1 - it.q_row0);
+        it.k_row0 = p.row_off[wf]; it.nk = p.vlen[wf];
+        it.v0 = it.k_row0;
+        it.head = head; it.key = wf * H + head; it.P = 0;
+    } else {
+        const int tile = idx / H, head = idx - tile * H;
+        const int s0 = tile * p.seqs_per_tile, ns = min(p.seqs_per_tile, p.n_seqs - s0);
+        it.q_row0 = s0 * p.P; it.q_rows = ns * p.P;
+        it.k_row0 = it.q_row0; it.nk = it.q_rows; it.v0 = it.q_row0;
+        it.head = head; it.key = idx; it.P = p.P;
     }
-    __device__ __forceinline__ void next(const int* toff, int n_groups, int n_heads) {
-        if (++tile < tiles) return;
-        tile = 0;
-        if (++head < n_heads) return;
-        head = 0;
-        do { ++wf; tiles = (wf < n_groups) ? toff[wf + 1] - toff[wf] : 1; } while (wf < n_groups && tiles == 0);
-    }
-};
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-              const __grid_constant__ CUtensorMap mapVt, const Params p) {
+              const __grid_constant__ CUtensorMap mapV, const Params p) {
     using namespace tc;
     if (p.stop != nullptr && *p.stop != 0) return;
 
@@ -85,33 +127,46 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t bar_base = p_s + P_BYTES;
     uint8_t* p_gen = smem_gen + (p_s - smem_base);
     int* toff = reinterpret_cast<int*>(smem_gen + (bar_base - smem_base) + BAR_BYTES);
-    // barriers
-    const uint32_t q_full = bar_base, q_empty = bar_base + 8, kv_full = bar_base + 16, kv_empty = bar_base + 24;
-    const uint32_t s_full = bar_base + 32, o_full = bar_base + 40, tmem_empty = bar_base + 48;
-    auto p_full = [&](uint32_t b) { return bar_base + 56 + 8 * b; };
-    auto p_empty = [&](uint32_t b) { return bar_base + 72 + 8 * b; };
-    const uint32_t tmem_slot = bar_base + 96;
+    // barriers (8 bytes each)
+    const uint32_t q_full = bar_base, q_empty = bar_base + 8;
+    auto kv_full = [&](uint32_t s) { return bar_base + 16 + 8 * s; };
+    auto kv_empty = [&](uint32_t s) { return bar_base + 32 + 8 * s; };
+    auto s_full = [&](uint32_t w) { return bar_base + 48 + 8 * w; };
+    auto o_full = [&](uint32_t w) { return bar_base + 64 + 8 * w; };
+    auto tmem_empty = [&](uint32_t w) { return bar_base + 80 + 8 * w; };
+    auto p_full = [&](uint32_t w, uint32_t b) { return bar_base + 96 + 8 * (2 * w + b); };
+    auto p_empty = [&](uint32_t w, uint32_t b) { return bar_base + 128 + 8 * (2 * w + b); };
+    const uint32_t tmem_slot = bar_base + 160;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    volatile int* done_cnt = reinterpret_cast<volatile int*>(smem_gen + (bar_base - smem_base) + 168);   // items finished per softmax warpgroup
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = p.n_groups, H = p.n_heads;
+    // K / V slots: CROSS keeps one (group, head) resident (<= 256 keys); SELF double-buffers per item (<= 128 keys)
+    const uint32_t n_slots = p.mode == 0 ? 1u : 2u;
+    const uint32_t k_tile = p.mode == 0 ? KMAX * 64 : (KMAX / 2) * 64;           // bytes of one (part, k-chunk) K tile
+    const uint32_t k_slot = 4 * k_tile, v_chunks = p.mode == 0 ? KMAX / KC : KMAX / KC / 2, v_slot = 2 * v_chunks * V_TILE;
 
-    // tiles per wireframe -> exclusive prefix in shared memory
-    for (int i = threadIdx.x; i < G; i += NUM_THREADS) {
-        const long long nq = ((long long)p.seq_off[i + 1] - p.seq_off[i]) * p.q_mul;
-        toff[i + 1] = (int)((nq + BQ - 1) / BQ);
+    if (p.mode == 0) {                                   // tiles per group -> exclusive prefix in shared memory
+        for (int i = threadIdx.x; i < p.n_groups; i += NUM_THREADS) {
+            const long long nq = ((long long)p.seq_off[i + 1] - p.seq_off[i]) * p.q_mul;
+            toff[i + 1] = (int)((nq + BQ - 1) / BQ);
+        }
     }
     if (threadIdx.x == 0) {
-        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
-        mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(tmem_empty, 128);
-        mbar_init(p_full(0), 128); mbar_init(p_full(1), 128); mbar_init(p_empty(0), 1); mbar_init(p_empty(1), 1);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (uint32_t s = 0; s < 2; ++s) {
+            mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
+            mbar_init(s_full(s), 1); mbar_init(o_full(s), 1); mbar_init(tmem_empty(s), 128);
+            mbar_init(p_full(s, 0), 128); mbar_init(p_full(s, 1), 128); mbar_init(p_empty(s, 0), 1); mbar_init(p_empty(s, 1), 1);
+        }
+        done_cnt[0] = 0; done_cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && p.mode == 0) {
         int acc = 0; toff[0] = 0;
-        for (int i = 1; i <= G; ++i) { acc += toff[i]; toff[i] = acc; }
+        for (int i = 1; i <= p.n_groups; ++i) { acc += toff[i]; toff[i] = acc; }
     }
     tc_fence_before();
     __syncthreads();
@@ -119,144 +174,191 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int item0 = (int)((long long)blockIdx.x * p.total_items / gridDim.x);
-    const int item1 = (int)((long long)(blockIdx.x + 1) * p.total_items / gridDim.x);
+    const int n_items = (int)((long long)(blockIdx.x + 1) * p.total_items / gridDim.x) - item0;
 
     if (warp == 0) {
-        if (lane == 0 && item0 < item1) {
+        if (lane == 0) {
             // ===== TMA producer =====
-            Cursor c; c.seek(toff, G, H, item0);
-            int cur_wf = -1, cur_head = -1; uint32_t n_kv = 0, n_q = 0;
-            for (int it = item0; it < item1; ++it, c.next(toff, G, H)) {
-                if (c.wf != cur_wf || c.head != cur_head) {
-                    cur_wf = c.wf; cur_head = c.head;
-                    mbar_wait(kv_empty, (n_kv & 1u) ^ 1u);                 // every MMA that read the previous K / Vt has retired
-                    const int nb = (p.vlen[c.wf] + KC - 1) / KC;
-                    mbar_expect_tx(kv_full, (uint32_t)nb * (4u * 2048u + 2u * V_TILE));
-                    const int col = p.layer_col + c.head * 64, krow = p.row_off[c.wf], vcol = p.colp_off[c.wf];
+            int hint = 0, cur_key = -1; uint32_t n_kv = 0;
+            for (int j = 0; j < n_items; ++j) {
+                Item it; get_item(p, toff, item0 + j, hint, it);
+                if (it.key != cur_key) {
+                    cur_key = it.key;
+                    const uint32_t slot = n_kv % n_slots;
+                    // every item that read the previous content of this slot must have finished its P V products: the softmax
+                    // warpgroups publish their completed-item counts after observing o_full
+                    const int need0 = (n_slots == 1u) ? (j + 1) / 2 : ((j & 1) ? 0 : j / 2);
+                    const int need1 = (n_slots == 1u) ? j / 2 : ((j & 1) ? j / 2 : 0);
+                    while (done_cnt[0] < need0 || done_cnt[1] < need1) __nanosleep(64);
+                    __threadfence_block();
+                    fence_proxy_async_smem();
+                    const int nb = (it.nk + KC - 1) / KC;
+                    mbar_expect_tx(kv_full(slot), (uint32_t)nb * (4u * 2048u + 2u * V_TILE));
+                    const uint32_t ks = k_s + slot * k_slot, vs = v_s + slot * v_slot;
                     for (int part = 0; part < 2; ++part)
                         for (int kch = 0; kch < 2; ++kch)
-                            for (int b = 0; b < nb; ++b)
-                                tma_load_3d(k_s + (part * 2 + kch) * K_TILE + b * 2048, &mapK, kv_full, col + kch * 32, krow + b * KC, part);
+                            for (int b2 = 0; b2 < nb; ++b2)
+                                tma_load_3d(ks + (part * 2 + kch) * k_tile + b2 * 2048, &mapK, kv_full(slot),
+                                            p.k_col + it.head * 64 + kch * 32, it.k_row0 + b2 * KC, part);
                     for (int part = 0; part < 2; ++part)
-                        for (int b = 0; b < nb; ++b)
-                            tma_load_3d(v_s + (part * (KMAX / KC) + b) * V_TILE, &mapVt, kv_full, vcol + b * KC, col, part);
+                        for (int b2 = 0; b2 < nb; ++b2) {
+                            const uint32_t dst = vs + (part * v_chunks + b2) * V_TILE;
+                            tma_load_3d(dst, &mapV, kv_full(slot), p.v_col + it.head * 64, it.v0 + b2 * KC, part);
+                        }
                     ++n_kv;
                 }
-                mbar_wait(q_empty, (n_q & 1u) ^ 1u);
+                while (!mbar_test(q_empty, ((uint32_t)j & 1u) ^ 1u)) __nanosleep(32);
                 mbar_expect_tx(q_full, Q_BYTES);
-                const int qrow = p.seq_off[c.wf] * p.q_mul + c.tile * BQ;
                 for (int part = 0; part < 2; ++part)
                     for (int kch = 0; kch < 2; ++kch)
-                        tma_load_3d(q_s + (part * 2 + kch) * Q_TILE, &mapQ, q_full, c.head * 64 + kch * 32, qrow, part);
-                ++n_q;
+                        tma_load_3d(q_s + (part * 2 + kch) * Q_TILE, &mapQ, q_full, p.q_col + it.head * 64 + kch * 32, it.q_row0, part);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && item0 < item1) {
-            // ===== MMA issuer =====
-            Cursor c; c.seek(toff, G, H, item0);
-            int cur_wf = -1, cur_head = -1; uint32_t n_kv = 0, n_it = 0, n_pc = 0;
-            const uint32_t d_s = tmem_base + S_COL, d_o = tmem_base + O_COL;
-            const uint32_t idesc_o = idesc_f16(64);
+        if (lane == 0) {
+            // ===== S issuer: S_j = Q_j K^T into the TMEM buffer of warpgroup j & 1 =====
             constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};            // (lo,hi), (hi,lo), (hi,hi): small products first
-            for (int it = item0; it < item1; ++it) {
-                const int wf = c.wf, head = c.head;
-                if (wf != cur_wf || head != cur_head) {
-                    cur_wf = wf; cur_head = head;
-                    mbar_wait(kv_full, n_kv & 1u);
+            int hint = 0, cur_key = -1; uint32_t n_kv = 0, slot = 0;
+            for (int j = 0; j < n_items; ++j) {
+                Item it; get_item(p, toff, item0 + j, hint, it);
+                const uint32_t w = (uint32_t)j & 1u;
+                if (it.key != cur_key) {
+                    cur_key = it.key;
+                    slot = n_kv % n_slots;
+                    mbar_wait(kv_full(slot), (n_kv / n_slots) & 1u);
                     ++n_kv;
                 }
-                const int lv = p.vlen[wf];
-                const int n16 = (lv + 15) & ~15, nb = (lv + KC - 1) / KC;
-                mbar_wait(q_full, n_it & 1u);
-                mbar_wait(tmem_empty, (n_it & 1u) ^ 1u);                   // S and O of the previous item have been read out
+                mbar_wait(q_full, (uint32_t)j & 1u);
+                mbar_wait(tmem_empty(w), (((uint32_t)j >> 1) & 1u) ^ 1u);  // S / O of this warpgroup's previous item have been read out
                 tc_fence_after();
-                const uint32_t idesc_s = idesc_f16(n16);
+                const uint32_t d_s = tmem_base + w * 256u;
+                const uint32_t idesc_s = idesc_f16((it.nk + 15) & ~15, 0);
+                const uint32_t ks = k_s + slot * k_slot;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int kch = 0; kch < 2; ++kch)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
+                    for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const uint64_t da = make_smem_desc(q_s + (pa[q] * 2 + kch) * Q_TILE) + (uint64_t)(2 * ks);
-                            const uint64_t db = make_smem_desc(k_s + (pb[q] * 2 + kch) * K_TILE) + (uint64_t)(2 * ks);
+                            const uint64_t da = make_smem_desc(q_s + (pa[q] * 2 + kch) * Q_TILE) + (uint64_t)(2 * s2);
+                            const uint64_t db = make_smem_desc(ks + (pb[q] * 2 + kch) * k_tile) + (uint64_t)(2 * s2);
                             umma_bf16(d_s, da, db, idesc_s, acc);
                             acc = 1;
                         }
                 umma_commit(q_empty);
-                umma_commit(s_full);
-                c.next(toff, G, H);
-                const bool last_of_group = (it + 1 == item1) || c.wf != wf || c.head != head;
-                acc = 0;
-                for (int b = 0; b < nb; ++b, ++n_pc) {
-                    const uint32_t buf = n_pc & 1u;
-                    mbar_wait(p_full(buf), (n_pc >> 1) & 1u);
+                umma_commit(s_full(w));
+            }
+        }
+    } else if (warp < 4) {
+        if (lane == 0) {
+            // ===== P V issuer of warpgroup w: O_j += P_c V_c as the softmax warpgroup publishes the chunks =====
+            constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+            const uint32_t w = (uint32_t)warp - 2u;
+            const uint32_t idesc_o = idesc_f16(64, 1);
+            const uint32_t d_o = tmem_base + w * 256u;                     // aliases S columns [0,64) of this warpgroup
+            int hint = 0, cur_key = -1; uint32_t n_kv = 0, slot = 0, c = 0;
+            for (int j = 0; j < n_items; ++j) {
+                Item it; get_item(p, toff, item0 + j, hint, it);
+                if (it.key != cur_key) { cur_key = it.key; slot = n_kv % n_slots; ++n_kv; }
+                if (((uint32_t)j & 1u) != w) continue;
+                const int nb = (it.nk + KC - 1) / KC;
+                const uint32_t vs = v_s + slot * v_slot;
+                uint32_t acc = 0;
+                for (int b2 = 0; b2 < nb; ++b2, ++c) {
+                    const uint32_t buf = c & 1u;
+                    mbar_wait(p_full(w, buf), (c >> 1) & 1u);
+                    // O aliases S columns [0,64): the first product must not start before S chunk 1 has been read (chunk 1 published)
+                    if (b2 == 0 && nb > 1) mbar_wait(p_full(w, buf ^ 1u), ((c + 1) >> 1) & 1u);
                     tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
+                    for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const uint64_t da = make_smem_desc(p_s + (buf * 2 + pa[q]) * P_TILE) + (uint64_t)(2 * ks);
-                            const uint64_t db = make_smem_desc(v_s + (pb[q] * (KMAX / KC) + b) * V_TILE) + (uint64_t)(2 * ks);
+                            const uint64_t da = make_smem_desc(p_s + ((w * 2 + buf) * 2 + pa[q]) * P_TILE) + (uint64_t)(2 * s2);
+                            const uint32_t vb = vs + (pb[q] * v_chunks + b2) * V_TILE;
+                            const uint64_t db = make_smem_desc_mn128(vb + s2 * 2048u);
                             umma_bf16(d_o, da, db, idesc_o, acc);
                             acc = 1;
                         }
-                    umma_commit(p_empty(buf));
+                    umma_commit(p_empty(w, buf));
                 }
-                umma_commit(o_full);
-                if (last_of_group) umma_commit(kv_empty);
-                ++n_it;
+                umma_commit(o_full(w));
             }
         }
     } else {
-        // ===== softmax + epilogue warps: thread = query row =====
+        // ===== softmax + epilogue warpgroups: thread = query row =====
+        const uint32_t w = (uint32_t)(warp - 4) >> 2;        // warpgroup 0 / 1
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + w * 256u;
         constexpr float kScale = 0.125f * 1.4426950408889634f;
-        // per-warp output staging: four 2 KB pieces that coincide with this warp's own rows of the four P tiles
-        auto piece = [&](int k) { return p_gen + k * P_TILE + q * 2048; };
-        Cursor c; c.seek(toff, G, H, item0 < item1 ? item0 : 0);
-        uint32_t n_it = 0, n_pc = 0;
-        for (int it = item0; it < item1; ++it, c.next(toff, G, H), ++n_it) {
-            const int lv = p.vlen[c.wf], nb = (lv + KC - 1) / KC;
-            const long long q_end = (long long)p.seq_off[c.wf + 1] * p.q_mul;
-            const long long qrow0 = (long long)p.seq_off[c.wf] * p.q_mul + (long long)c.tile * BQ;
-            mbar_wait(s_full, n_it & 1u);
+        uint8_t* pw = p_gen + w * 4 * P_TILE;                 // this warpgroup's P tiles [buf][part]
+        // per-warp output staging: four 2 KB pieces that coincide with this warp's own rows of its warpgroup's four P tiles
+        auto piece = [&](int k) { return pw + k * P_TILE + q * 2048; };
+        int hint = 0; uint32_t n_pc = 0;
+        for (int j = (int)w, k = 0; j < n_items; j += 2, ++k) {
+            Item it; get_item(p, toff, item0 + j, hint, it);
+            const int nb = (it.nk + KC - 1) / KC;
+            // keys this row attends to, and the union over the warp's rows
+            int klo = 0, khi = it.nk, wlo = 0, whi = it.nk;
+            if (it.P > 0) {
+                const bool valid = row < it.q_rows;
+                klo = valid ? (row / it.P) * it.P : 0; khi = valid ? klo + it.P : 0;
+                const int r0 = q * 32, r1 = min(q * 32 + 31, it.q_rows - 1);
+                wlo = (r0 / it.P) * it.P; whi = (r1 >= r0) ? (r1 / it.P) * it.P + it.P : 0;
+                if (r1 < r0) wlo = 0;
+            }
+            mbar_wait(s_full(w), (uint32_t)k & 1u);
             tc_fence_after();
             // ---- pass 1: row maximum over the valid keys ----
             float mx = -INFINITY;
             for (int b = 0; b < nb; ++b) {
+                if (b * KC >= whi || b * KC + KC <= wlo) continue;           // warp-uniform: no row of this warp attends to this chunk
                 uint32_t v[32];
-                tmem_ld32(t_lane + S_COL + b * KC, v);
+                tmem_ld32(t_s + b * KC, v);
                 tmem_ld_wait();
-                const int rem = lv - b * KC;
+                const int lo = klo - b * KC, hi = khi - b * KC;
+                if (lo <= 0 && hi >= KC) {                                  // whole chunk valid for this row
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < rem) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i >= lo && i < hi) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             const float bias = 12.0f - mx * kScale;           // p' = 2^(s*kScale - m' + 12) = 4096 * exp((s - m)/8)
             float lsum = 0.f;
             // ---- pass 2: probabilities per 32-key chunk -> fp16x2 -> shared memory (A operand of O += P V) ----
             for (int b = 0; b < nb; ++b, ++n_pc) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + S_COL + b * KC, v);
-                tmem_ld_wait();
                 const uint32_t buf = n_pc & 1u;
-                const int rem = lv - b * KC;
                 uint32_t hw[16], lw[16];
+                if (b * KC >= whi || b * KC + KC <= wlo) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), kScale, bias));
-                    p0 = (2 * i < rem) ? p0 : 0.f;
-                    p1 = (2 * i + 1 < rem) ? p1 : 0.f;
-                    lsum += p0 + p1;
-                    split_pair(p0, p1, hw[i], lw[i]);
+                    for (int i = 0; i < 16; ++i) { hw[i] = 0u; lw[i] = 0u; }
+                } else {
+                    uint32_t v[32];
+                    tmem_ld32(t_s + b * KC, v);
+                    tmem_ld_wait();
+                    const int lo = klo - b * KC, hi = khi - b * KC;
+                    const bool whole = (lo <= 0 && hi >= KC);                 // whole chunk valid for this row
+                    float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), kScale, bias));
+                        if (!whole) {
+                            p0 = (2 * i >= lo && 2 * i < hi) ? p0 : 0.f;
+                            p1 = (2 * i + 1 >= lo && 2 * i + 1 < hi) ? p1 : 0.f;
+                        }
+                        ls0 += p0; ls1 += p1;
+                        split_pair(p0, p1, hw[i], lw[i]);
+                    }
+                    lsum += ls0 + ls1;
                 }
-                mbar_wait(p_empty(buf), ((n_pc >> 1) & 1u) ^ 1u);         // the MMAs that read this buffer two chunks ago have retired
-                uint8_t* ph = p_gen + (buf * 2 + 0) * P_TILE + row * 64;
-                uint8_t* pl = p_gen + (buf * 2 + 1) * P_TILE + row * 64;
+                mbar_wait(p_empty(w, buf), ((n_pc >> 1) & 1u) ^ 1u);      // the MMAs that read this buffer two chunks ago have retired
+                uint8_t* ph = pw + (buf * 2 + 0) * P_TILE + row * 64;
+                uint8_t* pl = pw + (buf * 2 + 1) * P_TILE + row * 64;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {                          // 16-byte chunk cc lives at cc ^ ((row >> 1) & 3) (SWIZZLE_64B)
                     const int sw = (cc ^ ((row >> 1) & 3)) << 4;
@@ -264,17 +366,19 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lw[4 * cc], lw[4 * cc + 1], lw[4 * cc + 2], lw[4 * cc + 3]);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(p_full(buf));
+                tc_fence_before();                                        // this thread's S reads precede the O writes the arrive unlocks
+                mbar_arrive(p_full(w, buf));
             }
             // ---- epilogue: O / l -> fp16x2 -> global ----
-            mbar_wait(o_full, n_it & 1u);
+            mbar_wait(o_full(w), (uint32_t)k & 1u);
             tc_fence_after();
             uint32_t o0[32], o1[32];
-            tmem_ld32(t_lane + O_COL, o0);
-            tmem_ld32(t_lane + O_COL + 32, o1);
+            tmem_ld32(t_s, o0);
+            tmem_ld32(t_s + 32, o1);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(tmem_empty);
+            mbar_arrive(tmem_empty(w));
+            if ((warp & 3) == 0 && lane == 0) { __threadfence_block(); done_cnt[w] = k + 1; }   // this warpgroup's P V products of item j have retired
             const float inv = 1.0f / lsum;
             uint8_t* sh = piece(lane >> 4) + (lane & 15) * 128;           // hi row of this thread
             uint8_t* sl = piece(2 + (lane >> 4)) + (lane & 15) * 128;     // lo row
@@ -299,9 +403,8 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 for (int r4 = 0; r4 < 8; ++r4) {
                     const int r = r4 * 4 + (lane >> 3), ch = lane & 7;    // 8 lanes store one 128-byte row
                     const uint4 val = *reinterpret_cast<const uint4*>(piece(2 * part + (r >> 4)) + (r & 15) * 128 + ((ch ^ (r & 7)) << 4));
-                    const long long grow = qrow0 + q * 32 + r;
-                    if (grow < q_end)
-                        *reinterpret_cast<uint4*>(p.Os + (size_t)part * p.os_stride + (size_t)grow * p.ldo + c.head * 64 + ch * 8) = val;
+                    if (q * 32 + r < it.q_rows)
+                        *reinterpret_cast<uint4*>(p.Os + (size_t)part * p.os_stride + (size_t)(it.q_row0 + q * 32 + r) * p.ldo + it.head * 64 + ch * 8) = val;
                 }
             __syncwarp();
         }
@@ -309,28 +412,6 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// Transposed fp16x2 value cache: dst[part][col][colp_off[g] + j] = split(src[row_off[g] + j][col]); padding columns stay zero
-// (the buffer is zero-filled first).  grid (ceil(ld / 32), n_groups), block (32, 8).
-__global__ void build_vt_kernel(const float* __restrict__ src, int ld, const int* __restrict__ row_off, const int* __restrict__ vlen,
-                                const int* __restrict__ colp_off, uint16_t* __restrict__ dst, long long rp, int* ovf) {
-    __shared__ float tile[32][33];
-    const int g = blockIdx.y, c0 = blockIdx.x * 32;
-    const int r0 = row_off[g], n = vlen[g], cp = colp_off[g];
-    const long long part_stride = (long long)ld * rp;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        for (int jj = threadIdx.y; jj < 32; jj += 8) {
-            const int j = j0 + jj, col = c0 + threadIdx.x;
-            tile[jj][threadIdx.x] = (j < n && col < ld) ? src[(size_t)(r0 + j) * ld + col] : 0.f;
-        }
-        __syncthreads();
-        for (int cc = threadIdx.y; cc < 32; cc += 8) {
-            const int j = j0 + threadIdx.x, col = c0 + cc;
-            if (j < n && col < ld) store_split1(dst + (size_t)col * rp + cp + j, part_stride, tile[threadIdx.x][cc], 2, ovf);
-        }
-        __syncthreads();
-    }
 }
 
 }  // namespace ax

@@ -42,7 +42,8 @@ struct DevBuf {
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
         cap = want;
-        return cudaSuccess;
+        // fresh memory is zeroed: TMA boxes and GEMM tiles may touch rows past the valid ones, and 0 x (stale NaN pattern) must not happen
+        return cudaMemset(p, 0, want);
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -99,12 +100,11 @@ struct ffb_handle {
     DevBuf a_qkv, a_qc, kc_h, vc_h;               // [2][cap][3E], [2][cap][E], [2][R][Ld*E] halves
     CUtensorMap ms_qkv, ms_qc;
     bool half_pipe = false;                       // set per batch at plan time
-    // tcgen05 cross-attention (attn_x.cuh): transposed fp16x2 value cache [2][Ld*E][Rp] + TMA load maps of Q, K, Vt
-    DevBuf vt_h, d_colp_off;
-    long long Rp = 0;
-    CUtensorMap mx_q, mx_k, mx_vt;
-    bool attn_x_ok = false;                       // set per batch: half pipeline, <= 256 keys per wireframe, <= 1023 wireframes
-    int opt_attn_x = 1;
+    // tcgen05 attention (attn_x.cuh): TMA load maps
+    CUtensorMap mx_q, mx_k, mx_vrow;              // cross: Q rows of a_qc, K rows of kc_h, V rows of vc_h (MN-major operand)
+    CUtensorMap msf_q, msf_k, msf_v;              // self: q / k / v sections of a_qkv
+    bool attn_x_ok = false;                       // set per batch: half pipeline, <= 256 keys per wireframe, <= 255 wireframes
+    int opt_attn_x = 3;                           // bit 0: cross-attention on tcgen05, bit 1: self-attention on tcgen05
     int opt_attn_mma = 2;                         // attention core: 2 = mma.sync fp16x2 kernel (decode, while the GEMM format is fp16x2),
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
@@ -315,22 +315,24 @@ int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long o
     return FFB_OK;
 }
 
-// tcgen05 cross-attention: queries of wireframe i are rows [seq_off[i]*Pq, seq_off[i+1]*Pq) of Q, keys its rows of the cache
-int launch_attn_x(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const int* seq_off_dev,
-                  const std::vector<int>& seq_off_host, int Pq, const int* row_off, const int* vlen, const int* colp_off, int G,
-                  int layer_col, uint16_t* Os, long long os_stride, int ldo, double qk_pairs, const int* stop, cudaStream_t s) {
+// tcgen05 attention (attn_x.cuh).  The caller fills the mode-specific fields of `p`; total_items / grid are derived here.
+int launch_attn_x(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, ax::Params p,
+                  const std::vector<int>* seq_off_host, double qk_pairs, int prof_class, const int* stop, cudaStream_t s) {
     long long tiles = 0;
-    for (int i = 0; i < G; ++i) tiles += ((long long)(seq_off_host[i + 1] - seq_off_host[i]) * Pq + ax::BQ - 1) / ax::BQ;
+    if (p.mode == 0) {
+        for (int i = 0; i < p.n_groups; ++i)
+            tiles += ((long long)((*seq_off_host)[i + 1] - (*seq_off_host)[i]) * p.q_mul + ax::BQ - 1) / ax::BQ;
+    } else {
+        p.seqs_per_tile = ax::BQ / p.P;
+        tiles = (p.n_seqs + p.seqs_per_tile - 1) / p.seqs_per_tile;
+    }
     const long long items = tiles * h->H;
     if (items <= 0) return FFB_OK;
-    if (items > 0x7fffffffLL) return fail(h, FFB_ERR_ARG, "cross-attention: too many work items");
-    ax::Params p{};
-    p.seq_off = seq_off_dev; p.q_mul = Pq; p.row_off = row_off; p.vlen = vlen; p.colp_off = colp_off;
-    p.n_groups = G; p.n_heads = h->H; p.layer_col = layer_col; p.total_items = (int)items;
-    p.Os = Os; p.os_stride = os_stride; p.ldo = ldo; p.stop = stop;
+    if (items > 0x7fffffffLL) return fail(h, FFB_ERR_ARG, "attention: too many work items");
+    p.n_heads = h->H; p.total_items = (int)items; p.stop = stop;
     const int grid = (int)std::min<long long>(items, h->num_sms);
-    prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * qk_pairs, s);
-    ax::attn_x_kernel<<<grid, ax::NUM_THREADS, ax::SMEM_BYTES, s>>>(mq, mk, mvt, p);
+    prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
+    ax::attn_x_kernel<<<grid, ax::NUM_THREADS, ax::SMEM_BYTES, s>>>(mq, mk, mv, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -373,6 +375,20 @@ int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, ui
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (K=%llu rows=%llu)", (int)r,
                                        (unsigned long long)K, (unsigned long long)rows);
+    return FFB_OK;
+}
+
+// 16-bit [2][rows][ld] fp16x2 buffer -> 3-D LOAD map (col, row, split) with an explicit box and swizzle
+int encode_rows_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+                    CUtensorMapSwizzle swz) {
+    if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {ld, rows, 2};
+    const cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
+    const cuuint32_t box[3] = {box_cols, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(rows map) failed with CUresult %d", (int)r);
     return FFB_OK;
 }
 
@@ -548,9 +564,6 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     if (R > 0x7fffffffLL / std::max(h->E * 3, h->Ld * h->E)) return fail(h, FFB_ERR_ARG, "batch too large (memory rows)");
     h->h_row_off[N] = (int)R;
     h->R = R; h->Re = Re; h->max_vlen = max_vlen;
-    std::vector<int> colp_off(N + 1, 0);                                  // key columns of the transposed value cache, 32-aligned per wireframe
-    for (int i = 0; i < N; ++i) colp_off[i + 1] = colp_off[i] + (h->h_vlen[i] + 31) / 32 * 32;
-    h->Rp = std::max(colp_off[N], 32);
     pos_idx.resize(R); edge_src.resize(Re); edge_dst.resize(Re);
     long long e = 0;
     for (int i = 0; i < N; ++i) {
@@ -632,7 +645,6 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     FFB_TRY(upload(h, h->d_seq_off, h->h_seq_off, s));
     FFB_TRY(upload(h, h->d_slot_seq, slot_seq, s));
     FFB_TRY(upload(h, h->d_seq_slot, seq_slot, s));
-    FFB_TRY(upload(h, h->d_colp_off, colp_off, s));
     // the std::vectors above are pageable: make sure the copies are done before they go out of scope
     CU(h, cudaStreamSynchronize(s));
 
@@ -674,11 +686,13 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             h->attn_x_ok = (h->max_vlen <= ax::KMAX && N <= ax::MAX_GROUPS);
             if (h->attn_x_ok) {
                 const size_t LdE = (size_t)h->Ld * E;
-                CU(h, h->vt_h.ensure(2 * LdE * (size_t)h->Rp * 2));
                 FFB_TRY(encode_operand_map(h, &h->mx_q, h->a_qc.p, E, cr, ax::BQ, 2));
                 FFB_TRY(encode_operand_map(h, &h->mx_k, h->kc_h.p, LdE, (uint64_t)R, ax::KC, 2));
-                FFB_TRY(encode_operand_map(h, &h->mx_vt, h->vt_h.p, (uint64_t)h->Rp, LdE, 64, 2));
+                FFB_TRY(encode_rows_map(h, &h->mx_vrow, h->vc_h.p, LdE, (uint64_t)R, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
             }
+            FFB_TRY(encode_rows_map(h, &h->msf_q, h->a_qkv.p, 3 * E, cr, 32, ax::BQ, CU_TENSOR_MAP_SWIZZLE_64B));
+            FFB_TRY(encode_rows_map(h, &h->msf_k, h->a_qkv.p, 3 * E, cr, 32, ax::KC, CU_TENSOR_MAP_SWIZZLE_64B));
+            FFB_TRY(encode_rows_map(h, &h->msf_v, h->a_qkv.p, 3 * E, cr, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
         }
     }
     return FFB_OK;
@@ -731,12 +745,6 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
         split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
         split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
         h->launches += 2; CU(h, cudaGetLastError());
-        if (h->attn_x_ok) {  // transposed copy of the value cache for the tcgen05 cross-attention (B operand of O = P V, keys contiguous)
-            CU(h, cudaMemsetAsync(h->vt_h.p, 0, 2 * (size_t)LdE * (size_t)h->Rp * 2, s));
-            ax::build_vt_kernel<<<dim3((LdE + 31) / 32, N), dim3(32, 8), 0, s>>>(h->Vc.as<float>(), LdE, row_off, vlen, h->d_colp_off.as<int>(),
-                                                                              h->vt_h.as<uint16_t>(), h->Rp, h->state.as<int>() + 5);
-            h->launches++; CU(h, cudaGetLastError());
-        }
     }
     return FFB_OK;
 }
@@ -820,7 +828,11 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               else { l.C = qkv; l.ldc = 3 * E; l.Cmap = &h->mc_qkv3; }
               FFB_TRY(launch_tc(h, l, stop, s)); }
             if (!last) {
-                if (hp) {
+                if (hp && (h->opt_attn_x & 2) && P <= ax::BQ) {
+                    ax::Params ap{}; ap.mode = 1; ap.P = P; ap.n_seqs = B; ap.q_col = 0; ap.k_col = E; ap.v_col = 2 * E;
+                    ap.Os = aatt; ap.os_stride = ssE; ap.ldo = E;
+                    FFB_TRY(launch_attn_x(h, h->msf_q, h->msf_k, h->msf_v, ap, nullptr, (double)B * P * P, PC_ATTN_ROWS, stop, s));
+                } else if (hp) {
                     AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
                     AttnGroups g{}; g.ragged = 0; g.nq = P; g.nk = P; g.q_stride = P; g.q_off = 0; g.k_stride = P; g.o_stride = P;
                     FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, P, P, (double)B * P * P, PC_ATTN_ROWS, stop, s));
@@ -847,9 +859,12 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               else { l.C = qkv; l.ldc = E; l.Cmap = &h->mc_qkv1; }
               FFB_TRY(launch_tc(h, l, stop, s)); }
             { AttnGroups g{}; g.ragged = 1; g.q_begin = seq_off; g.q_mul = Pq; g.k_begin = row_off; g.k_len = vlen;
-              if (hp && h->attn_x_ok && h->opt_attn_x) {
-                  FFB_TRY(launch_attn_x(h, h->mx_q, h->mx_k, h->mx_vt, seq_off, h->h_seq_off, Pq, row_off, vlen, h->d_colp_off.as<int>(), N,
-                                        li * E, aatt, ssE, E, h->sum_seq_vlen * Pq, stop, s));
+              if (hp && h->attn_x_ok && (h->opt_attn_x & 1)) {
+                  ax::Params ap{}; ap.mode = 0; ap.seq_off = seq_off; ap.q_mul = Pq; ap.row_off = row_off; ap.vlen = vlen;
+                  ap.n_groups = N; ap.q_col = 0; ap.k_col = li * E; ap.v_col = li * E;
+                  ap.Os = aatt; ap.os_stride = ssE; ap.ldo = E;
+                  FFB_TRY(launch_attn_x(h, h->mx_q, h->mx_k, h->mx_vrow, ap, &h->h_seq_off, h->sum_seq_vlen * Pq,
+                                        PC_ATTN_TILED, stop, s));
               } else if (hp) {
                   const long long kvs = (long long)h->R * LdE;
                   AttnHalfIn in{aqc, h->cap_rows * E, E, h->kc_h.as<uint16_t>() + (size_t)li * E, kvs, h->vc_h.as<uint16_t>() + (size_t)li * E, kvs, LdE};
@@ -970,7 +985,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->vt_h, &h->d_colp_off};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -995,7 +1010,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_ATTN_MMA:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
             h->opt_attn_mma = value; return FFB_OK;
-        case FFB_OPT_ATTN_X: h->opt_attn_x = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -1381,45 +1396,47 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
         qh.release(); kh.release(); vh.release();
         return rc;
     }
-    if (kind == 5) {     // tcgen05 cross-attention kernel: group g = "wireframe" g with nq queries and nk (<= 256) keys
-        if (nk > ax::KMAX || G > ax::MAX_GROUPS) return fail(h, FFB_ERR_UNSUPPORTED, "op_attention kind 5: needs nk <= 256 and G <= 1023");
-        if (ldq != H * 64 || ldk % 32 || ldk < H * 64) return fail(h, FFB_ERR_ARG, "op_attention kind 5: ldq must be H*64, ldk a multiple of 32");
-        const size_t Mq = (size_t)G * nq, Mp = (Mq + 127) / 128 * 128, Rk = (size_t)G * nk;
-        const int nkp = (nk + 31) / 32 * 32;
-        const size_t Rp = (size_t)G * nkp;
-        std::vector<int> seq_off(G + 1), row_off(G), vlen(G), colp(G);
+    if (kind == 5 || kind == 6) {
+        // tcgen05 kernel.  5: CROSS (group g = "wireframe" g with nq queries, nk <= 256 keys); 6: SELF (block-diagonal over G
+        // sequences of nq == nk <= 128 rows)
+        const bool self = (kind == 6);
+        if (nk > ax::KMAX || (!self && G > ax::MAX_GROUPS)) return fail(h, FFB_ERR_UNSUPPORTED, "op_attention kind 5: needs nk <= 256 and G <= 255");
+        if (self && (nq != nk || nq > ax::BQ)) return fail(h, FFB_ERR_UNSUPPORTED, "op_attention kind 6: needs nq == nk <= 128");
+        if (ldq != H * 64 || ldk % 32 || ldk < H * 64) return fail(h, FFB_ERR_ARG, "op_attention kind 5/6: ldq must be H*64, ldk a multiple of 32");
+        const size_t Mq = (size_t)G * nq, Rk = (size_t)G * nk;
+        std::vector<int> seq_off(G + 1), row_off(G), vlen(G);
         for (int g = 0; g <= G; ++g) seq_off[g] = g;
-        for (int g = 0; g < G; ++g) { row_off[g] = g * nk; vlen[g] = nk; colp[g] = g * nkp; }
-        DevBuf qh, kh, vt, os, meta;
+        for (int g = 0; g < G; ++g) { row_off[g] = g * nk; vlen[g] = nk; }
+        DevBuf qh, kh, vh, os, meta;
         int rc = FFB_OK;
         do {
-            if (qh.ensure(2 * Mp * ldq * 2) != cudaSuccess || kh.ensure(2 * Rk * ldk * 2) != cudaSuccess || vt.ensure(2 * (size_t)ldk * Rp * 2) != cudaSuccess ||
-                os.ensure(2 * Mp * ldq * 2) != cudaSuccess || meta.ensure((4 * (size_t)G + 1) * sizeof(int)) != cudaSuccess) {
+            if (qh.ensure(2 * Mq * ldq * 2) != cudaSuccess || kh.ensure(2 * Rk * ldk * 2) != cudaSuccess || vh.ensure(2 * Rk * ldk * 2) != cudaSuccess ||
+                os.ensure(2 * Mq * ldq * 2) != cudaSuccess || meta.ensure((3 * (size_t)G + 1) * sizeof(int)) != cudaSuccess) {
                 rc = fail(h, FFB_ERR_CUDA, "op_attention: out of device memory"); break; }
             int* m = meta.as<int>();
             cudaMemcpyAsync(m, seq_off.data(), (G + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
             cudaMemcpyAsync(m + G + 1, row_off.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
             cudaMemcpyAsync(m + 2 * G + 1, vlen.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
-            cudaMemcpyAsync(m + 3 * G + 1, colp.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
-            cudaMemsetAsync(qh.p, 0, 2 * Mp * ldq * 2, s); cudaMemsetAsync(vt.p, 0, 2 * (size_t)ldk * Rp * 2, s);
-            cudaMemsetAsync(os.p, 0, 2 * Mp * ldq * 2, s);
-            // q is [Mq, ldq] contiguous: split as one array, the parts are then Mq*ldq elements apart (the map below says so)
+            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention: upload failed"); break; }
+            // [rows, ld] contiguous arrays: split as one array, the parts are then rows*ld elements apart (the maps below say so)
             split_array_kernel<<<grid1d((long long)Mq * ldq / 4), 256, 0, s>>>(q, qh.as<uint16_t>(), (long long)Mq * ldq / 4, 1.0f, 2);
             split_array_kernel<<<grid1d((long long)Rk * ldk / 4), 256, 0, s>>>(k, kh.as<uint16_t>(), (long long)Rk * ldk / 4, 1.0f, 2);
-            ax::build_vt_kernel<<<dim3((ldk + 31) / 32, G), dim3(32, 8), 0, s>>>(v, ldk, m + G + 1, m + 2 * G + 1, m + 3 * G + 1, vt.as<uint16_t>(),
-                                                                              (long long)Rp, nullptr);
+            split_array_kernel<<<grid1d((long long)Rk * ldk / 4), 256, 0, s>>>(v, vh.as<uint16_t>(), (long long)Rk * ldk / 4, 1.0f, 2);
             h->launches += 3;
-            CUtensorMap mq, mk, mvt;
-            if ((rc = encode_operand_map(h, &mq, qh.p, ldq, Mq, ax::BQ, 2)) != FFB_OK) break;
-            if ((rc = encode_operand_map(h, &mk, kh.p, ldk, Rk, ax::KC, 2)) != FFB_OK) break;
-            if ((rc = encode_operand_map(h, &mvt, vt.p, Rp, ldk, 64, 2)) != FFB_OK) break;
-            if ((rc = launch_attn_x(h, mq, mk, mvt, m, seq_off, nq, m + G + 1, m + 2 * G + 1, m + 3 * G + 1, G, 0, os.as<uint16_t>(),
-                                    (long long)Mp * ldq, ldq, (double)G * nq * nk, nullptr, s)) != FFB_OK) break;
-            sum_split_kernel<<<grid1d((long long)Mq * ldq), 256, 0, s>>>(os.as<uint16_t>(), (long long)Mp * ldq, out, (long long)Mq * ldq, 2);
+            CUtensorMap mq, mk, mv;
+            if ((rc = encode_rows_map(h, &mq, qh.p, ldq, Mq, 32, ax::BQ, CU_TENSOR_MAP_SWIZZLE_64B)) != FFB_OK) break;
+            if ((rc = encode_rows_map(h, &mk, kh.p, ldk, Rk, 32, ax::KC, CU_TENSOR_MAP_SWIZZLE_64B)) != FFB_OK) break;
+            if ((rc = encode_rows_map(h, &mv, vh.p, ldk, Rk, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B)) != FFB_OK) break;
+            ax::Params ap{};
+            ap.Os = os.as<uint16_t>(); ap.os_stride = (long long)Mq * ldq; ap.ldo = ldq;
+            if (self) { ap.mode = 1; ap.P = nq; ap.n_seqs = G; }
+            else { ap.mode = 0; ap.seq_off = m; ap.q_mul = nq; ap.row_off = m + G + 1; ap.vlen = m + 2 * G + 1; ap.n_groups = G; }
+            if ((rc = launch_attn_x(h, mq, mk, mv, ap, &seq_off, (double)G * nq * nk, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break;
+            sum_split_kernel<<<grid1d((long long)Mq * ldq), 256, 0, s>>>(os.as<uint16_t>(), (long long)Mq * ldq, out, (long long)Mq * ldq, 2);
             h->launches++;
-            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention kind 5: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention kind %d: %s", kind, cudaGetErrorString(cudaGetLastError())); break; }
         } while (0);
-        qh.release(); kh.release(); vt.release(); os.release(); meta.release();
+        qh.release(); kh.release(); vh.release(); os.release(); meta.release();
         return rc;
     }
     const int saved = h->opt_attn_mma, saved_fmt = h->tc_fmt;

@@ -177,8 +177,9 @@ enum { FFB_OPT_STAGGER = 8 };
 /* 1 (default): fp16x2 GEMM writes fp32 outputs with asynchronous TMA bulk stores (reduce-add for the in-place residual);
  * 0 = coalesced st.global epilogue. */
 enum { FFB_OPT_TMA_EPILOGUE = 9 };
-/* 1 (default): decoder cross-attention of the fp16x2 pipeline runs on the tcgen05 kernel (attn_x.cuh; needs <= 256 keys per
- * wireframe, otherwise the mma.sync kernel is used automatically); 0 = always the mma.sync kernel. */
+/* Attention cores of the fp16x2 pipeline on the tcgen05 kernel (attn_x.cuh), bit mask: 1 = decoder cross-attention (needs <= 256
+ * keys per wireframe and <= 255 wireframes per batch, otherwise the mma.sync kernel is used automatically), 2 = decoder
+ * self-attention (prefix <= 128).  Default 3; 0 = always the mma.sync kernel. */
 enum { FFB_OPT_ATTN_X = 10 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----

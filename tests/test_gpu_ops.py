@@ -107,16 +107,34 @@ def test_attention_half_inputs(eng, G, nq, nk):
     assert np.max(np.abs(got - want)) <= 2e-5
 
 
-@pytest.mark.parametrize("G,nq,nk", [(3, 1, 1), (5, 7, 7), (4, 36, 36), (2, 37, 37), (2, 130, 65), (3, 64, 220), (1, 258, 256),
-                                     (6, 300, 33), (40, 1, 36), (9, 513, 100), (160, 140, 224)])
-def test_attention_tcgen05_cross(eng, G, nq, nk):
-    """attn_x_kernel (tcgen05 + TMEM + TMA): S = Q K^T and O = P V as fp16x2 split products, softmax in fp32, <= 256 keys.
-    The last case has more work items than SMs x 8, so persistent CTAs walk several (group, head) pairs and tiles."""
+CROSS_CASES = [(3, 1, 1), (5, 7, 7), (4, 36, 36), (2, 37, 37), (2, 130, 65), (3, 64, 220), (1, 258, 256), (6, 300, 33), (40, 1, 36),
+               (9, 513, 100), (160, 140, 224)]
+
+
+@pytest.mark.parametrize("G,nq,nk", CROSS_CASES)
+def test_attention_tcgen05_cross(eng, G, nq, nk, kind=5):
+    """attn_x_kernel (tcgen05 + TMEM + TMA), CROSS mode: S = Q K^T and O = P V as fp16x2 split products, softmax in fp32,
+    <= 256 keys, V rows consumed through an MN-major descriptor.  The last case has more work items than SMs x 8, so persistent
+    CTAs walk several (group, head) pairs and tiles."""
     H = OURS.num_head
     rng = np.random.default_rng(G * 100 + nq + nk + 2)
     q = (rng.normal(size=(G * nq, H * 64)) * 1.5).astype(np.float32)
     k = (rng.normal(size=(G * nk, H * 64)) * 1.5).astype(np.float32)
     v = (rng.normal(size=(G * nk, H * 64)) * 1.5).astype(np.float32)
-    got = eng.op_attention(5, _t(q), _t(k), _t(v), G, nq, nk).cpu().numpy()
+    got = eng.op_attention(kind, _t(q), _t(k), _t(v), G, nq, nk).cpu().numpy()
     want = _attn_ref(q, k, v, G, nq, nk, H)
+    assert np.max(np.abs(got - want)) <= 2e-5
+
+
+@pytest.mark.parametrize("G,P", [(1, 1), (3, 1), (300, 1), (7, 2), (5, 7), (40, 16), (9, 31), (10, 32), (11, 33), (100, 36), (7, 37),
+                                 (3, 64), (5, 65), (2, 128), (3000, 36), (2500, 5)])
+def test_attention_tcgen05_self(eng, G, P):
+    """attn_x_kernel, SELF mode: tiles of floor(128 / P) whole sequences, block-diagonal softmax (decoder self-attention, no mask)."""
+    H = OURS.num_head
+    rng = np.random.default_rng(G * 100 + P + 3)
+    q = (rng.normal(size=(G * P, H * 64)) * 1.5).astype(np.float32)
+    k = (rng.normal(size=(G * P, H * 64)) * 1.5).astype(np.float32)
+    v = (rng.normal(size=(G * P, H * 64)) * 1.5).astype(np.float32)
+    got = eng.op_attention(6, _t(q), _t(k), _t(v), G, P, P).cpu().numpy()
+    want = _attn_ref(q, k, v, G, P, P, H)
     assert np.max(np.abs(got - want)) <= 2e-5

@@ -146,9 +146,11 @@ def test_tensor_core_and_simt_paths_agree_on_a_real_batch():
     assert ok, d
 
 
-def test_tcgen05_cross_attention_agrees_with_mma_sync_on_a_real_batch():
-    """Same batch decoded with the cross-attention core on tcgen05 (attn_x_kernel, default) and on mma.sync (attn_h_kernel):
-    identical tokens, logits within tolerance; ragged wireframes (different key counts, tiles straddling wireframes)."""
+@pytest.mark.parametrize("attn_x", [1, 2, 3])
+def test_tcgen05_attention_agrees_with_mma_sync_on_a_real_batch(attn_x):
+    """Same batch decoded with the attention cores on tcgen05 (attn_x_kernel; bit 0 cross, bit 1 self) and on
+    mma.sync (attn_h_kernel): identical tokens, logits within tolerance; ragged wireframes (different key counts, tiles
+    straddling wireframes and sequences)."""
     from faceformer_b200 import synth
     from faceformer_b200.lib import FFB_OPT_ATTN_X
     cfg = OURS
@@ -157,7 +159,7 @@ def test_tcgen05_cross_attention_agrees_with_mma_sync_on_a_real_batch():
     coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
     mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
     out = []
-    for mode in (0, 1):
+    for mode in (0, attn_x):
         e = Engine(cfg, MODE_PARALLEL, 0)
         e.load_state_dict(sd)
         e.set_option(FFB_OPT_TENSOR_CORE, 2)
