@@ -311,6 +311,12 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             }
             mbar_wait(s_full(w), (uint32_t)k & 1u);
             tc_fence_after();
+            // valid-key bit mask of this row within chunk b (CROSS: the same for every row; SELF: the row's own sequence)
+            auto chunk_mask = [&](int b) -> uint32_t {
+                const int lo = max(klo - b * KC, 0), hi = min(khi - b * KC, KC);
+                if (hi <= lo) return 0u;
+                return (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            };
             // ---- pass 1: row maximum over the valid keys ----
             float mx = -INFINITY;
             for (int b = 0; b < nb; ++b) {
@@ -318,13 +324,18 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                 uint32_t v[32];
                 tmem_ld32(t_s + b * KC, v);
                 tmem_ld_wait();
-                const int lo = klo - b * KC, hi = khi - b * KC;
-                if (lo <= 0 && hi >= KC) {                                  // whole chunk valid for this row
+                const uint32_t M = chunk_mask(b);
+                if (M == 0xffffffffu) {                                     // whole chunk valid for this row
+                    float m0 = mx, m1 = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                } else {
+                    for (int i = 0; i < 32; i += 4) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+                    }
+                    mx = fmaxf(m0, m1);
+                } else if (M != 0u) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (i >= lo && i < hi) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (M & (1u << i)) ? __uint_as_float(v[i]) : -INFINITY);
                 }
             }
             const float bias = 12.0f - mx * kScale;           // p' = 2^(s*kScale - m' + 12) = 4096 * exp((s - m)/8)
@@ -340,19 +351,29 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                     uint32_t v[32];
                     tmem_ld32(t_s + b * KC, v);
                     tmem_ld_wait();
-                    const int lo = klo - b * KC, hi = khi - b * KC;
-                    const bool whole = (lo <= 0 && hi >= KC);                 // whole chunk valid for this row
+                    const uint32_t M = chunk_mask(b);
                     float ls0 = 0.f, ls1 = 0.f;
+                    if (M == 0xffffffffu) {                                 // whole chunk valid: no selects
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
-                        float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), kScale, bias));
-                        if (!whole) {
-                            p0 = (2 * i >= lo && 2 * i < hi) ? p0 : 0.f;
-                            p1 = (2 * i + 1 >= lo && 2 * i + 1 < hi) ? p1 : 0.f;
+                        for (int i = 0; i < 16; ++i) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), kScale, bias));
+                            ls0 += p0; ls1 += p1;
+                            split_pair(p0, p1, hw[i], lw[i]);
                         }
-                        ls0 += p0; ls1 += p1;
-                        split_pair(p0, p1, hw[i], lw[i]);
+                    } else if (M != 0u) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), kScale, bias));
+                            p0 = (M & (1u << (2 * i))) ? p0 : 0.f;
+                            p1 = (M & (2u << (2 * i))) ? p1 : 0.f;
+                            ls0 += p0; ls1 += p1;
+                            split_pair(p0, p1, hw[i], lw[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { hw[i] = 0u; lw[i] = 0u; }
                     }
                     lsum += ls0 + ls1;
                 }
