@@ -94,6 +94,7 @@ struct ffb_handle {
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
     int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
     int opt_tma_out = 1;                          // fp16x2 GEMM: asynchronous TMA store / reduce-add epilogue
+    int opt_gemm_variant = 2;                     // fp16x2 GEMM pipeline variant (gemm_tc.cuh Cfg<NS, V>): 0, 1, or 2 = per launch
     CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
     CUtensorMap ms_h;                             // fp16x2 split STORE map of a_h (FFN hidden)
     // "half pipeline" (fp16x2 GEMM + fp16x2 attention): q,k,v and the cross-attention query never exist in fp32
@@ -444,7 +445,11 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     // TMA epilogue: only when the residual (if any) is the in-place form C += ..., which a reduce-add expresses exactly
     p.tma_out = (h->opt_tma_out && h->tc_fmt == 2 && l.Cmap && ((l.C && (!l.R || (l.R == l.C && l.ldr == l.ldc))) || (!l.C && l.Cs))) ? 1 : 0;
     const CUtensorMap& mc = l.Cmap ? *l.Cmap : *l.W;
-    if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+    // variant 1 (two staging buffers, 3 operand stages) is faster for plain / split stores, variant 0 for the in-place residual (measured,
+    // profiles/tune_gemm.py --random); 2 = choose per launch
+    if (h->tc_fmt == 2 && (h->opt_gemm_variant == 1 || (h->opt_gemm_variant == 2 && !l.R)))
+        tc::gemm_kernel<2, 1><<<grid, tc::NUM_THREADS, tc::Cfg<2, 1>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+    else if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
     else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
     prof_end(h, s);
     h->launches++;
@@ -952,6 +957,7 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2, 1>::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(ax::attn_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ax::SMEM_BYTES);
@@ -1011,6 +1017,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
             h->opt_attn_mma = value; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
+        case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1 or 2 (auto)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -1335,6 +1342,10 @@ int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t 
             cs.ensure(3 * Mp * (size_t)N * 2) != cudaSuccess || cf.ensure(Mp * (size_t)N * 4) != cudaSuccess) {
             rc = fail(h, FFB_ERR_CUDA, "bench_linear_tc: out of device memory"); break; }
         cudaMemsetAsync(as.p, 0, 3 * Mp * K * 2, s); cudaMemsetAsync(ws.p, 0, 3 * (size_t)N * K * 2, s);
+        if (flags & 32) {   // realistic operand bits (power draw depends on the data): pseudo-random fp16 values in (-2, 2) and their small "lo" parts
+            fill_random_half_kernel<<<grid1d((long long)(3 * Mp * K)), 256, 0, s>>>(as.as<uint16_t>(), (long long)(3 * Mp * K), (long long)(Mp * K), 1u);
+            fill_random_half_kernel<<<grid1d((long long)(3 * (size_t)N * K)), 256, 0, s>>>(ws.as<uint16_t>(), (long long)(3 * (size_t)N * K), (long long)((size_t)N * K), 2u);
+        }
         cudaMemsetAsync(cf.p, 0, Mp * (size_t)N * 4, s); cudaMemsetAsync(bias.p, 0, (size_t)N * 4, s);
         CUtensorMap mA, mW;
         if ((rc = encode_operand_map(h, &mA, as.p, K, Mp, tc::BM, h->tc_fmt)) != FFB_OK) break;

@@ -49,20 +49,24 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
-template <int NS> struct Cfg {
+// V: pipeline variant of the fp16x2 kernel.  0 = 4 operand stages + one 4 KB epilogue staging buffer per warp;
+//    1 = 3 operand stages + two staging buffers per warp (the next 32x32 block is formatted while TMA still reads the previous one)
+template <int NS, int V = 0> struct Cfg {
     static_assert(NS == 2 || NS == 3, "NS: 2 = fp16x2, 3 = bf16x3");
-    static constexpr int STAGES = (NS == 2) ? 4 : 3;
+    static_assert(V == 0 || (V == 1 && NS == 2), "variant 1 exists for fp16x2 only");
+    static constexpr int STAGES = (NS == 2) ? (V == 1 ? 3 : 4) : 3;
+    static constexpr int EPI_BUFS = (V == 1) ? 2 : 1;
     static constexpr int DRAIN_KB = (NS == 2) ? 4 : 2;            // k-blocks accumulated in TMEM per drain (24 MMAs either way)
     static constexpr int NPROD = (NS == 2) ? 3 : 6;
     static constexpr int STAGE_BYTES = NS * (A_TILE_BYTES + B_TILE_BYTES);            // 48 KB / 72 KB
     static constexpr bool STAGED_EPI = (NS == 2);
-    static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * 32 * 32 * 4 : 0;        // 32 KB
+    static constexpr int EPI_BYTES = STAGED_EPI ? EPI_BUFS * EPI_WARPS * 32 * 32 * 4 : 0;        // 32 / 64 KB
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     // kind::f16 instruction descriptor: D=f32 (bit 4), A/B format (0 = f16, 1 = bf16) at bits 7/10, K-major, N=256, M=128
     static constexpr uint32_t FMT = (NS == 2) ? 0u : 1u;
     static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
-static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<3>::SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<2, 1>::SMEM_BYTES <= 232448 && Cfg<3>::SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 
 struct Params {
     int M, N, K;                 // N % 256 == 0, K % 32 == 0
@@ -118,7 +122,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N = 0> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
@@ -165,11 +169,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int NS>
+template <int NS, int V = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapC, const Params p) {
-    using C_ = Cfg<NS>;
+    using C_ = Cfg<NS, V>;
     constexpr int STAGES = C_::STAGES, DRAIN_KB = C_::DRAIN_KB, STAGE_BYTES = C_::STAGE_BYTES;
     if (p.stop != nullptr && *p.stop != 0) return;
 
@@ -267,7 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         const int e = warp - EPI_WARP0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int hcol = e >> 2;                      // which 128-column half of the tile
-        float* stg = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base)) + e * 1024;   // 32x32 floats per warp (NS = 2)
+        float* stg0 = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base)) + e * 1024 * C_::EPI_BUFS;   // 32x32 floats per warp and buffer (NS = 2)
+        uint32_t n_blk = 0;                           // 32x32 blocks handed to TMA so far (selects the staging buffer)
         float acc[128];
         uint32_t c = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -302,14 +307,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                 // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----
                 const bool tma_out = p.tma_out && (p.C != nullptr);
                 const bool tma_cs = p.tma_out && (p.C == nullptr) && (p.Cs != nullptr);
-                const uint32_t stg_s = epi_base + (uint32_t)e * 4096u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                 // (fully unrolled: acc[] must stay in registers)
+                    const uint32_t sbuf = (C_::EPI_BUFS == 2) ? (n_blk & 1u) : 0u;
+                    float* stg = stg0 + sbuf * 1024;
+                    const uint32_t stg_s = epi_base + ((uint32_t)e * C_::EPI_BUFS + sbuf) * 4096u;
                     if (tma_cs) {
                         // ---- asynchronous split output: the block goes out as two fp16 tiles (hi, lo) of 32 x 32 halves, laid out as the
                         // SWIZZLE_64B boxes of mapC (3-D: col, row, split) expect: 64-byte rows, 16-byte chunk c stored at c ^ ((row >> 1) & 3)
-                        if (lane == 0) tma_store_wait_read();
+                        if (lane == 0) tma_store_wait_read<C_::EPI_BUFS - 1>();
                         __syncwarp();
+                        ++n_blk;
                         bool ovf = false;
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {                 // 8 values per 16-byte chunk
@@ -343,8 +351,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         // ---- asynchronous path: the 32x32 block (value = acc*scale + bias, ReLU) is laid out exactly as the
                         // SWIZZLE_128B box of mapC expects and handed to the TMA engine: plain store, or reduce-add into C when the
                         // residual aliases C (x += ...).  The warp does not wait for global memory, only for its staging buffer.
-                        if (lane == 0) tma_store_wait_read();          // previous block has been read out of the staging buffer
+                        if (lane == 0) tma_store_wait_read<C_::EPI_BUFS - 1>();   // the block that used this staging buffer has been read out
                         __syncwarp();
+                        ++n_blk;
 #pragma unroll
                         for (int cc = 0; cc < 8; ++cc) {
                             float4 v = make_float4(acc[j * 32 + 4 * cc] * p.out_scale, acc[j * 32 + 4 * cc + 1] * p.out_scale,

@@ -105,6 +105,15 @@ __global__ void absmax_kernel(const float* __restrict__ src, long long n, int* _
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_int(m));
 }
 
+// benchmark helper: pseudo-random halves; elements of the first split ~ U(-2, 2), later splits ~ 2^-11 of that (like real lo parts)
+__global__ void fill_random_half_kernel(uint16_t* __restrict__ dst, long long n, long long split_stride, unsigned seed) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned x = (unsigned)i * 2654435761u + seed * 40503u; x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+        const float u = ((x & 0xffffu) / 32768.0f - 1.0f) * 2.0f;
+        dst[i] = __half_as_ushort(__float2half_rn(i < split_stride ? u : u * 4.8828125e-4f));
+    }
+}
+
 // dst[i] = sum of the splits of element i  (test hook: re-sum a split array)
 __global__ void sum_split_kernel(const uint16_t* __restrict__ src, long long stride, float* __restrict__ dst, long long n, int fmt) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -181,6 +181,9 @@ enum { FFB_OPT_TMA_EPILOGUE = 9 };
  * keys per wireframe and <= 255 wireframes per batch, otherwise the mma.sync kernel is used automatically), 2 = decoder
  * self-attention (prefix <= 128).  Default 3; 0 = always the mma.sync kernel. */
 enum { FFB_OPT_ATTN_X = 10 };
+/* fp16x2 GEMM pipeline variant: 0 = 4 operand stages + 1 epilogue staging buffer per warp, 1 = 3 stages + 2 staging buffers,
+ * 2 (default) = variant 1 for plain / split stores and variant 0 for the in-place residual. */
+enum { FFB_OPT_GEMM_VARIANT = 11 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
