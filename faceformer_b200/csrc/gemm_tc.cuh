@@ -318,25 +318,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         if (lane == 0) tma_store_wait_read<C_::EPI_BUFS - 1>();
                         __syncwarp();
                         ++n_blk;
-                        bool ovf = false;
+                        float amax = 0.f;                                // max |value| of the block: one FMNMX per value instead of two compares
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {                 // 8 values per 16-byte chunk
+                            float xv[8];
+                            if (p.bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 32 + 8 * cc));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 32 + 8 * cc + 4));
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) xv[u] = fmaf(acc[j * 32 + 8 * cc + u], p.out_scale, bv[u]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) xv[u] = acc[j * 32 + 8 * cc + u] * p.out_scale;
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) xv[u] = fmaxf(xv[u], 0.f);
+                            }
                             uint32_t hw[4], lw[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                float x0 = acc[j * 32 + 8 * cc + 2 * u] * p.out_scale, x1 = acc[j * 32 + 8 * cc + 2 * u + 1] * p.out_scale;
-                                if (p.bias) { x0 += __ldg(p.bias + col0 + j * 32 + 8 * cc + 2 * u); x1 += __ldg(p.bias + col0 + j * 32 + 8 * cc + 2 * u + 1); }
-                                if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                                ovf |= !(fabsf(x0) <= 65504.f) | !(fabsf(x1) <= 65504.f);
-                                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-                                hw[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                lw[u] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                                const float x0 = xv[2 * u], x1 = xv[2 * u + 1];
+                                amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                                const __half2 h = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                                hw[u] = *reinterpret_cast<const uint32_t*>(&h);
+                                lw[u] = *reinterpret_cast<const uint32_t*>(&l);
                             }
                             uint8_t* base = reinterpret_cast<uint8_t*>(stg) + lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4);
                             *reinterpret_cast<uint4*>(base) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                             *reinterpret_cast<uint4*>(base + 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
+                        const bool ovf = !(amax <= 65504.f);              // +-inf included (a NaN would already be a NaN in the reference)
                         if (ovf && p.overflow) *p.overflow = 1;
                         fence_proxy_async_smem();
                         __syncwarp();

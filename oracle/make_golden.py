@@ -17,6 +17,7 @@ regenerated from the seed on the GPU box, where /root/reference does not exist):
   memory           f32    encoder memory [N,L,E] (padded rows included, as the reference computes them)
   prefix / prefix_logits   a random forced token prefix [P,B] and its logits [B,L]
                    through the reference's own sub-modules (model_para.py:217-227)
+  last_logits64 / prefix_logits64   the same logits with the reference model run in float64 (noise floor of fp32)
 
     python oracle/make_golden.py            # writes tests/golden/*.npz
 """
@@ -35,7 +36,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from faceformer_b200 import synth  # noqa: E402
-from faceformer_b200.config import (MODE_PARALLEL, MODE_SEQ2SEQ, OURS, SEQ2SEQ, TINY, ModelConfig)  # noqa: E402
+from faceformer_b200.config import (MODE_PARALLEL, MODE_SEQ2SEQ, OURS, OURS_PERSPECTIVE, SEQ2SEQ, TINY, ModelConfig)  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -54,6 +55,18 @@ CASES = {
                                 inputs=("synth", 0, [10, 14]), prefix_P=6),
     "seq2seq_single64": dict(cfg=SEQ2SEQ, mode=MODE_SEQ2SEQ, n=1, weights=("synth", 1, "diverse"),
                              inputs=("synth", 1, [64]), prefix_P=20),
+    # BASELINE.json configs[3] geometry (ours-perspective.yml: num_lines 202, T 38); greedy only -- the reference has no beam search
+    "perspective_small": dict(cfg=OURS_PERSPECTIVE, mode=MODE_PARALLEL, n=3, weights=("synth", 2, "diverse"),
+                              inputs=("synth", 2, [12, 30, 21]), prefix_P=8),
+    # BASELINE.json configs[1] "<= 512 edges": a wireframe with more than 256 memory rows (274), num_lines overridden to 300
+    "ours_wide300": dict(cfg=OURS.replace(num_lines=300), mode=MODE_PARALLEL, n=1, weights=("synth", 5, "diverse"),
+                         inputs=("synth", 7, [270]), prefix_P=6),
+}
+
+# encoder-only fixture for BASELINE.json configs[4] (2048-edge wireframes): every 8th memory row of the reference's encoder output
+ENCODER_CASES = {
+    "encoder_2048": dict(cfg=OURS.replace(num_lines=2048), mode=MODE_PARALLEL, n=1, weights=("synth", 6, "diverse"),
+                         inputs=("synth", 8, [2048]), row_step=8),
 }
 
 
@@ -147,13 +160,43 @@ def make_case(name, spec):
     assert np.array_equal(last_logits.argmax(1), flat[:, steps]), "stop-rule reconstruction is inconsistent"
     prefix = random_prefix(cfg, mode, batch, spec["prefix_P"], seed=len(name))
     memory, prefix_logits = reference_logits(m, mode, batch, prefix)
+    # the same two evaluations with the reference model in float64: the distance between the reference's own fp32 result
+    # and the exact one is the noise floor any fp32 implementation is judged against (tests/util.py logits_close)
+    m64 = build_reference(cfg, mode, sd).double()
+    b64 = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in batch.items()}
+    _, last_logits64 = reference_logits(m64, mode, b64, np.ascontiguousarray(flat[:, :steps].T))
+    _, prefix_logits64 = reference_logits(m64, mode, b64, prefix)
     meta = dict(name=name, cfg=cfg.to_dict(), mode=mode, n=n, weights=list(spec["weights"]),
                 inputs=[x if not isinstance(x, np.ndarray) else x.tolist() for x in spec["inputs"]],
                 torch=torch.__version__, threads=torch.get_num_threads(), ref_seconds=round(dt, 3))
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), predict=predict,
                         steps=np.int64(steps), last_logits=last_logits, memory=memory.astype(np.float32),
-                        prefix=prefix, prefix_logits=prefix_logits)
+                        prefix=prefix, prefix_logits=prefix_logits, last_logits64=last_logits64, prefix_logits64=prefix_logits64)
     print(f"{name}: predict {predict.shape} steps {steps} distinct {len(np.unique(predict))} ref {dt:.2f}s", flush=True)
+
+
+def make_encoder_case(name, spec):
+    """memory = encoder(embeddings) through the reference's own sub-modules (model_para.py:191-210), rows subsampled."""
+    cfg, mode, n = spec["cfg"], spec["mode"], spec["n"]
+    sd = load_weights(spec["weights"], cfg, mode)
+    batch = load_inputs(spec["inputs"], cfg, mode, n)
+    m = build_reference(cfg, mode, sd)
+    torch.set_num_threads(os.cpu_count())
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    t0 = time.time()
+    with torch.no_grad():
+        input_mask = m.process_masks(tb["input_mask"])
+        val, pos, _ = m.get_embeddings(tb["input"], tb["label"])
+        source, pos = m.patch_source(val, pos)
+        memory = m.encoder(source, src_key_padding_mask=input_mask, pos=pos).transpose(0, 1).contiguous().numpy()
+    dt = time.time() - t0
+    rows = np.arange(0, memory.shape[1], spec["row_step"])
+    meta = dict(name=name, cfg=cfg.to_dict(), mode=mode, n=n, weights=list(spec["weights"]),
+                inputs=[x if not isinstance(x, np.ndarray) else x.tolist() for x in spec["inputs"]],
+                torch=torch.__version__, threads=torch.get_num_threads(), ref_seconds=round(dt, 3))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), rows=rows, memory_rows=memory[:, rows].astype(np.float32),
+                        steps=np.int64(0))
+    print(f"{name}: memory {memory.shape} -> {len(rows)} rows kept, ref {dt:.2f}s", flush=True)
 
 
 def main():
@@ -162,6 +205,10 @@ def main():
         if only and name not in only:
             continue
         make_case(name, spec)
+    for name, spec in ENCODER_CASES.items():
+        if only and name not in only:
+            continue
+        make_encoder_case(name, spec)
 
 
 if __name__ == "__main__":

@@ -45,7 +45,7 @@ def test_golden_full_decode(name, device_path):
     assert np.array_equal(pred, g["predict"]), f"{(pred != g['predict']).sum()} token mismatches"
     lg = e.get_last_logits()
     lg = lg.cpu().numpy() if device_path else lg
-    ok, d = logits_close(lg, g["last_logits"])
+    ok, d = logits_close(lg, g["last_logits"], b64=g.get("last_logits64"))
     assert ok, f"last-step logits differ by {d}"
     mem = e.get_memory()
     mem = mem.cpu().numpy() if device_path else mem
@@ -53,6 +53,19 @@ def test_golden_full_decode(name, device_path):
     assert np.max(np.abs(mem[vm] - g["memory"][vm])) <= LOGIT_TOL
     assert np.all(mem[~vm] == 0)
     assert e.kernel_launches() > 0
+    e.close()
+
+
+def test_golden_encoder_2048_edges():
+    """BASELINE.json configs[4] geometry: 2048-edge wireframe (L = 2052 memory rows, flash-style key streaming in the encoder
+    self-attention); encoder memory against the reference's (every 8th row kept in the fixture)."""
+    g = load_case("encoder_2048")
+    e = make_engine(g)
+    b = g["batch"]
+    e.encode(torch.from_numpy(b["input"]).cuda().flatten(2), torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda())
+    mem = e.get_memory().cpu().numpy()
+    assert mem.shape == (1, g["cfg"].mem_len, g["cfg"].num_model)
+    assert np.max(np.abs(mem[:, g["rows"]] - g["memory_rows"])) <= LOGIT_TOL
     e.close()
 
 
@@ -64,7 +77,7 @@ def test_golden_forced_prefix_logits(name):
     b = g["batch"]
     e.encode(b["input"].reshape(b["input"].shape[0], b["input"].shape[1], -1), b["input_mask"], b["num_input"])
     lg = e.forced_prefix_logits(g["prefix"])
-    ok, d = logits_close(lg, g["prefix_logits"])
+    ok, d = logits_close(lg, g["prefix_logits"], b64=g.get("prefix_logits64"))
     assert ok, f"forced-prefix logits differ by {d}"
     e.close()
 

@@ -86,7 +86,7 @@ def test_tc_accumulation_has_no_truncation_bias(eng, fmt):
     assert abs(rel.mean()) <= (5e-7 if fmt == 3 else 1e-6), rel.mean()
 
 
-@pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64"])
+@pytest.mark.parametrize("name", ["ours_parallel_small", "seq2seq_single64", "perspective_small", "ours_wide300"])
 @pytest.mark.parametrize("fmt", [2, 3])
 def test_golden_full_decode_forced_tensor_core(name, fmt):
     g = load_case(name)
@@ -99,7 +99,7 @@ def test_golden_full_decode_forced_tensor_core(name, fmt):
     pred, steps = e.forward_eval(coords, torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda())
     assert steps == g["steps"]
     assert np.array_equal(pred.cpu().numpy(), g["predict"])
-    ok, d = logits_close(e.get_last_logits().cpu().numpy(), g["last_logits"])
+    ok, d = logits_close(e.get_last_logits().cpu().numpy(), g["last_logits"], b64=g.get("last_logits64"))
     assert ok, f"last-step logits differ by {d}"
     assert e.kernel_launches() > 0 and e.fp16_fallbacks() == 0
     e.close()
@@ -117,7 +117,7 @@ def test_golden_forced_prefix_logits_forced_tensor_core(name, fmt):
     b = g["batch"]
     e.encode(b["input"].reshape(b["input"].shape[0], b["input"].shape[1], -1), b["input_mask"], b["num_input"])
     lg = e.forced_prefix_logits(g["prefix"])
-    ok, d = logits_close(lg, g["prefix_logits"])
+    ok, d = logits_close(lg, g["prefix_logits"], b64=g.get("prefix_logits64"))
     assert ok, f"forced-prefix logits differ by {d}"
     e.close()
 

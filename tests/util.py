@@ -41,12 +41,17 @@ def valid_rows_mask(batch, cfg):
     return np.concatenate([np.ones((m.shape[0], cfg.num_token), bool), m], axis=1)
 
 
-def logits_close(a, b, tol=LOGIT_TOL):
-    """Masked entries must be exactly finfo.min on both sides; the rest within tol.
+def logits_close(a, b, tol=LOGIT_TOL, b64=None):
+    """Masked entries must be exactly finfo.min on both sides; the rest within tol of the reference's fp32 logits `b`.
 
     tol is ABSOLUTE (1e-4) while max|logit| <= 32.  The trained fixture produces logits up to ~210,
     where one fp32 ulp is already 1.5e-5 and the reference's own fp32-vs-fp64 noise exceeds 1e-4,
-    so beyond 32 the budget grows proportionally: tol * max|logit| / 32 (3.1e-6 relative)."""
+    so beyond 32 the budget grows proportionally: tol * max|logit| / 32 (3.1e-6 relative).
+
+    Noise-floor clause (b64 = the reference evaluated in float64, stored in the fixture): two correct fp32 evaluations of
+    the same function can be farther apart than 1e-4 when the reference's own fp32 result is ~1e-4 from the exact one
+    (measured 0.8e-4 on the ours.yml-size fixtures, profiles/logit_noise.py).  Such a comparison passes if our logits are no
+    farther from the float64 evaluation than NOISE_FACTOR x the reference's own fp32 logits are."""
     a, b = np.asarray(a), np.asarray(b)
     fmin = np.finfo(np.float32).min
     ma, mb = a == fmin, b == fmin
@@ -56,8 +61,19 @@ def logits_close(a, b, tol=LOGIT_TOL):
         return True, 0.0
     d = float(np.max(np.abs(a[~ma] - b[~mb])))
     scale = max(1.0, float(np.max(np.abs(b[~mb]))) / LOGIT_SCALE)
-    return d <= tol * scale, d
+    if d <= tol * scale:
+        return True, d
+    if b64 is not None:
+        t = np.asarray(b64, np.float64)[~mb]
+        n32 = float(np.max(np.abs(b[~mb].astype(np.float64) - t)))
+        d64 = float(np.max(np.abs(a[~ma].astype(np.float64) - t)))
+        return d64 <= NOISE_FACTOR * n32, d
+    return False, d
 
+
+NOISE_FACTOR = 3.0        # measured: 0.7x - 2.3x over all fixtures and pipelines
 
 CASES_ALL = ["tiny_parallel_trained", "tiny_parallel_trained_b", "tiny_parallel_ragged", "tiny_seq2seq",
-             "ours_parallel_small", "seq2seq_single64"]
+             "ours_parallel_small", "seq2seq_single64",
+             "perspective_small",     # BASELINE.json configs[3] geometry (ours-perspective.yml), greedy
+             "ours_wide300"]          # configs[1] "<= 512 edges": 274 memory rows (> 256: mma.sync cross-attention)
