@@ -13,6 +13,7 @@
 #include "../../include/ffb200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "attn_mma.cuh"
 #include "attn_f16.cuh"
 #include "attn_h.cuh"
@@ -24,6 +25,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace ffb;
@@ -94,7 +96,9 @@ struct ffb_handle {
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
     int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
     int opt_tma_out = 1;                          // fp16x2 GEMM: asynchronous TMA store / reduce-add epilogue
-    int opt_gemm_variant = 2;                     // fp16x2 GEMM pipeline variant (gemm_tc.cuh Cfg<NS, V>): 0, 1, or 2 = per launch
+    int opt_gemm_variant = 2;                     // fp16x2 GEMM: 0 / 1 = single-CTA pipeline variant (gemm_tc.cuh Cfg<NS, V>), 2 = variant per launch,
+                                                  // 3 = CTA-pair kernel (gemm_tc2.cuh, cta_group::2) wherever the TMA epilogue applies
+    std::unordered_map<const CUtensorMap*, CUtensorMap> w_half_maps;   // W map (256-row boxes) -> its twin with 128-row boxes (CTA-pair kernel)
     CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
     CUtensorMap ms_h;                             // fp16x2 split STORE map of a_h (FFN hidden)
     // "half pipeline" (fp16x2 GEMM + fp16x2 attention): q,k,v and the cross-attention query never exist in fp32
@@ -393,6 +397,17 @@ int encode_rows_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint
     return FFB_OK;
 }
 
+// weight operand [fmt][rows][K]: the 256-row-box map of the single-CTA kernel plus (fp16x2) its 128-row-box twin for the CTA-pair kernel
+int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, uint32_t box_rows, int fmt);
+int encode_weight_maps(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, int fmt) {
+    int rc = encode_operand_map(h, m, base, K, rows, tc::BN, fmt);
+    if (rc != FFB_OK || fmt != 2) return rc;
+    CUtensorMap half;
+    rc = encode_operand_map(h, &half, base, K, rows, tc2::BN / 2, fmt);
+    if (rc == FFB_OK) h->w_half_maps[m] = half;
+    return rc;
+}
+
 // fp32 [rows, ld] output buffer -> 2-D map, box 32 x 32 floats (128-byte rows), SWIZZLE_128B (the staging layout of the epilogue)
 int encode_output_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint64_t rows) {
     if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
@@ -425,7 +440,7 @@ struct TcLin {
     float* C = nullptr; int ldc = 0; const float* R = nullptr; int ldr = 0;
     const CUtensorMap* Cmap = nullptr;          // fp32 [rows, ldc] map of C (box 32x32, SWIZZLE_128B): enables the TMA epilogue (fp16x2)
     uint16_t* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
-    int M = 0, N = 0, K = 0, relu = 0;
+    int M = 0, N = 0, K = 0, relu = 0, dry_store = 0;
 };
 
 int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
@@ -443,8 +458,21 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     if (h->opt_stagger && tiles >= 4 * grid) p.stagger_ns = (unsigned)((l.K / tc::BK) * 130 * (h->tc_fmt == 2 ? 3 : 6) / 4);
     prof_begin(h, PC_LINEAR_TC, 2.0 * l.M * (double)l.N * l.K, s);
     // TMA epilogue: only when the residual (if any) is the in-place form C += ..., which a reduce-add expresses exactly
+    p.dry_store = l.dry_store;
     p.tma_out = (h->opt_tma_out && h->tc_fmt == 2 && l.Cmap && ((l.C && (!l.R || (l.R == l.C && l.ldr == l.ldc))) || (!l.C && l.Cs))) ? 1 : 0;
     const CUtensorMap& mc = l.Cmap ? *l.Cmap : *l.W;
+    if (h->tc_fmt == 2 && h->opt_gemm_variant == 3 && p.tma_out) {
+        auto it = h->w_half_maps.find(l.W);
+        if (it != h->w_half_maps.end()) {
+            const int tiles2 = ((l.M + 2 * tc2::BM - 1) / (2 * tc2::BM)) * (l.N / tc2::BN);
+            const int pairs = std::max(1, std::min(tiles2, h->num_sms / 2));
+            tc2::gemm2_kernel<<<2 * pairs, tc2::NUM_THREADS, tc2::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, it->second, mc, p);
+            prof_end(h, s);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            return FFB_OK;
+        }
+    }
     // variant 1 (two staging buffers, 3 operand stages) is faster for plain / split stores, variant 0 for the in-place residual (measured,
     // profiles/tune_gemm.py --random); 2 = choose per launch
     if (h->tc_fmt == 2 && (h->opt_gemm_variant == 1 || (h->opt_gemm_variant == 2 && !l.R)))
@@ -498,7 +526,7 @@ int split_weight(ffb_handle* h, const float* src, uint16_t* dst, size_t rows, si
     split_array_kernel<<<grid1d(n4), 256, 0, s>>>(src, dst, n4, scale, fmt);
     h->launches++;
     CU(h, cudaGetLastError());
-    return encode_operand_map(h, map, dst, K, rows, tc::BN, fmt);
+    return encode_weight_maps(h, map, dst, K, rows, fmt);
 }
 
 // Build (once per format) the split weights and (per batch) the activation-operand maps of format `fmt`.
@@ -958,6 +986,7 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2, 1>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc2::gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(ax::attn_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ax::SMEM_BYTES);
@@ -1017,7 +1046,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
             h->opt_attn_mma = value; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
-        case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1 or 2 (auto)"); h->opt_gemm_variant = value; return FFB_OK;
+        case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1, 2 (auto) or 3 (CTA pairs)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
             if (value && !h->tc_ok) return fail(h, FFB_ERR_UNSUPPORTED, "tensor-core path needs num_model and num_feedforward multiples of 256");
@@ -1349,10 +1378,11 @@ int ffb_bench_linear_tc(ffb_handle* h, int32_t M, int32_t N, int32_t K, int32_t 
         cudaMemsetAsync(cf.p, 0, Mp * (size_t)N * 4, s); cudaMemsetAsync(bias.p, 0, (size_t)N * 4, s);
         CUtensorMap mA, mW;
         if ((rc = encode_operand_map(h, &mA, as.p, K, Mp, tc::BM, h->tc_fmt)) != FFB_OK) break;
-        if ((rc = encode_operand_map(h, &mW, ws.p, K, N, tc::BN, h->tc_fmt)) != FFB_OK) break;
+        if ((rc = encode_weight_maps(h, &mW, ws.p, K, N, h->tc_fmt)) != FFB_OK) break;
         TcLin l; l.A0 = &mA; l.W = &mW; l.M = M; l.N = N; l.K = K;
         if (flags & 1) l.bias = bias.as<float>();
         if (flags & 4) l.relu = 1;
+        if (flags & 64) l.dry_store = 1;
         if (flags & 8) { l.Cs = cs.as<uint16_t>(); l.cs_stride = (long long)Mp * N; l.ldcs = N; }
         else if (!(flags & 16)) { l.C = cf.as<float>(); l.ldc = N; if (flags & 2) { l.R = cf.as<float>(); l.ldr = N; } }
         CUtensorMap mC;

@@ -80,6 +80,7 @@ struct Params {
     int* overflow;               // set to 1 if a split output exceeds the fp16 range (NS = 2)
     unsigned stagger_ns;         // start delay per phase group (blockIdx & 3), 0 = none
     int tma_out;                 // NS = 2: write C through mapC with TMA bulk stores (reduce-add when R aliases C)
+    int dry_store;               // benchmark only: format and stage the output but do not issue the TMA stores
     const int* stop;
 };
 
@@ -355,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         if (ovf && p.overflow) *p.overflow = 1;
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !p.dry_store) {
                             tma_store_3d(&mapC, stg_s, col0 + j * 32, row0, 0);
                             tma_store_3d(&mapC, stg_s + 2048u, col0 + j * 32, row0, 1);
                             tma_store_commit();
@@ -382,7 +383,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         }
                         fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the async proxy
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !p.dry_store) {
                             if (p.R) tma_reduce_add_2d(&mapC, stg_s, col0 + j * 32, row0);
                             else tma_store_2d(&mapC, stg_s, col0 + j * 32, row0);
                             tma_store_commit();

@@ -182,7 +182,8 @@ enum { FFB_OPT_TMA_EPILOGUE = 9 };
  * self-attention (prefix <= 128).  Default 3; 0 = always the mma.sync kernel. */
 enum { FFB_OPT_ATTN_X = 10 };
 /* fp16x2 GEMM pipeline variant: 0 = 4 operand stages + 1 epilogue staging buffer per warp, 1 = 3 stages + 2 staging buffers,
- * 2 (default) = variant 1 for plain / split stores and variant 0 for the in-place residual. */
+ * 2 (default) = variant 1 for plain / split stores and variant 0 for the in-place residual,
+ * 3 = experimental CTA-pair kernel (tcgen05 cta_group::2, gemm_tc2.cuh; correct but slower in round 1). */
 enum { FFB_OPT_GEMM_VARIANT = 11 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----

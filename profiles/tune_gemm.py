@@ -15,8 +15,9 @@ from faceformer_b200.lib import FFB_OPT_GEMM_VARIANT, FFB_OPT_TMA_EPILOGUE, FFB_
 
 e = Engine(OURS, MODE_PARALLEL, 0)
 RND = 32 if "--random" in sys.argv else 0        # pseudo-random operand bits instead of zeros (realistic power draw)
-FLAGS = {"nostore": 16 | RND, "plain": 0 | RND, "bias": 1 | RND, "bias+res": 3 | RND, "bias+relu+split": 13 | RND}
-for fmt, stag, var in ((2, 1, 0), (2, 1, 1), (2, 0, 0), (3, 0, 0)):
+FLAGS = {"nostore": 16 | RND, "plain": 0 | RND, "bias": 1 | RND, "bias+res": 3 | RND, "bias+relu+split": 13 | RND,
+         "dry bias+res": 67 | RND, "dry split": 77 | RND}     # dry = output formatted and staged, TMA stores not issued
+for fmt, stag, var in ((2, 1, 0), (2, 1, 1), (2, 1, 3), (2, 0, 0), (3, 0, 0)):
   e.set_option(FFB_OPT_TC_FORMAT, fmt)
   e.set_option(FFB_OPT_TMA_EPILOGUE, stag)
   e.set_option(FFB_OPT_GEMM_VARIANT, var)

@@ -27,11 +27,12 @@ def _t(a):
 @pytest.mark.parametrize("M,N,K", [(1, 256, 32), (128, 256, 512), (100, 512, 512), (129, 1536, 512), (1000, 512, 1024),
                                    (4097, 1024, 512), (20000, 512, 512)])
 @pytest.mark.parametrize("variant", ["plain", "bias_relu", "bias_res", "via_split"])
-@pytest.mark.parametrize("fmt", [2, 3, 21])
+@pytest.mark.parametrize("fmt", [2, 3, 21, 23])
 def test_tc_linear_is_fp32_class(eng, M, N, K, variant, fmt):
     from faceformer_b200.lib import FFB_OPT_GEMM_VARIANT
-    eng.set_option(FFB_OPT_GEMM_VARIANT, 1 if fmt == 21 else 0)     # 21 = fp16x2, pipeline variant 1 (3 stages, 2 staging buffers)
-    fmt = 2 if fmt == 21 else fmt
+    # 21 = fp16x2, pipeline variant 1 (3 stages, 2 staging buffers); 23 = fp16x2 on CTA pairs (gemm_tc2.cuh, cta_group::2)
+    eng.set_option(FFB_OPT_GEMM_VARIANT, {21: 1, 23: 3}.get(fmt, 0))
+    fmt = 2 if fmt in (21, 23) else fmt
     eng.set_option(FFB_OPT_TC_FORMAT, fmt)
     rng = np.random.default_rng(M + N + K)
     A = (rng.normal(size=(M, K)) * rng.choice([0.01, 1.0, 30.0], size=(M, 1))).astype(np.float32)
