@@ -343,17 +343,36 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             // ---- pass 2: probabilities per 32-key chunk -> fp16x2 -> shared memory (A operand of O += P V) ----
             for (int b = 0; b < nb; ++b, ++n_pc) {
                 const uint32_t buf = n_pc & 1u;
-                uint32_t hw[16], lw[16];
-                if (b * KC >= whi || b * KC + KC <= wlo) {
+                uint8_t* ph = pw + (buf * 2 + 0) * P_TILE + row * 64;
+                uint8_t* pl = pw + (buf * 2 + 1) * P_TILE + row * 64;
+                const int rsw = (row >> 1) & 3;                           // 16-byte chunk cc lives at cc ^ ((row >> 1) & 3) (SWIZZLE_64B)
+                // each case waits for the buffer (the MMAs that read it two chunks ago have retired) and stores its own words, so the
+                // all-zero cases do not drag 32 register moves through the hot path
+                auto publish = [&](const uint32_t (&hw)[16], const uint32_t (&lw)[16]) {
+                    mbar_wait(p_empty(w, buf), ((n_pc >> 1) & 1u) ^ 1u);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { hw[i] = 0u; lw[i] = 0u; }
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int sw = (cc ^ rsw) << 4;
+                        *reinterpret_cast<uint4*>(ph + sw) = make_uint4(hw[4 * cc], hw[4 * cc + 1], hw[4 * cc + 2], hw[4 * cc + 3]);
+                        *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lw[4 * cc], lw[4 * cc + 1], lw[4 * cc + 2], lw[4 * cc + 3]);
+                    }
+                };
+                auto publish_zero = [&]() {
+                    mbar_wait(p_empty(w, buf), ((n_pc >> 1) & 1u) ^ 1u);
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) { *reinterpret_cast<uint4*>(ph + (cc << 4)) = z; *reinterpret_cast<uint4*>(pl + (cc << 4)) = z; }
+                };
+                if (b * KC >= whi || b * KC + KC <= wlo) {
+                    publish_zero();
                 } else {
                     uint32_t v[32];
                     tmem_ld32(t_s + b * KC, v);
                     tmem_ld_wait();
                     const uint32_t M = chunk_mask(b);
-                    float ls0 = 0.f, ls1 = 0.f;
                     if (M == 0xffffffffu) {                                 // whole chunk valid: no selects
+                        uint32_t hw[16], lw[16];
+                        float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
@@ -361,7 +380,11 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             ls0 += p0; ls1 += p1;
                             split_pair(p0, p1, hw[i], lw[i]);
                         }
+                        lsum += ls0 + ls1;
+                        publish(hw, lw);
                     } else if (M != 0u) {
+                        uint32_t hw[16], lw[16];
+                        float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), kScale, bias));
@@ -371,20 +394,11 @@ attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
                             ls0 += p0; ls1 += p1;
                             split_pair(p0, p1, hw[i], lw[i]);
                         }
+                        lsum += ls0 + ls1;
+                        publish(hw, lw);
                     } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { hw[i] = 0u; lw[i] = 0u; }
+                        publish_zero();
                     }
-                    lsum += ls0 + ls1;
-                }
-                mbar_wait(p_empty(w, buf), ((n_pc >> 1) & 1u) ^ 1u);      // the MMAs that read this buffer two chunks ago have retired
-                uint8_t* ph = pw + (buf * 2 + 0) * P_TILE + row * 64;
-                uint8_t* pl = pw + (buf * 2 + 1) * P_TILE + row * 64;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {                          // 16-byte chunk cc lives at cc ^ ((row >> 1) & 3) (SWIZZLE_64B)
-                    const int sw = (cc ^ ((row >> 1) & 3)) << 4;
-                    *reinterpret_cast<uint4*>(ph + sw) = make_uint4(hw[4 * cc], hw[4 * cc + 1], hw[4 * cc + 2], hw[4 * cc + 3]);
-                    *reinterpret_cast<uint4*>(pl + sw) = make_uint4(lw[4 * cc], lw[4 * cc + 1], lw[4 * cc + 2], lw[4 * cc + 3]);
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();                                        // this thread's S reads precede the O writes the arrive unlocks

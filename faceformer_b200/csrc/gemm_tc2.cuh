@@ -56,6 +56,12 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Relaxed remote arrive: no cluster-scope release fence (which would wait for the thread's outstanding bulk stores).  Enough for
+// handing a drained TMEM accumulator back: the tcgen05.ld results are ordered by tcgen05.fence::before_thread_sync on this side
+// and tcgen05.fence::after_thread_sync on the MMA side.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -207,7 +213,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(buf), 0));      // the leader's MMA thread owns the accumulators
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar(buf), 0));      // the leader's MMA thread owns the accumulators
             }
             const int col0 = nt * BN + hcol * 128;
             const int row0 = mt * 2 * BM + (int)rank * BM + q * 32;
