@@ -1183,6 +1183,67 @@ int ffb_forward_eval(ffb_handle* h, const float* coords, const uint8_t* pad_mask
     return ffb_decode_greedy(h, predict, loc, steps_run, stream);
 }
 
+int ffb_featurize(ffb_handle* h, const double* points, const int64_t* edge_off, const int64_t* wf_edge_off, int32_t N,
+                  float* coords, uint8_t* pad_mask, int64_t* num_input, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!points || !edge_off || !wf_edge_off || !coords || !pad_mask || !num_input) return fail(h, FFB_ERR_ARG, "ffb_featurize: NULL argument");
+    if (N < 1) return fail(h, FFB_ERR_ARG, "n_wireframes must be >= 1");
+    if (h->cfg.in_dim % 2 != 0) return fail(h, FFB_ERR_UNSUPPORTED, "ffb_featurize needs point_dim 2");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nl = h->cfg.num_lines, P = h->cfg.in_dim / 2;
+    if (P < 2) return fail(h, FFB_ERR_UNSUPPORTED, "ffb_featurize needs >= 2 points per line");
+    // the offsets are planned on the host (they are tiny); validate like the reference would fail (IndexError / empty edge)
+    std::vector<int64_t> wf(N + 1);
+    CU(h, cudaMemcpyAsync(wf.data(), wf_edge_off, (N + 1) * sizeof(int64_t), loc == FFB_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (wf[0] != 0) return fail(h, FFB_ERR_ARG, "wf_edge_off[0] must be 0");
+    for (int i = 0; i < N; ++i) {
+        if (wf[i + 1] < wf[i]) return fail(h, FFB_ERR_ARG, "wf_edge_off must be non-decreasing");
+        if (wf[i + 1] - wf[i] > nl) return fail(h, FFB_ERR_ARG, "wireframe %d has %lld edges, num_lines is %d (the reference raises IndexError)", i, (long long)(wf[i + 1] - wf[i]), nl);
+    }
+    const int64_t ne = wf[N];
+    std::vector<int64_t> eo(ne + 1);
+    CU(h, cudaMemcpyAsync(eo.data(), edge_off, (ne + 1) * sizeof(int64_t), loc == FFB_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (eo[0] != 0) return fail(h, FFB_ERR_ARG, "edge_off[0] must be 0");
+    for (int64_t e = 0; e < ne; ++e)
+        if (eo[e + 1] - eo[e] < 1) return fail(h, FFB_ERR_ARG, "edge %lld has no points", (long long)e);
+    const int64_t npts = eo[ne];
+    const size_t out_bytes = (size_t)N * nl * P * 2 * sizeof(float);
+    const double* d_pts = points; const int64_t* d_eo = edge_off; const int64_t* d_wf = wf_edge_off;
+    float* d_out = coords; uint8_t* d_mask = pad_mask; int64_t* d_ni = num_input;
+    DevBuf in_stage, out_stage;
+    if (loc == FFB_HOST) {
+        const size_t pb = (size_t)std::max<int64_t>(npts, 1) * 2 * sizeof(double), eb = (size_t)(ne + 1) * sizeof(int64_t), wb = (size_t)(N + 1) * sizeof(int64_t);
+        const size_t a8 = (pb + 7) / 8 * 8;
+        if (in_stage.ensure(a8 + eb + wb) != cudaSuccess || out_stage.ensure(out_bytes + (size_t)N * sizeof(int64_t) + (size_t)N * nl) != cudaSuccess) {
+            in_stage.release(); out_stage.release();
+            return fail(h, FFB_ERR_CUDA, "ffb_featurize: out of device memory");
+        }
+        uint8_t* ib = in_stage.as<uint8_t>();
+        cudaMemcpyAsync(ib, points, (size_t)npts * 2 * sizeof(double), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ib + a8, eo.data(), eb, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ib + a8 + eb, wf.data(), wb, cudaMemcpyHostToDevice, s);
+        d_pts = reinterpret_cast<const double*>(ib); d_eo = reinterpret_cast<const int64_t*>(ib + a8); d_wf = reinterpret_cast<const int64_t*>(ib + a8 + eb);
+        uint8_t* ob = out_stage.as<uint8_t>();
+        d_out = reinterpret_cast<float*>(ob); d_ni = reinterpret_cast<int64_t*>(ob + out_bytes); d_mask = ob + out_bytes + (size_t)N * sizeof(int64_t);
+    }
+    featurize_kernel<<<grid1d((long long)N * nl * P), 256, 0, s>>>(d_pts, reinterpret_cast<const long long*>(d_eo), reinterpret_cast<const long long*>(d_wf),
+                                                                d_out, d_mask, reinterpret_cast<long long*>(d_ni), N, nl, P);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && loc == FFB_HOST) {
+        cudaMemcpyAsync(coords, d_out, out_bytes, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(num_input, d_ni, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(pad_mask, d_mask, (size_t)N * nl, cudaMemcpyDeviceToHost, s);
+        e = cudaStreamSynchronize(s);
+    }
+    if (loc == FFB_HOST) { if (e == cudaSuccess) e = cudaStreamSynchronize(s); in_stage.release(); out_stage.release(); }
+    if (e != cudaSuccess) return fail(h, FFB_ERR_CUDA, "ffb_featurize: %s", cudaGetErrorString(e));
+    return FFB_OK;
+}
+
 int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream) {
     if (!h) return FFB_ERR_ARG;
     if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_get_memory before ffb_encode");

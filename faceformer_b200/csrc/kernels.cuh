@@ -370,6 +370,45 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// featurize: edge polylines -> [N, num_lines, P, 2] float32 + padding mask (datasets/data_para.py:8-25,59-68).
+//   2-point edge: P points on the segment, x = x1 + (x2 - x1) * t with t = linspace(0, 1, P), evaluated in float64 exactly as
+//   numpy does (multiply, then add: no FMA; t_i = i * (1 / (P - 1)), last = 1) and rounded to float32 on assignment;
+//   longer polyline: points at indices linspace(0, n - 1, P).round(0) (round-half-even), cast to float32.
+// One thread per (edge slot, sample); padded slots are zero-filled, mask = 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void featurize_kernel(const double* __restrict__ pts, const long long* __restrict__ edge_off,
+                                 const long long* __restrict__ wf_off, float* __restrict__ out, uint8_t* __restrict__ mask,
+                                 long long* __restrict__ num_input, int N, int num_lines, int P) {
+    const long long total = (long long)N * num_lines * P;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % P);
+        const long long slot = idx / P;
+        const int e = (int)(slot % num_lines), w = (int)(slot / num_lines);
+        const long long e0 = wf_off[w], ne = wf_off[w + 1] - e0;
+        float2 o = make_float2(0.f, 0.f);
+        if (e < ne) {
+            const long long p0 = edge_off[e0 + e], n = edge_off[e0 + e + 1] - p0;
+            if (n == 2) {
+                const double t = (i == P - 1) ? 1.0 : __dmul_rn((double)i, 1.0 / (double)(P - 1));
+                const double x1 = pts[2 * p0], y1 = pts[2 * p0 + 1], x2 = pts[2 * p0 + 2], y2 = pts[2 * p0 + 3];
+                o.x = (float)__dadd_rn(x1, __dmul_rn(__dsub_rn(x2, x1), t));
+                o.y = (float)__dadd_rn(y1, __dmul_rn(__dsub_rn(y2, y1), t));
+            } else {
+                const double step = (double)(n - 1) / (double)(P - 1);
+                const double y = (i == P - 1) ? (double)(n - 1) : __dmul_rn((double)i, step);
+                const long long j = (long long)rint(y);
+                o.x = (float)pts[2 * (p0 + j)]; o.y = (float)pts[2 * (p0 + j) + 1];
+            }
+        }
+        reinterpret_cast<float2*>(out)[idx] = o;
+        if (i == 0) {
+            mask[slot] = (e < ne) ? 0 : 1;
+            if (e == 0) num_input[w] = ne;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention group geometry
 // ------------------------------------------------------------------------------------------------
 struct AttnGroups {

@@ -186,6 +186,38 @@ class Engine:
         self.encode(coords, pad_mask, num_input)
         return self.decode_greedy(want_steps, out)
 
+    # -- the step before the path ------------------------------------------------
+    def featurize(self, wireframes, device: bool = True):
+        """wireframes: list (one per wireframe) of lists of edges, an edge = sequence of (x, y) points -- the `edges` entry of the
+        dataset JSON (datasets/data_para.py:59-68).  Returns (input [N, num_lines, P, 2] f32, input_mask [N, num_lines] bool,
+        num_input [N] i64) as torch tensors on the engine's GPU (device=True) or numpy arrays computed through host buffers."""
+        import torch
+        pts, eoff, woff = [], [0], [0]
+        for edges in wireframes:
+            for e in edges:
+                a = np.asarray(e, dtype=np.float64).reshape(-1, 2)
+                pts.append(a)
+                eoff.append(eoff[-1] + a.shape[0])
+            woff.append(woff[-1] + len(edges))
+        pts = np.ascontiguousarray(np.concatenate(pts, 0) if pts else np.zeros((0, 2), np.float64))
+        eoff, woff = np.asarray(eoff, np.int64), np.asarray(woff, np.int64)
+        n, nl, P = len(wireframes), self.cfg.num_lines, self.cfg.num_points_per_line
+        if device:
+            dev = torch.device("cuda", self.device)
+            t_pts, t_e, t_w = (torch.from_numpy(x).to(dev) for x in (pts, eoff, woff))
+            out = torch.empty((n, nl, P, 2), dtype=torch.float32, device=dev)
+            mask = torch.empty((n, nl), dtype=torch.uint8, device=dev)
+            ni = torch.empty((n,), dtype=torch.int64, device=dev)
+            self._check(self._lib.ffb_featurize(self._h, _ptr(t_pts), _ptr(t_e), _ptr(t_w), n, _ptr(out), _ptr(mask), _ptr(ni),
+                                                FFB_DEVICE, self._stream()))
+            return out, mask.bool(), ni
+        out = np.empty((n, nl, P, 2), np.float32)
+        mask = np.empty((n, nl), np.uint8)
+        ni = np.empty((n,), np.int64)
+        self._check(self._lib.ffb_featurize(self._h, _ptr(pts), _ptr(eoff), _ptr(woff), n, _ptr(out), _ptr(mask), _ptr(ni),
+                                            FFB_HOST, self._stream()))
+        return out, mask.astype(bool), ni
+
     # -- parity hooks ---------------------------------------------------------------------------
     def get_memory(self):
         import torch

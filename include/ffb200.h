@@ -121,6 +121,20 @@ int ffb_forward_eval(ffb_handle* h, const float* coords, const uint8_t* pad_mask
                      const int64_t* num_input, int32_t n_wireframes, int64_t* predict,
                      int loc, int32_t* steps_run, void* stream);
 
+/* Input featurisation, the step right before the path: what ABCDataset_Parallel.__getitem__ does per wireframe
+ * with sample_points (faceformer/datasets/data_para.py:8-25,59-68), for a whole batch on the device.
+ *   points       double [n_points_total, 2]   all edge polylines of the batch, concatenated (JSON coordinates are doubles)
+ *   edge_off     int64  [n_edges_total + 1]   prefix offsets of the edges into `points` (an edge needs >= 1 point)
+ *   wf_edge_off  int64  [N + 1]               prefix offsets of the wireframes into the edges (<= num_lines edges each)
+ * outputs (same location as the inputs):
+ *   coords       float  [N, num_lines, in_dim] 2-point edges resampled on the segment (float64 arithmetic like numpy, rounded to
+ *                                              float32), longer polylines index-resampled; padded slots zero     inputs['input']
+ *   pad_mask     uint8  [N, num_lines]         1 = padding                                                       inputs['input_mask']
+ *   num_input    int64  [N]                                                                                      inputs['num_input']
+ * Requires point_dim 2 (in_dim = 2 * num_points_per_line).  Results are bit-identical to the reference's. */
+int ffb_featurize(ffb_handle* h, const double* points, const int64_t* edge_off, const int64_t* wf_edge_off, int32_t n_wireframes,
+                  float* coords, uint8_t* pad_mask, int64_t* num_input, int loc, void* stream);
+
 /* Parity hooks (used by tests; they do not change decode results). */
 
 /* Encoder memory, float [N, L, E] (= inputs['embedding'] of model.py:216); rows of padded
