@@ -1244,6 +1244,63 @@ int ffb_featurize(ffb_handle* h, const double* points, const int64_t* edge_off, 
     return FFB_OK;
 }
 
+int ffb_parse_faces(ffb_handle* h, const int64_t* predict, int32_t N, int32_t F, const double* points, const int64_t* edge_off,
+                    const int64_t* wf_edge_off, double tol, int32_t check_enclosed, uint8_t* valid, int32_t* face_type, int32_t* n_loops,
+                    int32_t* loop_len, int32_t* indices, int32_t* n_indices, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!predict || !points || !edge_off || !wf_edge_off || !valid || !face_type || !n_loops || !loop_len || !indices || !n_indices)
+        return fail(h, FFB_ERR_ARG, "ffb_parse_faces: NULL argument");
+    if (N < 1 || F < 1) return fail(h, FFB_ERR_ARG, "ffb_parse_faces: n_wireframes and F must be >= 1");
+    const int T = h->T;
+    if (T > PF_MAX_T) return fail(h, FFB_ERR_UNSUPPORTED, "ffb_parse_faces: seq_len %d > %d", T, PF_MAX_T);
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t S = (size_t)N * F;
+    const long long* d_pred = reinterpret_cast<const long long*>(predict);
+    const double* d_pts = points; const int64_t* d_eo = edge_off; const int64_t* d_wf = wf_edge_off;
+    uint8_t* d_valid = valid; int* d_ft = face_type; int* d_nl = n_loops; int* d_ll = loop_len; int* d_idx = indices; int* d_ni = n_indices;
+    DevBuf in_stage, out_stage;
+    size_t o_ft = 0, o_nl = 0, o_ni = 0, o_ll = 0, o_idx = 0, o_valid = 0;
+    if (loc == FFB_HOST) {
+        std::vector<int64_t> wf(wf_edge_off, wf_edge_off + N + 1);
+        const int64_t ne = wf[N];
+        const int64_t npts = edge_off[ne];
+        const size_t pb = (size_t)std::max<int64_t>(npts, 1) * 2 * sizeof(double), eb = (size_t)(ne + 1) * 8, wb = (size_t)(N + 1) * 8, prb = S * T * 8;
+        o_ft = 0; o_nl = o_ft + S * 4; o_ni = o_nl + S * 4; o_ll = o_ni + S * 4; o_idx = o_ll + S * T * 4; o_valid = o_idx + S * T * 4;
+        if (in_stage.ensure(pb + eb + wb + prb) != cudaSuccess || out_stage.ensure(o_valid + S) != cudaSuccess) {
+            in_stage.release(); out_stage.release();
+            return fail(h, FFB_ERR_CUDA, "ffb_parse_faces: out of device memory");
+        }
+        uint8_t* ib = in_stage.as<uint8_t>();
+        cudaMemcpyAsync(ib, points, (size_t)npts * 16, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ib + pb, edge_off, eb, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ib + pb + eb, wf_edge_off, wb, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ib + pb + eb + wb, predict, prb, cudaMemcpyHostToDevice, s);
+        d_pts = reinterpret_cast<const double*>(ib); d_eo = reinterpret_cast<const int64_t*>(ib + pb); d_wf = reinterpret_cast<const int64_t*>(ib + pb + eb);
+        d_pred = reinterpret_cast<const long long*>(ib + pb + eb + wb);
+        uint8_t* ob = out_stage.as<uint8_t>();
+        d_ft = reinterpret_cast<int*>(ob + o_ft); d_nl = reinterpret_cast<int*>(ob + o_nl); d_ni = reinterpret_cast<int*>(ob + o_ni);
+        d_ll = reinterpret_cast<int*>(ob + o_ll); d_idx = reinterpret_cast<int*>(ob + o_idx); d_valid = ob + o_valid;
+    }
+    parse_faces_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d_pred, N, F, T, d_pts, reinterpret_cast<const long long*>(d_eo),
+                                                                  reinterpret_cast<const long long*>(d_wf), tol, check_enclosed, h->cfg.num_token, 1,
+                                                                  d_valid, d_ft, d_nl, d_ll, d_idx, d_ni);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (loc == FFB_HOST) {
+        if (e == cudaSuccess) {
+            cudaMemcpyAsync(face_type, d_ft, S * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(n_loops, d_nl, S * 4, cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(n_indices, d_ni, S * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(loop_len, d_ll, S * T * 4, cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(indices, d_idx, S * T * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(valid, d_valid, S, cudaMemcpyDeviceToHost, s);
+        }
+        const cudaError_t e2 = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = e2;
+        in_stage.release(); out_stage.release();
+    }
+    if (e != cudaSuccess) return fail(h, FFB_ERR_CUDA, "ffb_parse_faces: %s", cudaGetErrorString(e));
+    return FFB_OK;
+}
+
 int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream) {
     if (!h) return FFB_ERR_ARG;
     if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_get_memory before ffb_encode");

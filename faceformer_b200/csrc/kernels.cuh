@@ -409,6 +409,86 @@ __global__ void featurize_kernel(const double* __restrict__ pts, const long long
 }
 
 // ------------------------------------------------------------------------------------------------
+// parse_faces: predicted co-edge sequences -> canonical face loops, the step right after the path.
+// One thread per predicted sequence (wireframe w, slot f):
+//   1. Trainer.parse_parallel_faces, predict half (trainer.py:196-206): cut after the first token in [face_type_offset, token.len)
+//      (the whole row if there is none), face type = that token - face_type_offset, subtract token.len, keep 0 <= v < num_edges;
+//      an empty result is no face.
+//   2. is_face_enclosed (dataset/tests/check_faces_enclosed.py:11-46): walk the edges; every edge must start where the previous one
+//      ended (|dx| < tol and |dy| < tol on the polylines' first / last points, doubles), an edge that ends where the current loop
+//      started closes the loop; the face is kept only if the last loop is closed.
+//   3. filter_faces_by_encloseness (post_processing.py:8-20): every loop rolled so that its smallest index comes first (first
+//      occurrence, like np.argmin), loops ordered by their first index (stable).
+// Outputs per sequence: valid, face_type, n_loops, loop_len[<= T], indices[<= T] (loops concatenated in canonical order), n_indices.
+// With check_enclosed = 0 only step 1 runs (n_loops = 0, indices in predicted order).
+// ------------------------------------------------------------------------------------------------
+constexpr int PF_MAX_T = 320;
+__global__ void parse_faces_kernel(const long long* __restrict__ predict, int N, int F, int T, const double* __restrict__ pts,
+                                   const long long* __restrict__ edge_off, const long long* __restrict__ wf_off, double tol,
+                                   int check_enclosed, int num_token, int type_offset, uint8_t* __restrict__ valid,
+                                   int* __restrict__ face_type, int* __restrict__ n_loops, int* __restrict__ loop_len,
+                                   int* __restrict__ indices, int* __restrict__ n_indices) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= (long long)N * F) return;
+    const int w = (int)(s / F);
+    const long long* p = predict + s * T;
+    int* idx = indices + s * T;
+    int* ll = loop_len + s * T;
+    const long long e0 = wf_off[w], ne = wf_off[w + 1] - e0;
+    int cut = T - 1;
+    for (int t = 0; t < T; ++t) { const long long v = p[t]; if (v >= type_offset && v < num_token) { cut = t; break; } }
+    const int ftype = (int)(p[cut] - type_offset);
+    int n = 0;
+    for (int t = 0; t <= cut; ++t) { const long long v = p[t] - num_token; if (v >= 0 && v < ne) idx[n++] = (int)v; }
+    bool ok = n > 0;
+    int nl = 0;
+    if (ok && check_enclosed) {
+        double cx = 0, cy = 0, lx = 0, ly = 0;            // start point of the open loop, end point of the previous edge
+        bool open = false; int cur = 0;
+        for (int i = 0; i < n && ok; ++i) {
+            const long long a = edge_off[e0 + idx[i]], b = edge_off[e0 + idx[i] + 1] - 1;
+            const double fx = pts[2 * a], fy = pts[2 * a + 1], ex = pts[2 * b], ey = pts[2 * b + 1];
+            if (!open) { cx = fx; cy = fy; open = true; }
+            else if (!(fabs(lx - fx) < tol && fabs(ly - fy) < tol)) { ok = false; break; }
+            lx = ex; ly = ey; ++cur;
+            if (fabs(ex - cx) < tol && fabs(ey - cy) < tol) { open = false; ll[nl++] = cur; cur = 0; }
+        }
+        if (open) ok = false;
+        if (ok) {
+            // roll every loop so that its smallest index comes first (in place, by cyclic rotation through a small stack buffer)
+            int pos = 0;
+            for (int l = 0; l < nl; ++l) {
+                const int len = ll[l];
+                int am = 0;
+                for (int i = 1; i < len; ++i) if (idx[pos + i] < idx[pos + am]) am = i;
+                if (am) {                                  // rotate left by am: three reversals
+                    auto rev = [&](int a, int b) { while (a < b) { const int t2 = idx[pos + a]; idx[pos + a] = idx[pos + b]; idx[pos + b] = t2; ++a; --b; } };
+                    rev(0, am - 1); rev(am, len - 1); rev(0, len - 1);
+                }
+                pos += len;
+            }
+            // order the loops by their first index: stable insertion sort of (start, len) with a scratch copy of the indices
+            int tmp[PF_MAX_T]; int start[PF_MAX_T];
+            pos = 0;
+            for (int l = 0; l < nl; ++l) { start[l] = pos; pos += ll[l]; }
+            for (int i = 0; i < n; ++i) tmp[i] = idx[i];
+            for (int a = 1; a < nl; ++a) {
+                const int st = start[a], le = ll[a], key = tmp[st];
+                int b = a - 1;
+                while (b >= 0 && tmp[start[b]] > key) { start[b + 1] = start[b]; ll[b + 1] = ll[b]; --b; }
+                start[b + 1] = st; ll[b + 1] = le;
+            }
+            pos = 0;
+            for (int l = 0; l < nl; ++l) for (int i = 0; i < ll[l]; ++i) idx[pos++] = tmp[start[l] + i];
+        }
+    }
+    valid[s] = ok ? 1 : 0;
+    face_type[s] = ftype;
+    n_loops[s] = ok ? nl : 0;
+    n_indices[s] = ok ? n : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention group geometry
 // ------------------------------------------------------------------------------------------------
 struct AttnGroups {

@@ -192,15 +192,7 @@ class Engine:
         dataset JSON (datasets/data_para.py:59-68).  Returns (input [N, num_lines, P, 2] f32, input_mask [N, num_lines] bool,
         num_input [N] i64) as torch tensors on the engine's GPU (device=True) or numpy arrays computed through host buffers."""
         import torch
-        pts, eoff, woff = [], [0], [0]
-        for edges in wireframes:
-            for e in edges:
-                a = np.asarray(e, dtype=np.float64).reshape(-1, 2)
-                pts.append(a)
-                eoff.append(eoff[-1] + a.shape[0])
-            woff.append(woff[-1] + len(edges))
-        pts = np.ascontiguousarray(np.concatenate(pts, 0) if pts else np.zeros((0, 2), np.float64))
-        eoff, woff = np.asarray(eoff, np.int64), np.asarray(woff, np.int64)
+        pts, eoff, woff = self._ragged(wireframes)
         n, nl, P = len(wireframes), self.cfg.num_lines, self.cfg.num_points_per_line
         if device:
             dev = torch.device("cuda", self.device)
@@ -217,6 +209,66 @@ class Engine:
         self._check(self._lib.ffb_featurize(self._h, _ptr(pts), _ptr(eoff), _ptr(woff), n, _ptr(out), _ptr(mask), _ptr(ni),
                                             FFB_HOST, self._stream()))
         return out, mask.astype(bool), ni
+
+    # -- the step after the path --------------------------------------------------
+    @staticmethod
+    def _ragged(wireframes):
+        pts, eoff, woff = [], [0], [0]
+        for edges in wireframes:
+            for e in edges:
+                a = np.asarray(e, dtype=np.float64).reshape(-1, 2)
+                pts.append(a)
+                eoff.append(eoff[-1] + a.shape[0])
+            woff.append(woff[-1] + len(edges))
+        pts = np.ascontiguousarray(np.concatenate(pts, 0) if pts else np.zeros((0, 2), np.float64))
+        return pts, np.asarray(eoff, np.int64), np.asarray(woff, np.int64)
+
+    def parse_faces(self, predict, wireframes, tol: float = 2e-4, check_enclosed: bool = True):
+        """predict: int64 [N, F, T] (CUDA tensor or numpy) as returned by forward_eval; wireframes: the raw `edges` lists.
+        Returns one list per wireframe of (face_type, loops) -- loops = tuple of tuples of edge indices, rolled and ordered as
+        filter_faces_by_encloseness does (post_processing.py:8-20); with check_enclosed=False (face_type, indices) as
+        Trainer.parse_parallel_faces returns them (trainer.py:196-206)."""
+        import torch
+        pts, eoff, woff = self._ragged(wireframes)
+        dev = _is_cuda(predict)
+        n, f, t = predict.shape
+        if t != self.cfg.seq_len(self.mode):
+            raise FFBError(f"predict has T={t}, the engine was created for T={self.cfg.seq_len(self.mode)}")
+        if dev:
+            d = predict.device
+            predict = predict.contiguous()
+            ins = [torch.from_numpy(x).to(d) for x in (pts, eoff, woff)]
+            valid = torch.empty((n, f), dtype=torch.uint8, device=d)
+            ft, nl, ni = (torch.empty((n, f), dtype=torch.int32, device=d) for _ in range(3))
+            ll, idx = (torch.empty((n, f, t), dtype=torch.int32, device=d) for _ in range(2))
+            loc = FFB_DEVICE
+        else:
+            predict = np.ascontiguousarray(predict, dtype=np.int64)
+            ins = [pts, eoff, woff]
+            valid = np.empty((n, f), np.uint8)
+            ft, nl, ni = (np.empty((n, f), np.int32) for _ in range(3))
+            ll, idx = (np.empty((n, f, t), np.int32) for _ in range(2))
+            loc = FFB_HOST
+        self._check(self._lib.ffb_parse_faces(self._h, _ptr(predict), n, f, _ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), float(tol),
+                                              1 if check_enclosed else 0, _ptr(valid), _ptr(ft), _ptr(nl), _ptr(ll), _ptr(idx), _ptr(ni),
+                                              loc, self._stream()))
+        if dev:
+            valid, ft, nl, ni, ll, idx = (x.cpu().numpy() for x in (valid, ft, nl, ni, ll, idx))
+        out = []
+        for w in range(n):
+            faces = []
+            for s in np.nonzero(valid[w])[0]:
+                ind = idx[w, s, :ni[w, s]].tolist()
+                if check_enclosed:
+                    loops, pos = [], 0
+                    for le in ll[w, s, :nl[w, s]].tolist():
+                        loops.append(tuple(ind[pos:pos + le]))
+                        pos += le
+                    faces.append((int(ft[w, s]), tuple(loops)))
+                else:
+                    faces.append((int(ft[w, s]), tuple(ind)))
+            out.append(faces)
+        return out
 
     # -- parity hooks ---------------------------------------------------------------------------
     def get_memory(self):

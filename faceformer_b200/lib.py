@@ -49,6 +49,7 @@ SIGNATURES = {
     "ffb_decode_greedy": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int32), _P]),
     "ffb_forward_eval": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int, C.POINTER(C.c_int32), _P]),
     "ffb_featurize": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int, _P]),
+    "ffb_parse_faces": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_double, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "ffb_get_memory": (C.c_int, [_P, _P, C.c_int, _P]),
     "ffb_get_last_logits": (C.c_int, [_P, _P, C.c_int, _P]),
     "ffb_get_last_pointer": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),

@@ -135,6 +135,23 @@ int ffb_forward_eval(ffb_handle* h, const float* coords, const uint8_t* pad_mask
 int ffb_featurize(ffb_handle* h, const double* points, const int64_t* edge_off, const int64_t* wf_edge_off, int32_t n_wireframes,
                   float* coords, uint8_t* pad_mask, int64_t* num_input, int loc, void* stream);
 
+/* Prediction parsing, the step right after the path: for every predicted sequence of `predict` [N, F, T] what
+ * Trainer.parse_parallel_faces (faceformer/trainer.py:196-206, predict half) and filter_faces_by_encloseness
+ * (faceformer/post_processing.py:8-20 over dataset/tests/check_faces_enclosed.py:11-46) do in Python, one thread per sequence:
+ * cut after the first face-type token, drop the token offset and out-of-range indices, require every edge to start where the previous
+ * one ended (|dx| < tol and |dy| < tol on the polylines' end points) and every loop to close, roll each loop so that its smallest
+ * index comes first and order the loops by their first index.  `points` / `edge_off` / `wf_edge_off` as in ffb_featurize.
+ *   valid      uint8 [N, F]     1 = the sequence yields a face (check_enclosed: ... an enclosed one)
+ *   face_type  int32 [N, F]     type token - face_type_offset (of the cut position; meaningful where valid)
+ *   n_loops    int32 [N, F]     loops of the face (0 when check_enclosed == 0)
+ *   loop_len   int32 [N, F, T]  first n_loops entries: loop lengths in canonical order
+ *   indices    int32 [N, F, T]  first n_indices entries: edge indices, loops concatenated in canonical order
+ *   n_indices  int32 [N, F]
+ * check_enclosed = post_process.is_coedge (config.py:52), tol = post_process.enclosedness_tol (config.py:51: 2e-4). */
+int ffb_parse_faces(ffb_handle* h, const int64_t* predict, int32_t n_wireframes, int32_t F, const double* points,
+                    const int64_t* edge_off, const int64_t* wf_edge_off, double tol, int32_t check_enclosed, uint8_t* valid,
+                    int32_t* face_type, int32_t* n_loops, int32_t* loop_len, int32_t* indices, int32_t* n_indices, int loc, void* stream);
+
 /* Parity hooks (used by tests; they do not change decode results). */
 
 /* Encoder memory, float [N, L, E] (= inputs['embedding'] of model.py:216); rows of padded
