@@ -113,14 +113,21 @@ struct ffb_handle {
     int opt_attn_mma = 2;                         // attention core: 2 = mma.sync fp16x2 kernel (decode, while the GEMM format is fp16x2),
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
+    int ovf_slot = 4;                             // state[] slot the fp16-range checks of the kernels raise: 4 = decode, 6 = tensor-core encoder
+    int opt_enc_tc = 1;                           // encoder layers + cross K/V projections on the tcgen05 pipeline when the batch allows it
+    bool enc_used_tc = false;
+    CUtensorMap mc_kc, mc_vc;                     // fp32 output maps of the cross-attention cache
     int num_sms = 148;
     int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
     int fp16_fallbacks = 0;                       // decodes re-run in bf16x3 because an activation exceeded the fp16 range
     struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; float s_sa_in, s_sa_out, s_ca_q, s_ca_out, s_l1, s_l2; };
+    struct EncTcW { CUtensorMap sa_in, sa_out, l1, l2; float s_sa_in, s_sa_out, s_l1, s_l2; };
     struct TcSet {                                // everything that depends on the operand format
         bool ready = false;
         DevBuf wsplit;                            // [fmt][N][K] 16-bit splits of every decode-step weight matrix
         std::vector<DecTcW> layers;
+        std::vector<EncTcW> enc;                  // encoder layers
+        CUtensorMap ck, cv; float s_ck = 1.f, s_cv = 1.f;   // packed cross-attention K / V projections of all decoder layers [Ld*E, E]
         CUtensorMap proj; float s_proj = 1.f;
         CUtensorMap m_x2, m_x2p, m_att, m_h;      // activation-operand maps (re-encoded per batch)
     };
@@ -150,6 +157,8 @@ int fail(ffb_handle* h, int code, const char* fmt, ...) {
 #define CU(h, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
     return fail((h), FFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 #define FFB_TRY(expr) do { int _r = (expr); if (_r != FFB_OK) return _r; } while (0)
+
+inline int* ovf_ptr(ffb_handle* h) { return h->state.as<int>() ? h->state.as<int>() + h->ovf_slot : nullptr; }
 
 enum { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_ROWS, PC_ATTN_TILED, PC_POINTER, PC_OTHER, PC_LINEAR_TC, PC_COUNT };
 constexpr int TC_MIN_ROWS = 2048;
@@ -272,7 +281,7 @@ int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, con
                      uint16_t* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || nq <= 0) return FFB_OK;
     AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
-    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
+    g.split_fmt = h->tc_fmt; g.overflow = ovf_ptr(h);
     if (h->opt_attn_mma)
         return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, nq, (double)G * nq * nk, PC_ATTN_ROWS, stop, s, Os, os_stride);
     dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
@@ -307,7 +316,7 @@ int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long o
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
     const int qtiles = (max_q_rows + AF_BQ - 1) / AF_BQ;
     if (qtiles > 65535) return fail(h, FFB_ERR_ARG, "attention: too many query tiles per group");
-    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
+    g.split_fmt = h->tc_fmt; g.overflow = ovf_ptr(h);
     dim3 grid(G, h->H, qtiles);
     prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
     const int qr_cap = std::min(AF_BQ, (std::min(max_q_rows, AF_BQ) + 15) & ~15);      // rows per Q tile buffer
@@ -349,7 +358,7 @@ int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, co
                       uint16_t* Os = nullptr, long long os_stride = 0) {
     if (G <= 0 || max_q_rows <= 0) return FFB_OK;
     AttnGroups g = g_in;
-    g.split_fmt = h->tc_fmt; g.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr;
+    g.split_fmt = h->tc_fmt; g.overflow = ovf_ptr(h);
     if (h->opt_attn_mma)
         return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, max_q_rows, qk_pairs, PC_ATTN_TILED, stop, s, Os, os_stride);
     if (G > 65535) return fail(h, FFB_ERR_ARG, "attention: more than 65535 groups");
@@ -450,7 +459,7 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.out_scale = 1.0f / l.w_scale; p.bias = l.bias;
     p.C = l.C; p.ldc = l.ldc; p.R = l.R; p.ldr = l.ldr;
     p.Cs = l.Cs; p.cs_split_stride = l.cs_stride; p.ldcs = l.ldcs; p.relu = l.relu;
-    p.overflow = h->state.as<int>() ? h->state.as<int>() + 4 : nullptr; p.stop = stop;
+    p.overflow = ovf_ptr(h); p.stop = stop;
     const int tiles = ((l.M + tc::BM - 1) / tc::BM) * (l.N / tc::BN);
     const int grid = std::min(tiles, h->num_sms);
     // phase-stagger only when every CTA has several tiles to amortise it: a quarter of one tile's mainloop time per group
@@ -486,11 +495,12 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
 }
 
 int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* b, uint16_t* out_plain, uint16_t* out_pos,
-                    long long split_stride, const float* pos, int pos_mod, int M, int E, const int* stop, cudaStream_t s) {
+                    long long split_stride, const float* pos, int pos_mod, int M, int E, const int* stop, cudaStream_t s,
+                    const int* pos_idx = nullptr) {
     if (M <= 0) return FFB_OK;
     prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
     layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
-                                                       h->state.as<int>() ? h->state.as<int>() + 4 : nullptr, stop);
+                                                       ovf_ptr(h), stop, pos_idx);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -535,7 +545,8 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
     const size_t E = h->E, FF = h->FF, Ld = h->Ld;
     if (!T.ready) {
         const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
-        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E) * 2));
+        const size_t Le = h->Le, per_enc = 3 * E * E + E * E + FF * E + E * FF;
+        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E + Le * per_enc + 2 * Ld * E * E) * 2));
         uint16_t* wp = T.wsplit.as<uint16_t>();
         T.layers.resize(Ld);
         for (size_t l = 0; l < Ld; ++l) {
@@ -548,7 +559,18 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
             FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &D.l1, fmt, &D.s_l1, s)); wp += fmt * FF * E;
             FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
         }
-        FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &T.proj, fmt, &T.s_proj, s));
+        FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &T.proj, fmt, &T.s_proj, s)); wp += fmt * E * E;
+        T.enc.resize(Le);
+        for (size_t l = 0; l < Le; ++l) {
+            const EncLayerW& L = h->w.enc[l];
+            ffb_handle::EncTcW& D = T.enc[l];
+            FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &D.sa_in, fmt, &D.s_sa_in, s)); wp += fmt * 3 * E * E;
+            FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &D.sa_out, fmt, &D.s_sa_out, s)); wp += fmt * E * E;
+            FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &D.l1, fmt, &D.s_l1, s)); wp += fmt * FF * E;
+            FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
+        }
+        FFB_TRY(split_weight(h, h->w.ckw, wp, Ld * E, E, &T.ck, fmt, &T.s_ck, s)); wp += fmt * Ld * E * E;
+        FFB_TRY(split_weight(h, h->w.cvw, wp, Ld * E, E, &T.cv, fmt, &T.s_cv, s));
         T.ready = true;
     }
     if (h->cap_rows > 0) {
@@ -723,6 +745,8 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
                 FFB_TRY(encode_operand_map(h, &h->mx_k, h->kc_h.p, LdE, (uint64_t)R, ax::KC, 2));
                 FFB_TRY(encode_rows_map(h, &h->mx_vrow, h->vc_h.p, LdE, (uint64_t)R, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
             }
+            FFB_TRY(encode_output_map(h, &h->mc_kc, h->Kc.p, (uint64_t)h->Ld * E, (uint64_t)R));
+            FFB_TRY(encode_output_map(h, &h->mc_vc, h->Vc.p, (uint64_t)h->Ld * E, (uint64_t)R));
             FFB_TRY(encode_rows_map(h, &h->msf_q, h->a_qkv.p, 3 * E, cr, 32, ax::BQ, CU_TENSOR_MAP_SWIZZLE_64B));
             FFB_TRY(encode_rows_map(h, &h->msf_k, h->a_qkv.p, 3 * E, cr, 32, ax::KC, CU_TENSOR_MAP_SWIZZLE_64B));
             FFB_TRY(encode_rows_map(h, &h->msf_v, h->a_qkv.p, 3 * E, cr, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -731,7 +755,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     return FFB_OK;
 }
 
-int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
+int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool allow_tc) {
     const int E = h->E, FF = h->FF, R = (int)h->R, Re = (int)h->Re, N = h->N;
     const Weights& w = h->w;
     float* x = h->x.as<float>(); float* x2 = h->x2.as<float>(); float* qkv = h->qkv.as<float>();
@@ -747,6 +771,53 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
     token_rows_kernel<<<grid1d((long long)N * h->cfg.num_token * (E / 4)), 256, 0, s>>>(w.tok_table, row_off, x, N, h->cfg.num_token, E);
     h->launches++; CU(h, cudaGetLastError());
 
+    // Encoder layers + cross K / V projections on the tcgen05 pipeline (fp16x2 GEMMs, tcgen05 attention) when the batch is large
+    // enough and every wireframe has <= 256 memory rows; otherwise fp32 SIMT GEMMs + the 3xTF32 mma.sync attention kernel.
+    const ffb_handle::TcSet& TS = h->tcs[0];
+    const bool enc_tc = allow_tc && h->opt_enc_tc && h->half_pipe && h->tc_fmt == 2 && h->attn_x_ok && (h->opt_attn_x & 1) && TS.ready &&
+                        (int)TS.enc.size() == h->Le && (h->opt_tc == 2 || R >= TC_MIN_ROWS);
+    h->enc_used_tc = enc_tc;
+    const int LdE = h->Ld * E;
+    if (enc_tc) {
+        uint16_t* ax2 = h->a_x2.as<uint16_t>(); uint16_t* ax2p = h->a_x2p.as<uint16_t>();
+        uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>(); uint16_t* aqkv = h->a_qkv.as<uint16_t>();
+        const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;
+        h->ovf_slot = 6;                                                  // an fp16-range overflow here makes ffb_encode redo the encoder in fp32
+        CU(h, cudaMemsetAsync(h->state.as<int>() + 6, 0, sizeof(int), s));
+        int rc = FFB_OK;
+        for (int li = 0; li < h->Le && rc == FFB_OK; ++li) {              // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
+            const EncLayerW& L = w.enc[li];
+            const ffb_handle::EncTcW& Tw = TS.enc[li];
+            rc = launch_ln_split(h, x, L.n1w, L.n1b, ax2, ax2p, ssE, w.pos, 1, R, E, nullptr, s, pos_idx);   // q = k = LN(x) + pos, v = LN(x)
+            if (rc != FFB_OK) break;
+            { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN; l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = L.sa.in_b;
+              l.M = R; l.N = 3 * E; l.K = E; l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv;
+              if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
+            { ax::Params ap{}; ap.mode = 0; ap.seq_off = row_off; ap.q_mul = 1; ap.row_off = row_off; ap.vlen = vlen; ap.n_groups = N;
+              ap.q_col = 0; ap.k_col = E; ap.v_col = 2 * E; ap.Os = aatt; ap.os_stride = ssE; ap.ldo = E;
+              if ((rc = launch_attn_x(h, h->msf_q, h->msf_k, h->msf_v, ap, &h->h_row_off, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break; }
+            { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = L.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+              l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = E; if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
+            if ((rc = launch_ln_split(h, x, L.n2w, L.n2b, ax2, nullptr, ssE, nullptr, 1, R, E, nullptr, s)) != FFB_OK) break;
+            { TcLin l; l.A0 = &TS.m_x2; l.W = &Tw.l1; l.w_scale = Tw.s_l1; l.bias = L.l1b; l.relu = 1; l.Cs = ah; l.cs_stride = ssF; l.ldcs = FF;
+              l.Cmap = &h->ms_h; l.M = R; l.N = FF; l.K = E; if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
+            { TcLin l; l.A0 = &TS.m_h; l.W = &Tw.l2; l.w_scale = Tw.s_l2; l.bias = L.l2b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+              l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = FF; if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
+        }
+        if (rc == FFB_OK) rc = launch_ln(h, x, w.enc_nw, w.enc_nb, mem, R, E, nullptr, s);   // encoder.norm (transformer.py:80-81)
+        if (rc == FFB_OK) {
+            // cross-attention K / V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
+            split_pos_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(mem, ax2, ax2p, ssE, w.pos, pos_idx, R, E, 2, ovf_ptr(h));
+            h->launches++;
+            { TcLin l; l.A0 = &TS.m_x2p; l.W = &TS.ck; l.w_scale = TS.s_ck; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE; l.Cmap = &h->mc_kc;
+              l.M = R; l.N = LdE; l.K = E; rc = launch_tc(h, l, nullptr, s); }
+            if (rc == FFB_OK) { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.cv; l.w_scale = TS.s_cv; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
+              l.Cmap = &h->mc_vc; l.M = R; l.N = LdE; l.K = E; rc = launch_tc(h, l, nullptr, s); }
+        }
+        h->ovf_slot = 4;
+        FFB_TRY(rc);
+        CU(h, cudaGetLastError());
+    } else {
     AttnGroups g{}; g.ragged = 1; g.q_begin = row_off; g.q_mul = 1; g.k_begin = row_off; g.k_len = vlen;
     for (int li = 0; li < h->Le; ++li) {                                  // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
         const EncLayerW& L = w.enc[li];
@@ -767,11 +838,11 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
 
     // cross-attention K/V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
     // (transformer.py:248-251; torch functional.py:5866-5873)
-    const int LdE = h->Ld * E;
     { Lin l; l.A = mem; l.lda = E; l.W = w.ckw; l.ldw = E; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE;
       l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = LdE; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
     { Lin l; l.A = mem; l.lda = E; l.W = w.cvw; l.ldw = E; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
       l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    }
     if (h->half_pipe) {      // fp16x2 copy of the cache for the half pipeline's cross-attention (overflow -> state[5], checked after the decode)
         const long long n4 = (long long)R * LdE / 4;
         CU(h, cudaMemsetAsync(h->state.as<int>() + 5, 0, sizeof(int), s));
@@ -1046,6 +1117,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
             h->opt_attn_mma = value; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
+        case FFB_OPT_ENCODER_TC: h->opt_enc_tc = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1, 2 (auto) or 3 (CTA pairs)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");
@@ -1116,7 +1188,14 @@ int ffb_encode(ffb_handle* h, const float* coords, const uint8_t* pad_mask, cons
         coords_dev = h->d_coords.as<float>();
     }
     h->attn_allow_f16 = false;
-    const int enc_rc = run_encoder(h, coords_dev, s);
+    int enc_rc = run_encoder(h, coords_dev, s, true);
+    if (enc_rc == FFB_OK && h->enc_used_tc) {          // an activation left the fp16 range in the tensor-core encoder: redo it in fp32
+        int ovf = 0;
+        cudaError_t ce = cudaMemcpyAsync(&ovf, h->state.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { h->attn_allow_f16 = true; return fail(h, FFB_ERR_CUDA, "ffb_encode: %s", cudaGetErrorString(ce)); }
+        if (ovf) { h->fp16_fallbacks++; enc_rc = run_encoder(h, coords_dev, s, false); }
+    }
     h->attn_allow_f16 = true;
     FFB_TRY(enc_rc);
     if (h->opt_timing) CU(h, cudaEventRecord(h->ev[1], s));

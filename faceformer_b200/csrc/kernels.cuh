@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
                                                               const float* __restrict__ beta, uint16_t* __restrict__ out_plain,
                                                               uint16_t* __restrict__ out_pos, long long split_stride,
                                                               const float* __restrict__ pos, int pos_mod,
-                                                              int M, int E, int fmt, int* ovf, const int* stop) {
+                                                              int M, int E, int fmt, int* ovf, const int* stop,
+                                                              const int* __restrict__ pos_idx = nullptr) {
     FFB_STOP_CHECK(stop);
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     }
     const float var = warp_sum(q) / (float)E;
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    const float* prow = (out_pos != nullptr) ? pos + (size_t)(row % pos_mod) * E : nullptr;
+    const float* prow = (out_pos != nullptr) ? pos + (size_t)(pos_idx ? pos_idx[row] : row % pos_mod) * E : nullptr;   // pos_idx: encoder rows
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (i < nv) {
@@ -366,6 +367,23 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
                 store_split4(out_pos + (size_t)row * E + c, split_stride, o, fmt, ovf);
             }
         }
+    }
+}
+
+// operand formatting without LayerNorm: out_plain <- split(x), out_pos <- split(x + pos[pos_idx[row]])  (A operands of the
+// once-per-wireframe cross-attention K / V projections, transformer.py:248-251)
+__global__ void __launch_bounds__(256) split_pos_kernel(const float* __restrict__ x, uint16_t* __restrict__ out_plain,
+                                                        uint16_t* __restrict__ out_pos, long long split_stride,
+                                                        const float* __restrict__ pos, const int* __restrict__ pos_idx,
+                                                        int M, int E, int fmt, int* ovf) {
+    const long long n4 = (long long)M * (E / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / (E / 4)), c = (int)(i % (E / 4)) * 4;
+        float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * E + c);
+        store_split4(out_plain + (size_t)row * E + c, split_stride, v, fmt, ovf);
+        const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + (size_t)pos_idx[row] * E + c));
+        v.x += pp.x; v.y += pp.y; v.z += pp.z; v.w += pp.w;
+        store_split4(out_pos + (size_t)row * E + c, split_stride, v, fmt, ovf);
     }
 }
 

@@ -216,6 +216,9 @@ enum { FFB_OPT_ATTN_X = 10 };
  * 2 (default) = variant 1 for plain / split stores and variant 0 for the in-place residual,
  * 3 = experimental CTA-pair kernel (tcgen05 cta_group::2, gemm_tc2.cuh; correct but slower in round 1). */
 enum { FFB_OPT_GEMM_VARIANT = 11 };
+/* 1 (default): encoder layers and the once-per-wireframe cross-attention K / V projections run on the tcgen05 pipeline (fp16x2 GEMMs,
+ * tcgen05 attention) when the batch has >= 2048 memory rows and <= 256 rows per wireframe; 0 = always fp32 SIMT + 3xTF32 mma.sync. */
+enum { FFB_OPT_ENCODER_TC = 12 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
