@@ -178,6 +178,37 @@ def test_tcgen05_attention_agrees_with_mma_sync_on_a_real_batch(attn_x):
     assert ok, d
 
 
+def test_tensor_core_encoder_matches_the_oracle_encoder():
+    """A batch with > 2048 memory rows: the encoder layers and the cross K/V projections run on the tcgen05 pipeline by default.
+    Encoder memory against the oracle's encoder (and against the fp32 SIMT encoder of this library): within 1e-4."""
+    from faceformer_b200 import synth
+    from faceformer_b200.lib import FFB_OPT_ENCODER_TC, FFB_OPT_PROFILE
+    from oracle import faceformer_oracle as orc
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 20, seed=11, lo=60, hi=216)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    mems = []
+    for enc_tc in (0, 1):
+        e = Engine(cfg, MODE_PARALLEL, 0)
+        e.load_state_dict(sd)
+        e.set_option(FFB_OPT_ENCODER_TC, enc_tc)
+        e.set_option(FFB_OPT_PROFILE, 1)
+        info = e.encode(coords, mask, ni)
+        prof = e.profile_read()
+        assert info["R"] >= 2048
+        assert (prof["linear_tc"]["launches"] > 0) == bool(enc_tc)
+        mems.append(e.get_memory().cpu().numpy())
+        assert e.fp16_fallbacks() == 0
+        e.close()
+    want = orc.encode(sd, cfg.to_dict(), MODE_PARALLEL, batch)[0].transpose(1, 0, 2)      # [N, L, E]
+    vm = valid_rows_mask(batch, cfg)
+    assert np.max(np.abs(mems[0][vm] - want[vm])) <= LOGIT_TOL
+    assert np.max(np.abs(mems[1][vm] - want[vm])) <= LOGIT_TOL
+    assert np.max(np.abs(mems[1][vm] - mems[0][vm])) <= LOGIT_TOL
+
+
 def test_fp16_overflow_falls_back_to_bf16x3():
     """FFN hidden activations beyond the fp16 range (linear1 x 65536, linear2 / 65536: the same function in exact
     arithmetic): the fp16x2 decode raises the overflow flag, is re-run in bf16x3 and still matches the SIMT path."""
