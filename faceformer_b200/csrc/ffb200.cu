@@ -774,8 +774,9 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
     // Encoder layers + cross K / V projections on the tcgen05 pipeline (fp16x2 GEMMs, tcgen05 attention) when the batch is large
     // enough and every wireframe has <= 256 memory rows; otherwise fp32 SIMT GEMMs + the 3xTF32 mma.sync attention kernel.
     const ffb_handle::TcSet& TS = h->tcs[0];
-    const bool enc_tc = allow_tc && h->opt_enc_tc && h->half_pipe && h->tc_fmt == 2 && h->attn_x_ok && (h->opt_attn_x & 1) && TS.ready &&
+    const bool enc_tc = allow_tc && h->opt_enc_tc && h->half_pipe && h->tc_fmt == 2 && TS.ready &&
                         (int)TS.enc.size() == h->Le && (h->opt_tc == 2 || R >= TC_MIN_ROWS);
+    const bool enc_ax = h->attn_x_ok && (h->opt_attn_x & 1);             // tcgen05 attention needs <= 256 rows per wireframe
     h->enc_used_tc = enc_tc;
     const int LdE = h->Ld * E;
     if (enc_tc) {
@@ -793,9 +794,15 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
             { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN; l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = L.sa.in_b;
               l.M = R; l.N = 3 * E; l.K = E; l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv;
               if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
-            { ax::Params ap{}; ap.mode = 0; ap.seq_off = row_off; ap.q_mul = 1; ap.row_off = row_off; ap.vlen = vlen; ap.n_groups = N;
+            if (enc_ax) {
+              ax::Params ap{}; ap.mode = 0; ap.seq_off = row_off; ap.q_mul = 1; ap.row_off = row_off; ap.vlen = vlen; ap.n_groups = N;
               ap.q_col = 0; ap.k_col = E; ap.v_col = 2 * E; ap.Os = aatt; ap.os_stride = ssE; ap.ldo = E;
-              if ((rc = launch_attn_x(h, h->msf_q, h->msf_k, h->msf_v, ap, &h->h_row_off, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break; }
+              if ((rc = launch_attn_x(h, h->msf_q, h->msf_k, h->msf_v, ap, &h->h_row_off, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break;
+            } else {                                                      // any number of keys: fp16x2 mma.sync kernel on the same operands
+              AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
+              AttnGroups g{}; g.ragged = 1; g.q_begin = row_off; g.q_mul = 1; g.k_begin = row_off; g.k_len = vlen;
+              if ((rc = launch_attn_h(h, in, aatt, ssE, g, N, h->max_vlen, h->max_vlen, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break;
+            }
             { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = L.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
               l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = E; if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
             if ((rc = launch_ln_split(h, x, L.n2w, L.n2b, ax2, nullptr, ssE, nullptr, 1, R, E, nullptr, s)) != FFB_OK) break;
