@@ -9,7 +9,9 @@
 //   Kc, Vc    cross-attention K/V cache [R, Ld*E]: computed ONCE per wireframe (the reference
 //             re-projects them every step for every sequence, transformer.py:248-251)
 //   tok       int32 [T, B_eff] step-major token buffer (== `predicts`, model_para.py:207,229)
-//   x, x2, qkv, att, h   activations of the current step, rows ordered (sequence, position)
+//   x, x2, qkv, att, h   fp32 activations of the current step, rows ordered (sequence, position)
+//   a_x2, a_x2p, a_att, a_h, a_qkv, a_qc, kc_h, vc_h   the same tensors as 16-bit operand splits (fp16x2: [2][rows][cols]) for the
+//             tensor-core pipeline: written by LayerNorm / GEMM / attention epilogues, read by TMA
 #include "../../include/ffb200.h"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
@@ -91,7 +93,7 @@ struct ffb_handle {
     // activations
     DevBuf x, x2, qkv, att, hb, xl;
     int last_P = 0;                               // P of the last executed pointer projection (seq2seq 'pointer')
-    // tensor-core path (gemm_tc.cuh): bf16x3 split weights + activation operands, TMA tensor maps
+    // tensor-core path (gemm_tc.cuh): fp16x2 / bf16x3 split weights + activation operands, TMA tensor maps
     bool tc_ok = false;                           // geometry supported (E, FF multiples of 256)
     int opt_tc = 1;                               // 0 off, 1 auto (M >= TC_MIN_ROWS), 2 force
     int opt_stagger = 0;                          // de-phase persistent GEMM CTAs (measured: no effect; kept for experiments)
@@ -887,7 +889,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>();
     uint16_t* aqkv = h->a_qkv.as<uint16_t>(); uint16_t* aqc = h->a_qc.as<uint16_t>();
     const bool hp = h->half_pipe && h->tc_fmt == 2;      // q,k,v / cross-q produced and consumed as fp16x2 (no fp32 copy)
-    const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the bf16x3 splits
+    const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the operand splits
     for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
         const DecLayerW& Lw = w.dec[li];
         const bool last = h->opt_prune && (li == Ld - 1);
@@ -930,7 +932,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             { Lin l; l.A = hb; l.lda = FF; l.W = Lw.l2w; l.ldw = FF; l.bias = Lw.l2b; l.C = cur; l.ldc = E; l.R = cur; l.ldr = E;
               l.M = rows; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, stop, s)); }
         } else {
-            // ---- tensor-core path: every GEMM operand is produced directly as bf16x3 splits ----
+            // ---- tensor-core path: every GEMM operand is produced directly in the split operand format (fp16x2 / bf16x3) ----
             const ffb_handle::DecTcW& Tw = TS.layers[li];
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
             { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2

@@ -1,8 +1,10 @@
 // kernels.cuh -- hand-written sm_100a kernels of the FaceFormer greedy pointer-decode path.
 //
-// fp32 end to end: the parity contract (token-exact vs the reference's CPU fp32 path, pointer
-// logits within 1e-4) leaves ~2x headroom over fp32 summation-order noise,
-// so every contraction here accumulates in fp32 with fp32 operands.
+// The fp32 SIMT kernels of this file accumulate in fp32 with fp32 operands (the parity contract - token-exact vs the
+// reference's CPU fp32 path, pointer logits at fp32-noise level - leaves no room for a plain 16-bit pass, SURVEY.md
+// section 7); they serve small steps / batches and odd geometries.  Large steps run on the split-precision tensor-core
+// kernels (gemm_tc.cuh, attn_x.cuh, attn_h.cuh), for which this file provides the operand formatting (LayerNorm -> fp16x2 /
+// bf16x3 splits), the pointer head, the loop control and the pre / post steps (featurize, parse_faces).
 //
 // Reference operations each kernel replaces (paths relative to /root/reference):
 //   linear_kernel      nn.Linear call sites: transformer.py:134,136,195,197, model_para.py:46,
