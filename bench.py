@@ -187,6 +187,9 @@ def run_ours(args):
     eng.load_blob(blob)
     eng.set_option(FFB_OPT_TC_FORMAT, args.tc_format)
     eng.set_option(FFB_OPT_TENSOR_CORE, args.tc)
+    if args.pdl >= 0:
+        from faceformer_b200.lib import FFB_OPT_PDL
+        eng.set_option(FFB_OPT_PDL, args.pdl)
     if args.gemm_variant >= 0:
         from faceformer_b200.lib import FFB_OPT_GEMM_VARIANT
         eng.set_option(FFB_OPT_GEMM_VARIANT, args.gemm_variant)
@@ -329,6 +332,7 @@ def main():
     ap.add_argument("--tc-format", type=int, default=2, choices=[2, 3], help="tensor-core operand format: 2 fp16x2, 3 bf16x3")
     ap.add_argument("--tc", type=int, default=1, choices=[0, 1, 2],
                     help="decode-step linear layers: 0 fp32 SIMT, 1 auto (tcgen05 bf16x3 when >= 2048 rows), 2 force tcgen05")
+    ap.add_argument("--pdl", type=int, default=-1, help="override FFB_OPT_PDL (-1 = library default)")
     ap.add_argument("--gemm-variant", type=int, default=-1, help="override FFB_OPT_GEMM_VARIANT (-1 = library default)")
     ap.add_argument("--attn-x", type=int, default=-1, help="override FFB_OPT_ATTN_X (bit mask; -1 = library default)")
     args = ap.parse_args()

@@ -39,6 +39,7 @@ __device__ __forceinline__ float ex2_approx(float x) {          // 2^x on the SF
 // decode) get small CTAs and many of them per SM.
 __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
                                                      long long os_stride, const AttnGroups g, int qr_cap, int kr_cap, const int* stop) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     extern __shared__ __align__(16) uint16_t smem_h[];
     const uint32_t qbytes = (uint32_t)qr_cap * AF_S * 2u, kbytes = (uint32_t)kr_cap * AF_S * 2u;

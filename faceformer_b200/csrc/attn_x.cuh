@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_x_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const Params p) {
     using namespace tc;
+    FFB_PDL_SYNC();
     if (p.stop != nullptr && *p.stop != 0) return;
 
     extern __shared__ uint8_t smem_raw[];

@@ -116,6 +116,7 @@ struct ffb_handle {
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
     int ovf_slot = 4;                             // state[] slot the fp16-range checks of the kernels raise: 4 = decode, 6 = tensor-core encoder
+    int opt_pdl = 0;                              // programmatic dependent launch for the decode-step kernels (measured 3 % slower: off)
     int opt_enc_tc = 1;                           // encoder layers + cross K/V projections on the tcgen05 pipeline when the batch allows it
     bool enc_used_tc = false;
     CUtensorMap mc_kc, mc_vc;                     // fp32 output maps of the cross-attention cache
@@ -230,6 +231,19 @@ void bind_weights(ffb_handle* h) {
     w.proj_w = take(E * E); w.proj_b = take(E);
 }
 
+// Launch with the programmatic-stream-serialization attribute (FFB_OPT_PDL): the kernel may be scheduled before its predecessor in
+// the stream has finished; every kernel launched this way starts with FFB_PDL_SYNC() / griddepcontrol.wait (kernels.cuh).
+template <class... KArgs, class... Args>
+inline void launch_k(ffb_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = h->opt_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int grid1d(long long total, int block = 256) {
     long long g = (total + block - 1) / block;
     return (int)std::max<long long>(1, std::min<long long>(g, 148LL * 32));
@@ -267,7 +281,7 @@ int launch_linear(ffb_handle* h, const Lin& l, const int* stop, cudaStream_t s) 
 int launch_ln(ffb_handle* h, const float* x, const float* g, const float* b, float* y, int M, int E, const int* stop, cudaStream_t s) {
     if (M <= 0) return FFB_OK;
     prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
-    layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, y, M, E, stop);
+    launch_k(h, layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, s, x, g, b, y, M, E, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -324,7 +338,7 @@ int launch_attn_h(ffb_handle* h, const AttnHalfIn& in, uint16_t* Os, long long o
     const int qr_cap = std::min(AF_BQ, (std::min(max_q_rows, AF_BQ) + 15) & ~15);      // rows per Q tile buffer
     const int kr_cap = std::min(AF_BK, (std::min(std::max(max_nk, 1), AF_BK) + 15) & ~15);   // rows per K / V tile buffer
     const int smem = (2 * qr_cap + 4 * kr_cap) * AF_S * 2;
-    attn_h_kernel<<<grid, 32 * (qr_cap / 16), smem, s>>>(in, O, h->E, Os, os_stride, g, qr_cap, kr_cap, stop);
+    launch_k(h, attn_h_kernel, grid, dim3(32 * (qr_cap / 16)), (size_t)smem, s, in, O, h->E, Os, os_stride, g, qr_cap, kr_cap, stop);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -348,7 +362,7 @@ int launch_attn_x(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, c
     p.n_heads = h->H; p.total_items = (int)items; p.stop = stop;
     const int grid = (int)std::min<long long>(items, h->num_sms);
     prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
-    ax::attn_x_kernel<<<grid, ax::NUM_THREADS, ax::SMEM_BYTES, s>>>(mq, mk, mv, p);
+    launch_k(h, ax::attn_x_kernel, dim3(grid), dim3(ax::NUM_THREADS), (size_t)ax::SMEM_BYTES, s, mq, mk, mv, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -487,9 +501,9 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     // variant 1 (two staging buffers, 3 operand stages) is faster for plain / split stores, variant 0 for the in-place residual (measured,
     // profiles/tune_gemm.py --random); 2 = choose per launch
     if (h->tc_fmt == 2 && (h->opt_gemm_variant == 1 || (h->opt_gemm_variant == 2 && !l.R)))
-        tc::gemm_kernel<2, 1><<<grid, tc::NUM_THREADS, tc::Cfg<2, 1>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
-    else if (h->tc_fmt == 2) tc::gemm_kernel<2><<<grid, tc::NUM_THREADS, tc::Cfg<2>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
-    else tc::gemm_kernel<3><<<grid, tc::NUM_THREADS, tc::Cfg<3>::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+        launch_k(h, tc::gemm_kernel<2, 1>, dim3(grid), dim3(tc::NUM_THREADS), (size_t)tc::Cfg<2, 1>::SMEM_BYTES, s, *l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+    else if (h->tc_fmt == 2) launch_k(h, tc::gemm_kernel<2, 0>, dim3(grid), dim3(tc::NUM_THREADS), (size_t)tc::Cfg<2>::SMEM_BYTES, s, *l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
+    else launch_k(h, tc::gemm_kernel<3, 0>, dim3(grid), dim3(tc::NUM_THREADS), (size_t)tc::Cfg<3>::SMEM_BYTES, s, *l.A0, l.A1 ? *l.A1 : *l.A0, *l.W, mc, p);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -501,8 +515,8 @@ int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* 
                     const int* pos_idx = nullptr) {
     if (M <= 0) return FFB_OK;
     prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
-    layernorm_split_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
-                                                       ovf_ptr(h), stop, pos_idx);
+    launch_k(h, layernorm_split_kernel, dim3((M + 7) / 8), dim3(256), 0, s, x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
+             ovf_ptr(h), stop, pos_idx);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -877,8 +891,8 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     const int LdE = Ld * E;
 
     prof_begin(h, PC_OTHER, 0.0, s);
-    gather_tgt_kernel<<<grid1d((long long)M * (E / 4)), 256, 0, s>>>(h->mem.as<float>(), row_off, h->d_seq_wf.as<int>(),
-                                                                     h->tok.as<int>(), x, B, P, E, stop);
+    launch_k(h, gather_tgt_kernel, dim3(grid1d((long long)M * (E / 4))), dim3(256), 0, s, (const float*)h->mem.as<float>(), row_off,
+             (const int*)h->d_seq_wf.as<int>(), (const int*)h->tok.as<int>(), x, B, P, E, stop);
     prof_end(h, s);
     h->launches++; CU(h, cudaGetLastError());
 
@@ -909,7 +923,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             } else {
                 // only pointer[-1] is consumed (model_para.py:176): carry just the last position from here on
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s));
-                copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
+                launch_k(h, copy_rows_kernel, dim3(grid1d((long long)B * (E / 4))), dim3(256), 0, s, (const float*)x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
                 { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E;
                   l.M = B; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
@@ -960,7 +974,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                     FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, 1, P, (double)B * P, PC_ATTN_ROWS, stop, s));
                 } else
                 FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, 1, P, P, P - 1, P, 1, stop, s, aatt, ssE));
-                copy_rows_kernel<<<grid1d((long long)B * (E / 4)), 256, 0, s>>>(x, xl, B, P, P - 1, E, stop);
+                launch_k(h, copy_rows_kernel, dim3(grid1d((long long)B * (E / 4))), dim3(256), 0, s, (const float*)x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
                 { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = xl; l.ldc = E; l.R = xl; l.ldr = E; l.Cmap = &h->mc_xl;
                   l.M = B; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
@@ -1014,11 +1028,11 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     pa.eos_count = (h->cfg.mode == FFB_MODE_SEQ2SEQ) ? st + 3 : nullptr;
     pa.stop = stop;
     prof_begin(h, PC_POINTER, 2.0 * E * h->sum_seq_vlen, s);
-    pointer_kernel<<<B, 256, 0, s>>>(pa);
+    launch_k(h, pointer_kernel, dim3(B), dim3(256), 0, s, pa);
     prof_end(h, s);
     h->launches++; CU(h, cudaGetLastError());
     if (append) {
-        step_end_kernel<<<1, 1, 0, s>>>(h->cfg.mode, B, st + 2, st + 3, st, st + 1);
+        launch_k(h, step_end_kernel, dim3(1), dim3(1), 0, s, h->cfg.mode, B, st + 2, st + 3, st, st + 1);
         h->launches++; CU(h, cudaGetLastError());
     }
     h->last_P = P;
@@ -1127,6 +1141,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             h->opt_attn_mma = value; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
         case FFB_OPT_ENCODER_TC: h->opt_enc_tc = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_PDL: h->opt_pdl = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1, 2 (auto) or 3 (CTA pairs)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");

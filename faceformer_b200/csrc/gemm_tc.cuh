@@ -176,7 +176,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapC, const Params p) {
     using C_ = Cfg<NS, V>;
     constexpr int STAGES = C_::STAGES, DRAIN_KB = C_::DRAIN_KB, STAGE_BYTES = C_::STAGE_BYTES;
-    if (p.stop != nullptr && *p.stop != 0) return;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // programmatic dependent launch (see FFB_PDL_SYNC): the next kernel's CTAs
+                                                                         // may be scheduled as ours retire
+    // everything up to the first read of global memory (barrier init, TMEM allocation) overlaps the previous kernel's tail
+    bool stopped = false;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -205,13 +208,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");                    // the previous kernel has completed and its writes are visible
+    stopped = (p.stop != nullptr && *p.stop != 0);                         // early-stopped decode: skip the work, still release TMEM below
 
     // De-phase the persistent CTAs: with identical tiles they would all reach their store phase together and hit the
     // HBM write path as one burst while the tensor pipe idles, then all compute while the write path idles
     // (measured: store time ADDED to mainloop time).  Four phase groups spread the bursts over a tile period.
     if (p.stagger_ns > 0) __nanosleep((blockIdx.x & 3u) * p.stagger_ns);
 
-    if (warp < EPI_WARP0) {
+    if (stopped) {
+    } else if (warp < EPI_WARP0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0 && lane == 0) {
             // ===== TMA producer =====

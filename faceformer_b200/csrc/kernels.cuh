@@ -30,6 +30,11 @@ namespace ffb {
 
 #define FFB_STOP_CHECK(stop) do { if ((stop) != nullptr && *(stop) != 0) return; } while (0)
 
+// Programmatic dependent launch (decode-step kernels, FFB_OPT_PDL): let the next kernel of the stream be scheduled onto SMs as this
+// grid's CTAs retire (its prologue - barrier init, TMEM allocation, descriptor fetch - then overlaps this grid's tail), and wait
+// until the previous grid has completed and flushed before touching any memory.  Both are no-ops in a normal launch.
+#define FFB_PDL_SYNC() do { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(256, 2) linear_kernel(const LinearArgs a) {
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y,
                                                         int M, int E, const int* stop) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
                                                               const float* __restrict__ pos, int pos_mod,
                                                               int M, int E, int fmt, int* ovf, const int* stop,
                                                               const int* __restrict__ pos_idx = nullptr) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -789,6 +796,7 @@ __global__ void __launch_bounds__(128) attn_tiled_kernel(const float* __restrict
 __global__ void gather_tgt_kernel(const float* __restrict__ mem, const int* __restrict__ row_off,
                                   const int* __restrict__ seq_wf, const int* __restrict__ tok,
                                   float* __restrict__ x, int B, int P, int E, const int* stop) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     const int e4n = E >> 2;
     const long long total = (long long)B * P * e4n;
@@ -804,6 +812,7 @@ __global__ void gather_tgt_kernel(const float* __restrict__ mem, const int* __re
 // dst[r] = src[r*mul + off]  (rows of E floats)
 __global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int mul, int off,
                                  int E, const int* stop) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     const int e4n = E >> 2;
     const long long total = (long long)rows * e4n;
@@ -853,6 +862,7 @@ struct PointerArgs {
 };
 
 __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
+    FFB_PDL_SYNC();
     FFB_STOP_CHECK(a.stop);
     __shared__ __align__(16) float ps[1024];
     __shared__ float bestv[8];
@@ -899,6 +909,7 @@ __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
 //   parallel (model_para.py:232): stop if all next < num_token  <=> nonstop_count == 0
 //   seq2seq  (model.py:207-210) : stop if cumulative EOS count == N
 __global__ void step_end_kernel(int mode, int n_seq, int* nonstop_count, int* eos_count, int* stop, int* steps_run) {
+    FFB_PDL_SYNC();
     if (*stop) return;
     *steps_run += 1;
     if (mode == 0) {

@@ -219,6 +219,10 @@ enum { FFB_OPT_GEMM_VARIANT = 11 };
 /* 1 (default): encoder layers and the once-per-wireframe cross-attention K / V projections run on the tcgen05 pipeline (fp16x2 GEMMs,
  * tcgen05 attention) when the batch has >= 2048 memory rows and <= 256 rows per wireframe; 0 = always fp32 SIMT + 3xTF32 mma.sync. */
 enum { FFB_OPT_ENCODER_TC = 12 };
+/* 1: the decode-step kernels are launched with programmatic stream serialization (programmatic dependent launch): each kernel's
+ * CTAs are scheduled as its predecessor's retire and wait (griddepcontrol.wait) before touching memory.  Default 0: measured 3 %
+ * SLOWER on the bench step (344 vs 333 ms), results identical. */
+enum { FFB_OPT_PDL = 13 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
