@@ -222,4 +222,46 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// attn_last_kernel: self-attention of the LAST prefix position only (the pruned last decoder layer, FFB_OPT_PRUNE_LAST: only
+// pointer[-1] is consumed, model_para.py:176).  One CTA per sequence, one warp per head: the query row b*P + P-1 against the P
+// keys / values of the sequence, all read as fp16x2 halves from the q|k|v operand buffer and recombined to fp32 (hi + lo), plain
+// fp32 dot products (lane = 2 head dims, warp-shuffle reduction), online softmax, output row b as fp16x2.
+// (The general kernels spend a whole CTA - staging, fragments, MMAs - on this one query row: 187 us per launch vs ~40 us here.)
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_last_kernel(const uint16_t* __restrict__ qkv, long long split_stride, int ld, int E,
+                                                        int P, int B, uint16_t* __restrict__ Os, long long os_stride, int ldo,
+                                                        const int* stop) {
+    FFB_PDL_SYNC();
+    FFB_STOP_CHECK(stop);
+    const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (b >= B || head * 64 >= E) return;
+    auto ld2 = [&](const uint16_t* base, long long row, int col) -> float2 {       // (hi + lo) of two adjacent elements
+        const __half2 h = *reinterpret_cast<const __half2*>(base + row * ld + col);
+        const __half2 l = *reinterpret_cast<const __half2*>(base + split_stride + row * ld + col);
+        const float2 hf = __half22float2(h), lf = __half22float2(l);
+        return make_float2(hf.x + lf.x, hf.y + lf.y);
+    };
+    const long long r0 = (long long)b * P;
+    const int c = head * 64 + 2 * lane;
+    const float2 q = ld2(qkv, r0 + P - 1, c);
+    constexpr float kScale = 0.125f * 1.4426950408889634f;                        // scores in the log2 domain
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < P; ++j) {
+        const float2 k = ld2(qkv, r0 + j, E + c);
+        const float2 v = ld2(qkv, r0 + j, 2 * E + c);
+        const float s = warp_sum(q.x * k.x + q.y * k.y) * kScale;
+        const float mn = fmaxf(m, s);
+        const float corr = ex2_approx(m - mn), p = ex2_approx(s - mn);
+        l = l * corr + p;
+        o0 = o0 * corr + p * v.x; o1 = o1 * corr + p * v.y;
+        m = mn;
+    }
+    const float inv = 1.0f / l;
+    uint32_t hw, lw;
+    split_pair(o0 * inv, o1 * inv, hw, lw);
+    *reinterpret_cast<uint32_t*>(Os + (size_t)b * ldo + c) = hw;
+    *reinterpret_cast<uint32_t*>(Os + os_stride + (size_t)b * ldo + c) = lw;
+}
+
 }  // namespace ffb

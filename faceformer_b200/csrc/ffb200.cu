@@ -968,7 +968,12 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                 { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E; l.Cmap = &h->mc_x;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             } else {
-                if (hp) {
+                if (hp && h->H <= 8) {       // one CTA per sequence, one warp per head (attn_h.cuh: attn_last_kernel)
+                    prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * h->H * (double)B * P, s);
+                    launch_k(h, attn_last_kernel, dim3(B), dim3(32 * h->H), 0, s, (const uint16_t*)aqkv, h->cap_rows * 3 * E, 3 * E, E, P, B, aatt, ssE, E, stop);
+                    prof_end(h, s);
+                    h->launches++; CU(h, cudaGetLastError());
+                } else if (hp) {
                     AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
                     AttnGroups g{}; g.ragged = 0; g.nq = 1; g.nk = P; g.q_stride = P; g.q_off = P - 1; g.k_stride = P; g.o_stride = 1;
                     FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, 1, P, (double)B * P, PC_ATTN_ROWS, stop, s));
