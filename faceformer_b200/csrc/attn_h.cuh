@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128, 3) attn_h_kernel(const AttnHalfIn in, flo
 // ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_last_kernel(const uint16_t* __restrict__ qkv, long long split_stride, int ld, int E,
                                                         int P, int B, uint16_t* __restrict__ Os, long long os_stride, int ldo,
-                                                        const int* stop) {
+                                                        const int* stop, const uint16_t* __restrict__ qlast, long long ql_split) {
     FFB_PDL_SYNC();
     FFB_STOP_CHECK(stop);
     const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,7 +244,14 @@ __global__ void __launch_bounds__(256) attn_last_kernel(const uint16_t* __restri
     };
     const long long r0 = (long long)b * P;
     const int c = head * 64 + 2 * lane;
-    const float2 q = ld2(qkv, r0 + P - 1, c);
+    // q: row b of the compact last-position buffer [2][B][E] (the q projection of the last layer is computed for these rows only),
+    // or the q columns of the full q|k|v buffer
+    float2 q;
+    if (qlast != nullptr) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(qlast + (size_t)b * E + c));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(qlast + ql_split + (size_t)b * E + c));
+        q = make_float2(hf.x + lf.x, hf.y + lf.y);
+    } else q = ld2(qkv, r0 + P - 1, c);
     constexpr float kScale = 0.125f * 1.4426950408889634f;                        // scores in the log2 domain
     float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
     for (int j = 0; j < P; ++j) {

@@ -105,6 +105,7 @@ struct ffb_handle {
     CUtensorMap ms_h;                             // fp16x2 split STORE map of a_h (FFN hidden)
     // "half pipeline" (fp16x2 GEMM + fp16x2 attention): q,k,v and the cross-attention query never exist in fp32
     DevBuf a_qkv, a_qc, kc_h, vc_h;               // [2][cap][3E], [2][cap][E], [2][R][Ld*E] halves
+    DevBuf a_ql; CUtensorMap ms_ql; long long cap_b = 0;   // [2][cap_b][E]: q of the last prefix position (pruned last layer)
     CUtensorMap ms_qkv, ms_qc;
     bool half_pipe = false;                       // set per batch at plan time
     // tcgen05 attention (attn_x.cuh): TMA load maps
@@ -422,6 +423,21 @@ int encode_rows_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t ld, uint
     return FFB_OK;
 }
 
+// fp16x2 operand view with an explicit row stride: rows `first, first + every, ...` of a [2][cap][K] buffer (the last prefix position of
+// every sequence: first = P - 1, every = P)
+int encode_operand_map_strided(ffb_handle* h, CUtensorMap* m, uint16_t* base, uint64_t K, uint64_t rows, uint64_t every, uint64_t first,
+                               uint64_t cap_rows, uint32_t box_rows) {
+    if (!g_encode_tiled) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[3] = {K, rows, 2};
+    const cuuint64_t strides[2] = {every * K * 2, cap_rows * K * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)tc::BK, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base + first * K, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FFB_ERR_CUDA, "cuTensorMapEncodeTiled(strided operand) failed with CUresult %d", (int)r);
+    return FFB_OK;
+}
+
 // weight operand [fmt][rows][K]: the 256-row-box map of the single-CTA kernel plus (fp16x2) its 128-row-box twin for the CTA-pair kernel
 int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, uint32_t box_rows, int fmt);
 int encode_weight_maps(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, int fmt) {
@@ -465,14 +481,14 @@ struct TcLin {
     float* C = nullptr; int ldc = 0; const float* R = nullptr; int ldr = 0;
     const CUtensorMap* Cmap = nullptr;          // fp32 [rows, ldc] map of C (box 32x32, SWIZZLE_128B): enables the TMA epilogue (fp16x2)
     uint16_t* Cs = nullptr; long long cs_stride = 0; int ldcs = 0;
-    int M = 0, N = 0, K = 0, relu = 0, dry_store = 0;
+    int M = 0, N = 0, K = 0, relu = 0, dry_store = 0, n_off = 0;
 };
 
 int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
     if (l.M <= 0) return FFB_OK;
     if (l.N % tc::BN != 0 || l.K % tc::BK != 0) return fail(h, FFB_ERR_ARG, "tc gemm: N %% 256 and K %% 32 must be 0 (N=%d K=%d)", l.N, l.K);
     tc::Params p{};
-    p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.out_scale = 1.0f / l.w_scale; p.bias = l.bias;
+    p.M = l.M; p.N = l.N; p.K = l.K; p.n_switch = l.n_switch; p.n_off = l.n_off; p.out_scale = 1.0f / l.w_scale; p.bias = l.bias;
     p.C = l.C; p.ldc = l.ldc; p.R = l.R; p.ldr = l.ldr;
     p.Cs = l.Cs; p.cs_split_stride = l.cs_stride; p.ldcs = l.ldcs; p.relu = l.relu;
     p.overflow = ovf_ptr(h); p.stop = stop;
@@ -754,6 +770,9 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             CU(h, h->kc_h.ensure(2 * (size_t)R * h->Ld * E * 2)); CU(h, h->vc_h.ensure(2 * (size_t)R * h->Ld * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_qkv, h->a_qkv.p, 3 * E, cr));
             FFB_TRY(encode_split_store_map(h, &h->ms_qc, h->a_qc.p, E, cr));
+            h->cap_b = (long long)rows_b;
+            CU(h, h->a_ql.ensure(2 * rows_b * E * 2));
+            FFB_TRY(encode_split_store_map(h, &h->ms_ql, h->a_ql.p, E, rows_b));
             h->attn_x_ok = (h->max_vlen <= ax::KMAX && N <= ax::MAX_GROUPS);
             if (h->attn_x_ok) {
                 const size_t LdE = (size_t)h->Ld * E;
@@ -949,6 +968,20 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             // ---- tensor-core path: every GEMM operand is produced directly in the split operand format (fp16x2 / bf16x3) ----
             const ffb_handle::DecTcW& Tw = TS.layers[li];
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
+            const bool q_last_only = last && hp && h->H <= 8;        // pruned last layer: q is needed for the last prefix position only
+            if (q_last_only) {
+                // k, v for every position: the column window [E, 3E) of the in-projection; q for the rows b*P + P-1 only, through a
+                // strided view of the LayerNorm output, into the compact buffer a_ql
+                { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = E / tc::BN; l.n_off = E;
+                  l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = M; l.N = 2 * E; l.K = E;
+                  l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv;
+                  FFB_TRY(launch_tc(h, l, stop, s)); }
+                CUtensorMap m_last;
+                FFB_TRY(encode_operand_map_strided(h, &m_last, ax2p, E, (uint64_t)B, (uint64_t)P, (uint64_t)(P - 1), (uint64_t)h->cap_rows, tc::BM));
+                { TcLin l; l.A0 = &m_last; l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = B; l.N = E; l.K = E;
+                  l.Cs = h->a_ql.as<uint16_t>(); l.cs_stride = h->cap_b * E; l.ldcs = E; l.Cmap = &h->ms_ql;
+                  FFB_TRY(launch_tc(h, l, stop, s)); }
+            } else
             { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN;      // q,k from x2+qpos; v from x2
               l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = M; l.N = 3 * E; l.K = E;
               if (hp) { l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv; }   // q,k,v straight to fp16x2
@@ -970,7 +1003,8 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             } else {
                 if (hp && h->H <= 8) {       // one CTA per sequence, one warp per head (attn_h.cuh: attn_last_kernel)
                     prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * h->H * (double)B * P, s);
-                    launch_k(h, attn_last_kernel, dim3(B), dim3(32 * h->H), 0, s, (const uint16_t*)aqkv, h->cap_rows * 3 * E, 3 * E, E, P, B, aatt, ssE, E, stop);
+                    launch_k(h, attn_last_kernel, dim3(B), dim3(32 * h->H), 0, s, (const uint16_t*)aqkv, h->cap_rows * 3 * E, 3 * E, E, P, B, aatt, ssE, E, stop,
+                             (const uint16_t*)h->a_ql.as<uint16_t>(), h->cap_b * E);
                     prof_end(h, s);
                     h->launches++; CU(h, cudaGetLastError());
                 } else if (hp) {
@@ -1119,7 +1153,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);

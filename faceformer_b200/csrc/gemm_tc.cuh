@@ -71,6 +71,8 @@ static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<2, 1>::SMEM_BYTES <= 232448 &&
 struct Params {
     int M, N, K;                 // N % 256 == 0, K % 32 == 0
     int n_switch;                // n-tiles >= n_switch read mapA1 instead of mapA0
+    int n_off;                   // column window: this launch computes output columns [n_off, n_off + N) of the full projection
+                                 // (W rows, bias entries and output columns are all shifted by n_off; multiple of 32)
     float out_scale;             // accumulator scale (undoes the power-of-two weight pre-scaling of the fp16 format)
     const float* bias;           // [N] or null
     float* C; int ldc;           // fp32 output (or null)
@@ -233,7 +235,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
                     for (int s = 0; s < NS; ++s) tma_load_3d(sa + s * A_TILE_BYTES, mapA, full_bar(stage), kc * BK, mt * BM, s);
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN, s);
+                    for (int s = 0; s < NS; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN + p.n_off, s);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -308,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
             }
-            const int col0 = nt * BN + hcol * 128;
+            const int col0 = nt * BN + hcol * 128 + p.n_off;
             const int row0 = mt * BM + q * 32;
             if constexpr (C_::STAGED_EPI) {
                 // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----

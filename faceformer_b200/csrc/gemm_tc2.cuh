@@ -131,7 +131,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             for (int t = pair; t < num_tiles; t += n_pairs) {
                 const int mt = t / n_tiles, nt = t % n_tiles;
                 const CUtensorMap* mapA = (nt >= p.n_switch) ? &mapA1 : &mapA0;
-                const int row_a = mt * 2 * BM + (int)rank * BM, row_w = nt * BN + (int)rank * (BN / 2);
+                const int row_a = mt * 2 * BM + (int)rank * BM, row_w = nt * BN + (int)rank * (BN / 2) + p.n_off;
                 for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t lbar = mapa(full_bar(stage), 0);
@@ -215,7 +215,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar(buf), 0));      // the leader's MMA thread owns the accumulators
             }
-            const int col0 = nt * BN + hcol * 128;
+            const int col0 = nt * BN + hcol * 128 + p.n_off;
             const int row0 = mt * 2 * BM + (int)rank * BM + q * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
