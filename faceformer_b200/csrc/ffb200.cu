@@ -117,6 +117,7 @@ struct ffb_handle {
                                                   // 1 = mma.sync 3xTF32 kernel, 0 = fp32 SIMT kernels
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
     int ovf_slot = 4;                             // state[] slot the fp16-range checks of the kernels raise: 4 = decode, 6 = tensor-core encoder
+    int opt_pointer_batched = 1;                  // pointer head batched per wireframe (bit-identical to pointer_kernel)
     int opt_pdl = 0;                              // programmatic dependent launch for the decode-step kernels (measured 3 % slower: off)
     int opt_enc_tc = 1;                           // encoder layers + cross K/V projections on the tcgen05 pipeline when the batch allows it
     bool enc_used_tc = false;
@@ -1067,7 +1068,10 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     pa.eos_count = (h->cfg.mode == FFB_MODE_SEQ2SEQ) ? st + 3 : nullptr;
     pa.stop = stop;
     prof_begin(h, PC_POINTER, 2.0 * E * h->sum_seq_vlen, s);
-    launch_k(h, pointer_kernel, dim3(B), dim3(256), 0, s, pa);
+    if (h->opt_pointer_batched && h->E % 128 == 0 && h->E <= 1024)   // the sequences of a wireframe share its memory rows: stream them once per 16 sequences
+        launch_k(h, pointer_batched_kernel, dim3((h->max_seq_per_wf + PB_SEQ - 1) / PB_SEQ, N), dim3(256), (size_t)PB_SEQ * E * sizeof(float), s, pa, seq_off);
+    else
+        launch_k(h, pointer_kernel, dim3(B), dim3(256), 0, s, pa);
     prof_end(h, s);
     h->launches++; CU(h, cudaGetLastError());
     if (append) {
@@ -1122,6 +1126,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc2::gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(pointer_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SEQ * 1024 * (int)sizeof(float));
+    if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(pointer_batched_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(ax::attn_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ax::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_x_kernel): %s", cudaGetErrorString(e));
     if (!g_encode_tiled) {
@@ -1181,6 +1187,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
         case FFB_OPT_ENCODER_TC: h->opt_enc_tc = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PDL: h->opt_pdl = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_POINTER_BATCHED: h->opt_pointer_batched = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1, 2 (auto) or 3 (CTA pairs)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_TENSOR_CORE: 0 off, 1 auto, 2 force");

@@ -908,6 +908,83 @@ __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
 // After each step: evaluate the reference's stop predicate and count the step.
 //   parallel (model_para.py:232): stop if all next < num_token  <=> nonstop_count == 0
 //   seq2seq  (model.py:207-210) : stop if cumulative EOS count == N
+// Batched variant: the sequences of one wireframe share its memory rows, so a CTA takes (wireframe, PB_SEQ of its sequences) and streams the
+// memory rows ONCE for all 16 (pointer_kernel re-reads them per sequence: ~1 GB through L2 per step at the bench size).  Per
+// (row, sequence) the dot product is evaluated in exactly the order of pointer_kernel (per-lane fmaf chain, then warp_sum), so logits and
+// tokens are bit-identical to it.  grid (ceil(max sequences per wireframe / PB_SEQ), N), 256 threads, dynamic smem PB_SEQ * E floats.
+constexpr int PB_SEQ = 4;
+__global__ void __launch_bounds__(256) pointer_batched_kernel(const PointerArgs a, const int* __restrict__ seq_off) {
+    FFB_PDL_SYNC();
+    FFB_STOP_CHECK(a.stop);
+    extern __shared__ __align__(16) float pb_smem[];
+    float* ps = pb_smem;                                     // [PB_SEQ][E]
+    __shared__ float bestv[8][PB_SEQ];
+    __shared__ int besti[8][PB_SEQ];
+    const int wf = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int s0 = seq_off[wf] + blockIdx.x * PB_SEQ;
+    const int nq = min(PB_SEQ, seq_off[wf + 1] - s0);
+    if (nq <= 0) return;
+    for (int i = tid; i < nq * a.E; i += 256) {
+        const int q = i / a.E, c = i - q * a.E;
+        ps[q * a.E + c] = a.ptr[((size_t)(s0 + q) * a.ptr_stride_rows + a.ptr_off) * a.E + c];
+    }
+    __syncthreads();
+    const int r0 = a.row_off[wf], vl = a.v_len[wf];
+    const int nv = a.E >> 7;                                 // float4 chunks per lane (E multiple of 128, <= 1024)
+    float bv = -INFINITY; int bi = 0x7fffffff;               // lane q < nq tracks the running best of sequence q over this warp's rows
+    for (int j = w; j < vl; j += 8) {
+        const float* mr = a.mem + (size_t)(r0 + j) * a.E;
+        float4 mv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i < nv) mv[i] = *reinterpret_cast<const float4*>(mr + lane * 4 + i * 128);
+        float sacc[PB_SEQ];
+#pragma unroll
+        for (int q = 0; q < PB_SEQ; ++q) {                   // independent fmaf chains (same per-chain order as pointer_kernel)
+            sacc[q] = 0.f;
+            if (q < nq) {
+                const float* pq = ps + q * a.E + lane * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < nv) {
+                        const float4 pv = *reinterpret_cast<const float4*>(pq + i * 128);
+                        sacc[q] = fmaf(mv[i].x, pv.x, sacc[q]); sacc[q] = fmaf(mv[i].y, pv.y, sacc[q]);
+                        sacc[q] = fmaf(mv[i].z, pv.z, sacc[q]); sacc[q] = fmaf(mv[i].w, pv.w, sacc[q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PB_SEQ; ++q) sacc[q] = warp_sum(sacc[q]);
+#pragma unroll
+        for (int q = 0; q < PB_SEQ; ++q) {
+            if (q < nq && lane == q) {
+                const float sv = sacc[q];
+                if (a.logits) a.logits[(size_t)(s0 + q) * a.L + j] = sv;
+                if (bi == 0x7fffffff || sv > bv || (sv != sv && bv == bv)) { bv = sv; bi = j; }      // first max; NaN counts as the maximum
+            }
+        }
+    }
+    if (a.logits)
+        for (int q = 0; q < nq; ++q)
+            for (int j = vl + tid; j < a.L; j += 256) a.logits[(size_t)(s0 + q) * a.L + j] = -FLT_MAX;   // finfo.min
+    if (lane < PB_SEQ) { bestv[w][lane] = bv; besti[w][lane] = bi; }
+    __syncthreads();
+    if (tid < nq) {
+        float v = bestv[0][tid]; int idx = besti[0][tid];
+        for (int k = 1; k < 8; ++k) {
+            if (besti[k][tid] == 0x7fffffff) continue;             // this warp had no rows
+            const float kv = bestv[k][tid]; const int ki = besti[k][tid];
+            const bool vn = (v != v), kn = (kv != kv);
+            if (idx == 0x7fffffff || (kn && (!vn || ki < idx)) || (!vn && !kn && (kv > v || (kv == v && ki < idx)))) { v = kv; idx = ki; }
+        }
+        if (a.tok_out) {
+            a.tok_out[s0 + tid] = idx;
+            if (a.nonstop_count && idx >= a.num_token) atomicAdd(a.nonstop_count, 1);
+            if (a.eos_count && idx == 3) atomicAdd(a.eos_count, 1);        // token.EOS == 3 (config.py:44)
+        }
+    }
+}
+
 __global__ void step_end_kernel(int mode, int n_seq, int* nonstop_count, int* eos_count, int* stop, int* steps_run) {
     FFB_PDL_SYNC();
     if (*stop) return;

@@ -20,7 +20,7 @@ HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh",
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
-FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13
+FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL, FFB_OPT_POINTER_BATCHED = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
 PROFILE_CLASSES = ("linear", "layernorm", "attn_rows", "attn_tiled", "pointer", "other", "linear_tc")
 
 

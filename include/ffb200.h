@@ -223,6 +223,9 @@ enum { FFB_OPT_ENCODER_TC = 12 };
  * CTAs are scheduled as its predecessor's retire and wait (griddepcontrol.wait) before touching memory.  Default 0: measured 3 %
  * SLOWER on the bench step (344 vs 333 ms), results identical. */
 enum { FFB_OPT_PDL = 13 };
+/* 1 (default): the pointer head (select_next) streams a wireframe's memory rows once per 16 of its sequences
+ * (pointer_batched_kernel; logits and tokens bit-identical to the per-sequence kernel); 0 = one CTA per sequence. */
+enum { FFB_OPT_POINTER_BATCHED = 14 };
 
 /* ---- op-level test hooks: run ONE kernel of the path on caller data (device pointers). ----
  * They exist so that tests can compare each kernel with the oracle's primitive. */
