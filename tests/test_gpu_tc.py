@@ -209,6 +209,31 @@ def test_tensor_core_encoder_matches_the_oracle_encoder():
     assert np.max(np.abs(mems[1][vm] - mems[0][vm])) <= LOGIT_TOL
 
 
+def test_more_wireframes_than_the_tcgen05_attention_groups():
+    """260 small wireframes in one batch: more groups than attn_x_kernel's prefix table holds (255), so the cross-attention and the
+    encoder self-attention take the mma.sync kernel while GEMMs and decoder self-attention stay on tcgen05.  Tokens equal to the
+    all-SIMT run, logits within tolerance."""
+    from faceformer_b200 import synth
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 260, seed=17, lo=6, hi=14)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    out = []
+    for mode in (0, 1):
+        e = Engine(cfg, MODE_PARALLEL, 0)
+        e.load_state_dict(sd)
+        e.set_option(FFB_OPT_TENSOR_CORE, mode)
+        pred, steps = e.forward_eval(coords, mask, ni)
+        out.append((pred.cpu().numpy(), steps, e.get_last_logits().cpu().numpy(), e.fp16_fallbacks(), e.batch_info()))
+        e.close()
+    assert out[1][4]["N"] == 260 and out[1][4]["R"] >= 2048 and out[1][3] == 0
+    assert out[0][1] == out[1][1]
+    assert np.array_equal(out[0][0], out[1][0]), f"{(out[0][0] != out[1][0]).sum()} token mismatches"
+    ok, d = logits_close(out[1][2], out[0][2], tol=2e-4)
+    assert ok, d
+
+
 def test_fp16_overflow_falls_back_to_bf16x3():
     """FFN hidden activations beyond the fp16 range (linear1 x 65536, linear2 / 65536: the same function in exact
     arithmetic): the fp16x2 decode raises the overflow flag, is re-run in bf16x3 and still matches the SIMT path."""
