@@ -296,6 +296,14 @@ def run_ours(args):
                     "avg_launch_ms": lin["ms"] / max(1, lin["launches"]), "launches_per_step": lin["launches"],
                     "share_of_step": lin["ms"] / tot_ms if tot_ms else None,
                     "fp32_ffma_peak_tflops": 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
+                    # whole-step view against the HBM roofline: algorithmic bytes of the decode (66 KB per (row, layer) for the
+                    # Ld-1 full decoder layers -- GEMM operands / outputs 40, LayerNorm 14, self-attention 8, cross-attention 4 KB -- and 18 KB
+                    # for the pruned last layer), rows = B_eff * S(S+1)/2, over the device-timed step
+                    "step_hbm": (lambda rows, t: {"algorithmic_bytes": rows * ((cfg.num_decoder_layers - 1) * 66e3 + 18e3),
+                                                  "achieved_gbs": rows * ((cfg.num_decoder_layers - 1) * 66e3 + 18e3) / t / 1e9,
+                                                  "peak_gbs": peaks["hbm_gbs"],
+                                                  "frac": rows * ((cfg.num_decoder_layers - 1) * 66e3 + 18e3) / t / 1e9 / peaks["hbm_gbs"]})(
+                        info["B_eff"] * S * (S + 1) / 2.0, ms / args.steps / 1e3),
                     "breakdown_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
                     "breakdown_tflops": {k: (round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 3) if v["ms"] > 0 else 0.0) for k, v in prof.items()}}
         cpu = None
@@ -306,7 +314,8 @@ def run_ours(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "dtype_note": "fp32-class: fp16x2 split operands (x = hi + lo), 3 tcgen05 passes per product, fp32 accumulation; fp32 LayerNorm / softmax / residuals",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "wireframes_per_step_per_gpu": N, "sequences_per_step_per_gpu": info["B"],
                        "sequences_decoded_per_gpu": info["B_eff"], "decode_steps": S, "memory_rows": info["R"],
                        "weights": f"synthetic seed {args.seed} recipe diverse (32.3 M params, fp32)",

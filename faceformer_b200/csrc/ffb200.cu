@@ -532,8 +532,12 @@ int launch_ln_split(ffb_handle* h, const float* x, const float* g, const float* 
                     const int* pos_idx = nullptr) {
     if (M <= 0) return FFB_OK;
     prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)E, s);
-    launch_k(h, layernorm_split_kernel, dim3((M + 7) / 8), dim3(256), 0, s, x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
-             ovf_ptr(h), stop, pos_idx);
+    if (E <= 512)
+        launch_k(h, layernorm_split_kernel<4>, dim3((M + 7) / 8), dim3(256), 0, s, x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
+                 ovf_ptr(h), stop, pos_idx);
+    else
+        launch_k(h, layernorm_split_kernel<8>, dim3((M + 7) / 8), dim3(256), 0, s, x, g, b, out_plain, out_pos, split_stride, pos, pos_mod, M, E, h->tc_fmt,
+                 ovf_ptr(h), stop, pos_idx);
     prof_end(h, s);
     h->launches++;
     CU(h, cudaGetLastError());

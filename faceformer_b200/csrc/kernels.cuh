@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // layernorm + operand formatting for the tensor-core GEMM: writes bf16x3 splits of y = LN(x) (out_plain) and/or of
 // y + pos[r % pos_mod] (out_pos) -- with_pos_embed (transformer.py:144-145,205-206) fused into the producer.
+template <int NV>      // float4 chunks per lane: E = 128 * NV columns (a compile-time bound keeps the row in NV * 4 registers: more CTAs per SM)
 __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, uint16_t* __restrict__ out_plain,
                                                               uint16_t* __restrict__ out_pos, long long split_stride,
@@ -338,11 +339,11 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const float* xr = x + (size_t)row * E;
-    float4 v[8];
-    const int nv = E >> 7;
+    float4 v[NV];
+    const int nv = E >> 7;                      // <= NV
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv) {
             v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     const float mean = warp_sum(s) / (float)E;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv) {
             v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
             q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     const float* prow = (out_pos != nullptr) ? pos + (size_t)(pos_idx ? pos_idx[row] : row % pos_mod) * E : nullptr;   // pos_idx: encoder rows
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv) {
             const int c = i * 128 + lane * 4;
             const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
