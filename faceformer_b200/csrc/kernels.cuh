@@ -66,17 +66,14 @@ __device__ __forceinline__ void store_split4(uint16_t* dst, long long stride, fl
         *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(o1);
         *reinterpret_cast<uint2*>(dst + 2 * stride) = *reinterpret_cast<const uint2*>(o2);
     } else {
-        const float x[4] = {v.x, v.y, v.z, v.w};
-        __align__(8) __half h[4], l[4];
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            bad |= !(fabsf(x[i]) <= 65504.f);
-            h[i] = __float2half_rn(x[i]);
-            l[i] = __float2half_rn(x[i] - __half2float(h[i]));
-        }
-        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(dst + stride) = *reinterpret_cast<const uint2*>(l);
+        // packed conversions (one F2FP per pair) and one max-|x| test instead of four compares
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        const bool bad = !(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) <= 65504.f) ||
+                         (v.x != v.x) || (v.y != v.y) || (v.z != v.z) || (v.w != v.w);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(dst + stride) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         if (bad && ovf) *ovf = 1;
     }
 }
