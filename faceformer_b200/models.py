@@ -156,6 +156,23 @@ class _SurfaceFormerB200Base(nn.Module):
             return self.forward_train(inputs)
         return self.forward_eval(inputs)
 
+    # -- the steps right before / after the path, on the same device ------
+    def _current_engine(self) -> Engine:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise FFBError("faceformer_b200 has no CPU path: move the model to a CUDA device first")
+        return self.engine(p.device.index if p.device.index is not None else torch.cuda.current_device())
+
+    def featurize(self, wireframes):
+        """Raw `edges` lists of the dataset JSON -> (input, input_mask, num_input) CUDA tensors, bit-identical to what
+        ABCDataset_Parallel.__getitem__ + the default collate produce (datasets/data_para.py:8-25,59-68)."""
+        return self._current_engine().featurize(wireframes, device=True)
+
+    def parse_faces(self, predict, wireframes, tol: float = 2e-4, check_enclosed: bool = True):
+        """inputs['predict'] + raw `edges` lists -> per wireframe the list of (face_type, loops) that parse_parallel_faces
+        (trainer.py:196-206) followed by filter_faces_by_encloseness (post_processing.py:8-20) return for the predictions."""
+        return self._current_engine().parse_faces(predict, wireframes, tol=tol, check_enclosed=check_enclosed)
+
 
 class SurfaceFormer_Parallel_B200(_SurfaceFormerB200Base):
     """Replaces SurfaceFormer_Parallel (model_para.py:12-259) on the eval path."""

@@ -70,3 +70,30 @@ def test_parse_faces_after_a_real_decode():
     want = [fo.filter_faces_by_encloseness(wfs[w], fo.parse_predicts(pn[w], len(wfs[w])), 2e-4) for w in range(len(wfs))]
     assert got == want and sum(len(f) for f in got) > 0
     e.close()
+
+
+@pytest.mark.gpu
+def test_model_class_featurize_decode_parse_roundtrip():
+    """The reference-facing class: raw edge lists -> featurize -> model(batch) -> parse_faces, all on the device; equals the
+    oracle's featurisation / parsing around the same decode."""
+    import torch
+    from faceformer_b200 import synth
+    from faceformer_b200.config import MODE_PARALLEL, TINY
+    from faceformer_b200.models import SurfaceFormer_Parallel_B200
+    from oracle import featurize_oracle as feo
+    wfs, _ = fo.synth_case(5, TINY.num_lines, TINY.max_face_length, 21)
+    sd = synth.synth_state_dict(TINY, MODE_PARALLEL, 3, "diverse")
+    m = SurfaceFormer_Parallel_B200(**TINY.model_kwargs(MODE_PARALLEL)).eval()
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    m = m.cuda()
+    inp, mask, ni = m.featurize(wfs)
+    oi, om, on = feo.featurize(wfs, TINY.num_lines)
+    assert np.array_equal(inp.cpu().numpy().view(np.uint32), oi.view(np.uint32)) and np.array_equal(mask.cpu().numpy(), om)
+    batch = {"input": inp, "input_mask": mask, "num_input": ni,
+             "label": torch.zeros((len(wfs), TINY.num_lines, TINY.max_face_length), dtype=torch.int64, device="cuda")}
+    with torch.no_grad():
+        out = m(batch)
+    got = m.parse_faces(out["predict"], wfs)
+    pn = out["predict"].cpu().numpy()
+    want = [fo.filter_faces_by_encloseness(wfs[w], fo.parse_predicts(pn[w], len(wfs[w])), 2e-4) for w in range(len(wfs))]
+    assert got == want
