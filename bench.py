@@ -2,21 +2,23 @@
 """bench.py -- decoded edges/sec (greedy) of the FaceFormer pointer-decode path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the CPU arm (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU arm (unmodified torch reference, oracle/_ref), rank 0 only
 
 A "step" is one pass of the hot path (model(batch): embedding + encoder + cross-K/V + the whole
 greedy loop) over one batch of synthetic wireframes.  Workload (BASELINE.json configs[1]):
 configs/ours.yml geometry (E=512, H=8, FF=1024, 6+6 layers, num_lines=216, T=37), batch=32
-wireframes per GPU, n_edges ~ U[24,216], greedy decode.  Metric: decoded edges/s = B*S / time, with
-B = N*F sequences the reference decodes per batch and S the executed decode steps.
+wireframes per GPU, n_edges ~ U[24,216], greedy decode.  Metric: decoded edges/s = B_eff*S / time, with
+B_eff the DISTINCT sequences of the batch (the reference decodes B = N*F slots, of which the F - n_i padded
+anchors of a wireframe are copies of one sequence; `value_slots` = B*S / time is the SURVEY.md 8d count) and S the
+executed decode steps.  Both arms report both counts.
 
 Keys beyond the base contract:
   value     device-resident inputs/outputs, CUDA-event timed on the launching stream, max over ranks
   e2e       same metric through the C ABI with HOST buffers (pinned): H2D of inputs and D2H of
             `predict` inside the timed region
-  roofline  the dominant kernel (linear_kernel): algorithmic FLOPs per launch / event-timed duration,
+  roofline  the dominant kernel (tc::gemm_kernel): algorithmic FLOPs per launch / event-timed duration,
             measured on one extra (untimed) step with an event pair around every launch
-  cpu_baseline  the numpy oracle port timed on this box's host cores on a bounded sample
+  cpu_baseline  the unmodified torch reference (oracle/_ref) timed on this box's host cores on a bounded stratified sample
 """
 from __future__ import annotations
 
@@ -40,6 +42,8 @@ from faceformer_b200.config import MODE_PARALLEL, OURS  # noqa: E402
 METRIC = "decoded_edges_per_sec"
 UNIT = "edges/s"
 WORKLOAD = "configs/ours.yml greedy decode, batch=32 wireframes/GPU, num_lines=216, T=37, n_edges~U[24,216]"
+COUNT_NOTE = ("value counts DISTINCT decoded sequences x steps (B_eff*S: padded-anchor slots are copies of one sequence and are not "
+              "counted); value_slots counts the reference's output slots (N*F*S, SURVEY.md 8d)")
 
 
 def load_peaks():
@@ -83,17 +87,24 @@ class ClockSampler(threading.Thread):
                     reasons=reasons, samples=len(self.rows))
 
 
-def cpu_sample(seed):
-    """Bounded sample of the workload for the CPU arm: ONE wireframe with 24 edges (the distribution's
-    smallest), full ours.yml model, all 36 decode steps -> 24*S decoded edges."""
-    cfg = OURS
-    batch = synth.synth_batch(cfg, MODE_PARALLEL, 1, seed=seed, num_edges=np.array([24], np.int64))
-    return cfg, batch
+# ---- CPU arm: the UNMODIFIED torch reference (oracle/_ref, copied by oracle/build_ref.py) on the host cores -------------------
+# A bounded, stratified sample of the workload (the reference needs 73 GFLOP per decoded sequence): each entry is one
+# model(batch) call.  "ragged" batches have padded anchors (F > n_i), like the N=32 GPU batch; singles are the reference's own test
+# batch size (trainer.py:51).
+CPU_SAMPLES = {
+    "step": [[24, 30]],                      # one ragged N=2 batch per `--impl reference` step (~5 s on 16 cores)
+    "baseline": [[24], [24, 30], [96]],      # the cpu_baseline leg of the default run (~20-40 s)
+}
 
 
 def use_all_cores():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core (BLAS thread pool raised at run time)."""
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core."""
     n = os.cpu_count() or 1
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=n)
@@ -112,46 +123,78 @@ def load_traffic(kernel_tag):
         return (None, None)
 
 
-def time_oracle(sd, seed, repeats=1):
-    from oracle import faceformer_oracle as orc
-    use_all_cores()
-    cfg, batch = cpu_sample(seed)
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        out = orc.forward_eval(sd, cfg.to_dict(), MODE_PARALLEL, batch)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    edges = int(batch["num_input"].max()) * 1 * out["steps"]
-    return edges / best, best, edges
+class CpuReference:
+    """model(batch) of the unmodified reference (kind "reference"); falls back to the numpy oracle port (kind "port") only when
+    oracle/_ref is absent."""
+
+    def __init__(self, sd):
+        self.cores = use_all_cores()
+        self.sd = sd
+        try:
+            import torch
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            from build_ref import import_reference
+            _, cls = import_reference()
+            m = cls(**OURS.model_kwargs(MODE_PARALLEL)).eval()
+            m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+            self.kind, self.model, self.torch = "reference", m, torch
+        except Exception as e:                          # noqa: BLE001
+            self.kind, self.model, self.why = "port", None, repr(e)
+
+    def run(self, sample, seed):
+        """-> dict(seconds, slots, distinct, steps): slots = sum N*F*S (what the reference decodes), distinct = the sequences that
+        differ (padded anchors are copies of the row-3 sequence)."""
+        sec = slots = distinct = 0
+        steps = []
+        for ne in sample:
+            ne = np.asarray(ne, np.int64)
+            batch = synth.synth_batch(OURS, MODE_PARALLEL, len(ne), seed=seed, num_edges=ne)
+            t0 = time.perf_counter()
+            if self.kind == "reference":
+                with self.torch.no_grad():
+                    pred = self.model({k: self.torch.from_numpy(v) for k, v in batch.items()})["predict"].numpy()
+                flat = pred.reshape(-1, pred.shape[-1])
+                S = next((s for s in range(1, flat.shape[1]) if np.all(flat[:, s] < 4)), flat.shape[1] - 1)
+            else:
+                from oracle import faceformer_oracle as orc
+                S = orc.forward_eval(self.sd, OURS.to_dict(), MODE_PARALLEL, batch)["steps"]
+            sec += time.perf_counter() - t0
+            F = int(ne.max())
+            slots += len(ne) * F * S
+            distinct += int(sum(n + (1 if (n < F and n < 4) else 0) for n in ne)) * S
+            steps.append(int(S))
+        return dict(seconds=sec, slots=slots, distinct=distinct, steps=steps)
+
+    def describe(self, sample, r):
+        what = ("unmodified torch reference (oracle/_ref: faceformer/models/model_para.py forward_eval), fp32, torch "
+                f"{self.torch.__version__}" if self.kind == "reference" else "numpy port (oracle/faceformer_oracle.py; oracle/_ref missing)")
+        return (f"{what}; model(batch) calls with n_edges {sample} (ragged batches decode N*F slots incl. padded anchors), full ours.yml "
+                f"model, steps {r['steps']}: {r['distinct']} distinct / {r['slots']} slot edges in {r['seconds']:.1f} s")
 
 
 def run_reference(args):
-    """CPU arm: the oracle port (numpy restatement of the reference as written) on host cores."""
+    """CPU arm: the reference's own CPU implementation on all host cores, one bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    try:
-        import torch
-        torch.set_num_threads(os.cpu_count())
-    except Exception:
-        pass
     sd = synth.synth_state_dict(OURS, MODE_PARALLEL, args.seed, "diverse")
-    times, edges = [], 0
+    ref = CpuReference(sd)
+    sample = CPU_SAMPLES["step"]
+    times, r = [], None
     for i in range(args.warmup + args.steps):
-        v, dt, edges = time_oracle(sd, args.seed)
+        r = ref.run(sample, args.seed)
         if i >= args.warmup:
-            times.append(dt)
+            times.append(r["seconds"])
     dt = float(np.mean(times))
-    value = edges / dt
-    sample = ("numpy/OpenBLAS port of forward_eval as written (oracle/faceformer_oracle.py), 1 wireframe x 24 edges, "
-              "full ours.yml model, 36 steps per step; the unmodified torch reference ran the same sample ~2.7x faster "
-              "in the build container (see DESIGN.md)")
+    value, value_slots = r["distinct"] / dt, r["slots"] / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "1 wireframe x 24 edges per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"one model(batch) call per step, n_edges {sample}", "edge_count": COUNT_NOTE},
+        "value_slots": value_slots,
+        "cpu_baseline": {"value": value, "value_slots": value_slots, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                         "sample": ref.describe(sample, r)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -258,11 +301,13 @@ def run_ours(args):
     launches = eng.kernel_launches() - l0
     clocks = sampler.stop() if sampler else None
 
-    edges_local = torch.tensor([float(info["B"] * S)], device=dev, dtype=torch.float64)
+    # [distinct sequences x steps (the work done), reference output slots x steps]
+    edges_local = torch.tensor([float(info["B_eff"] * S), float(info["B"] * S)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(edges_local)
-    edges_per_step = float(edges_local.item())
+    edges_per_step, slots_per_step = float(edges_local[0].item()), float(edges_local[1].item())
     value = edges_per_step * args.steps / (ms / 1e3)
+    value_slots = slots_per_step * args.steps / (ms / 1e3)
 
     # end to end through the C ABI with host buffers
     step_host()
@@ -308,20 +353,21 @@ def run_ours(args):
                     "breakdown_tflops": {k: (round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 3) if v["ms"] > 0 else 0.0) for k, v in prof.items()}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, edges = time_oracle(sd, args.seed)
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"oracle/faceformer_oracle.py (numpy), 1 wireframe x 24 edges, 36 steps = {edges} edges in {dt:.1f} s"}
+            ref = CpuReference(sd)
+            r = ref.run(CPU_SAMPLES["baseline"], args.seed)
+            cpu = {"value": r["distinct"] / r["seconds"], "value_slots": r["slots"] / r["seconds"], "unit": UNIT, "cores": ref.cores,
+                   "kind": ref.kind, "sample": ref.describe(CPU_SAMPLES["baseline"], r)}
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "value_slots": value_slots, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "dtype_note": "fp32-class: fp16x2 split operands (x = hi + lo), 3 tcgen05 passes per product, fp32 accumulation; fp32 LayerNorm / softmax / residuals",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "wireframes_per_step_per_gpu": N, "sequences_per_step_per_gpu": info["B"],
+            "config": {"workload": WORKLOAD, "edge_count": COUNT_NOTE, "wireframes_per_step_per_gpu": N, "sequences_per_step_per_gpu": info["B"],
                        "sequences_decoded_per_gpu": info["B_eff"], "decode_steps": S, "memory_rows": info["R"],
                        "weights": f"synthetic seed {args.seed} recipe diverse (32.3 M params, fp32)",
                        "l2": "no explicit flush: per-step activations + cross-K/V cache are GBs, far larger than the 126 MB L2",
                        "parallelism": f"dp{world} (whole batches per rank; NCCL weight broadcast + all-gather of predictions)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "value_slots": e2e_value * slots_per_step / edges_per_step, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}))
     eng.close()

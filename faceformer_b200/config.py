@@ -79,3 +79,8 @@ SEQ2SEQ = ModelConfig(num_lines=110, label_seq_length=259)             # configs
 TINY = ModelConfig(num_model=128, num_head=2, num_feedforward=256,
                    num_encoder_layers=2, num_decoder_layers=2,
                    num_lines=28, max_face_length=10, label_seq_length=24)
+# E = 512 / H = 8 geometry (on the tcgen05 grid: E, FF multiples of 256) small enough to TRAIN on the CPU with the reference's own
+# forward_train and to commit the checkpoint as an int8-grid fixture (oracle/train_fixture.py --cfg mid).
+MID = ModelConfig(num_model=512, num_head=8, num_feedforward=256,
+                  num_encoder_layers=1, num_decoder_layers=2,
+                  num_lines=28, max_face_length=10, label_seq_length=24)

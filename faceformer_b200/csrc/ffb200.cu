@@ -146,6 +146,10 @@ struct ffb_handle {
     std::vector<ProfRec> prof_recs;
     double sum_seq_vlen = 0, sum_vlen2 = 0;       // sum_i seqs_i*vlen_i and sum_i vlen_i^2 (attention FLOP accounting)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    volatile int* h_stop = nullptr;               // pinned host mirror of the stop flag, one slot per step (early stop without a host sync)
+    int h_stop_cap = 0;
+    int steps_launched = 0;                       // decode steps whose kernels were launched by the last ffb_decode_greedy
+    std::vector<CUtensorMap> m_last;              // per prefix length P: strided view of a_x2p (rows b*P + P-1), pruned last layer
     std::vector<uint8_t> h_mask;
     std::vector<int64_t> h_num_input;
 };
@@ -778,6 +782,10 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             h->cap_b = (long long)rows_b;
             CU(h, h->a_ql.ensure(2 * rows_b * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_ql, h->a_ql.p, E, rows_b));
+            h->m_last.resize(h->T);
+            for (int P = 1; P < h->T; ++P)
+                FFB_TRY(encode_operand_map_strided(h, &h->m_last[P], h->a_x2p.as<uint16_t>(), E, (uint64_t)h->B, (uint64_t)P, (uint64_t)(P - 1),
+                                                   (uint64_t)h->cap_rows, tc::BM));
             h->attn_x_ok = (h->max_vlen <= ax::KMAX && N <= ax::MAX_GROUPS);
             if (h->attn_x_ok) {
                 const size_t LdE = (size_t)h->Ld * E;
@@ -792,6 +800,42 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             FFB_TRY(encode_rows_map(h, &h->msf_v, h->a_qkv.p, 3 * E, cr, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
         }
     }
+    return FFB_OK;
+}
+
+// Cross-attention K / V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
+// (transformer.py:248-251; torch functional.py:5866-5873).  use_tc: fp16x2 tcgen05 GEMMs (the tensor-core encoder), else fp32 SIMT.
+int run_cross_cache(ffb_handle* h, cudaStream_t s, bool use_tc) {
+    const int E = h->E, R = (int)h->R, LdE = h->Ld * E;
+    const Weights& w = h->w;
+    float* mem = h->mem.as<float>();
+    const int* pos_idx = h->d_pos_idx.as<int>();
+    if (use_tc) {
+        const ffb_handle::TcSet& TS = h->tcs[0];
+        const long long ssE = h->cap_rows * E;
+        split_pos_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(mem, h->a_x2.as<uint16_t>(), h->a_x2p.as<uint16_t>(), ssE, w.pos, pos_idx, R, E, 2, ovf_ptr(h));
+        h->launches++;
+        { TcLin l; l.A0 = &TS.m_x2p; l.W = &TS.ck; l.w_scale = TS.s_ck; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE; l.Cmap = &h->mc_kc;
+          l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_tc(h, l, nullptr, s)); }
+        { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.cv; l.w_scale = TS.s_cv; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
+          l.Cmap = &h->mc_vc; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_tc(h, l, nullptr, s)); }
+        return FFB_OK;
+    }
+    { Lin l; l.A = mem; l.lda = E; l.W = w.ckw; l.ldw = E; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE;
+      l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = LdE; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    { Lin l; l.A = mem; l.lda = E; l.W = w.cvw; l.ldw = E; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
+      l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    return FFB_OK;
+}
+
+// fp16x2 copy of the cache for the half pipeline's cross-attention (overflow -> state[5], checked after the decode)
+int run_cross_cache_split(ffb_handle* h, cudaStream_t s) {
+    if (!h->half_pipe) return FFB_OK;
+    const long long n4 = (long long)h->R * h->Ld * h->E / 4;
+    CU(h, cudaMemsetAsync(h->state.as<int>() + 5, 0, sizeof(int), s));
+    split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
+    split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
+    h->launches += 2; CU(h, cudaGetLastError());
     return FFB_OK;
 }
 
@@ -852,15 +896,7 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
               l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = FF; if ((rc = launch_tc(h, l, nullptr, s)) != FFB_OK) break; }
         }
         if (rc == FFB_OK) rc = launch_ln(h, x, w.enc_nw, w.enc_nb, mem, R, E, nullptr, s);   // encoder.norm (transformer.py:80-81)
-        if (rc == FFB_OK) {
-            // cross-attention K / V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
-            split_pos_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(mem, ax2, ax2p, ssE, w.pos, pos_idx, R, E, 2, ovf_ptr(h));
-            h->launches++;
-            { TcLin l; l.A0 = &TS.m_x2p; l.W = &TS.ck; l.w_scale = TS.s_ck; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE; l.Cmap = &h->mc_kc;
-              l.M = R; l.N = LdE; l.K = E; rc = launch_tc(h, l, nullptr, s); }
-            if (rc == FFB_OK) { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.cv; l.w_scale = TS.s_cv; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
-              l.Cmap = &h->mc_vc; l.M = R; l.N = LdE; l.K = E; rc = launch_tc(h, l, nullptr, s); }
-        }
+        if (rc == FFB_OK) rc = run_cross_cache(h, s, true);
         h->ovf_slot = 4;
         FFB_TRY(rc);
         CU(h, cudaGetLastError());
@@ -882,22 +918,9 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
           l.M = R; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, nullptr, s)); }
     }
     FFB_TRY(launch_ln(h, x, w.enc_nw, w.enc_nb, mem, R, E, nullptr, s));   // encoder.norm (transformer.py:80-81)
-
-    // cross-attention K/V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
-    // (transformer.py:248-251; torch functional.py:5866-5873)
-    { Lin l; l.A = mem; l.lda = E; l.W = w.ckw; l.ldw = E; l.bias = w.ckb; l.C = h->Kc.as<float>(); l.ldc = LdE;
-      l.pos = w.pos; l.ldpos = E; l.pos_idx = pos_idx; l.pos_cols = LdE; l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
-    { Lin l; l.A = mem; l.lda = E; l.W = w.cvw; l.ldw = E; l.bias = w.cvb; l.C = h->Vc.as<float>(); l.ldc = LdE;
-      l.M = R; l.N = LdE; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    FFB_TRY(run_cross_cache(h, s, false));
     }
-    if (h->half_pipe) {      // fp16x2 copy of the cache for the half pipeline's cross-attention (overflow -> state[5], checked after the decode)
-        const long long n4 = (long long)R * LdE / 4;
-        CU(h, cudaMemsetAsync(h->state.as<int>() + 5, 0, sizeof(int), s));
-        split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
-        split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
-        h->launches += 2; CU(h, cudaGetLastError());
-    }
-    return FFB_OK;
+    return run_cross_cache_split(h, s);
 }
 
 // ---- one decode step --------------------------------------------------------------------------------
@@ -981,9 +1004,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                   l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = M; l.N = 2 * E; l.K = E;
                   l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv;
                   FFB_TRY(launch_tc(h, l, stop, s)); }
-                CUtensorMap m_last;
-                FFB_TRY(encode_operand_map_strided(h, &m_last, ax2p, E, (uint64_t)B, (uint64_t)P, (uint64_t)(P - 1), (uint64_t)h->cap_rows, tc::BM));
-                { TcLin l; l.A0 = &m_last; l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = B; l.N = E; l.K = E;
+                { TcLin l; l.A0 = &h->m_last[P];                      // encoded once per batch (plan_batch) l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = B; l.N = E; l.K = E;
                   l.Cs = h->a_ql.as<uint16_t>(); l.cs_stride = h->cap_b * E; l.ldcs = E; l.Cmap = &h->ms_ql;
                   FFB_TRY(launch_tc(h, l, stop, s)); }
             } else
@@ -1167,6 +1188,7 @@ int ffb_destroy(ffb_handle* h) {
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
+    if (h->h_stop) cudaFreeHost((void*)h->h_stop);
     delete h;
     return FFB_OK;
 }
@@ -1184,10 +1206,10 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (h->weights_loaded && h->tc_ok && h->opt_tc) { int rc = prepare_tc(h, value, nullptr); if (rc != FFB_OK) return rc; }
             return FFB_OK;
         case FFB_OPT_STAGGER: h->opt_stagger = value ? 1 : 0; return FFB_OK;
-        case FFB_OPT_TMA_EPILOGUE: h->opt_tma_out = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_TMA_EPILOGUE: h->opt_tma_out = value ? 1 : 0; h->encoded = false; return FFB_OK;   // half_pipe is planned per batch
         case FFB_OPT_ATTN_MMA:
             if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ATTN_MMA: 0 SIMT, 1 3xTF32, 2 fp16x2");
-            h->opt_attn_mma = value; return FFB_OK;
+            h->opt_attn_mma = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
         case FFB_OPT_ENCODER_TC: h->opt_enc_tc = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PDL: h->opt_pdl = value ? 1 : 0; return FFB_OK;
@@ -1227,6 +1249,7 @@ int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, vo
     if (h->tc_ok && h->opt_tc) FFB_TRY(prepare_tc(h, h->tc_fmt, s));
     CU(h, cudaStreamSynchronize(s));
     h->weights_loaded = true;
+    h->encoded = false; h->decoded = false;                 // mem / Kc / Vc of an earlier ffb_encode belong to the old weights
     return FFB_OK;
 }
 
@@ -1307,10 +1330,28 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         CU(h, cudaMemsetAsync(st, 0, 5 * sizeof(int), s));          // [5] = overflow seen while encoding: survives
         init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
         h->launches++; CU(h, cudaGetLastError());
-        for (int step = 0; step < T - 1; ++step) FFB_TRY(run_step(h, step + 1, true, s));   // no host sync inside the loop
+        // No host sync inside the loop.  The stop flag is mirrored into pinned host memory after every step; once a copy that has
+        // already landed shows it set, the remaining steps (whose kernels would all exit at once) are not launched at all.
+        if (h->h_stop_cap < T) {
+            if (h->h_stop) cudaFreeHost((void*)h->h_stop);
+            h->h_stop = nullptr; h->h_stop_cap = 0;
+            void* hp = nullptr;
+            CU(h, cudaHostAlloc(&hp, (size_t)T * sizeof(int), cudaHostAllocDefault));
+            h->h_stop = (volatile int*)hp; h->h_stop_cap = T;
+        }
+        for (int i = 0; i < T; ++i) h->h_stop[i] = 0;
+        h->steps_launched = 0;
+        for (int step = 0; step < T - 1; ++step) {
+            bool stopped = false;
+            for (int i = 0; i < step && !stopped; ++i) stopped = h->h_stop[i] != 0;
+            if (stopped) break;
+            FFB_TRY(run_step(h, step + 1, true, s));
+            CU(h, cudaMemcpyAsync((void*)(h->h_stop + step), st, sizeof(int), cudaMemcpyDeviceToHost, s));
+            h->steps_launched = step + 1;
+        }
         expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
         h->launches++; CU(h, cudaGetLastError());
-        if (!syncing) break;                      // fully asynchronous call: the overflow flag is left for ffb_overflowed()
+        if (!syncing) break;                      // fully asynchronous call: the caller must check ffb_overflowed() after its own sync
         int host_state[3] = {0, 0, 0};            // executed steps, fp16 overflow flag (decode), fp16 overflow flag (K/V cache split)
         CU(h, cudaMemcpyAsync(&host_state[0], st + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaMemcpyAsync(&host_state[1], st + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1470,6 +1511,28 @@ int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream) {
     return FFB_OK;
 }
 
+int ffb_set_memory(ffb_handle* h, const float* memory, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_set_memory before ffb_encode");
+    if (!memory) return fail(h, FFB_ERR_ARG, "memory is NULL");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)h->N * h->L * h->E * sizeof(float);
+    const float* src = memory;
+    if (loc == FFB_HOST) {
+        CU(h, h->d_out_stage.ensure(bytes));
+        CU(h, cudaMemcpyAsync(h->d_out_stage.p, memory, bytes, cudaMemcpyHostToDevice, s));
+        src = h->d_out_stage.as<float>();
+    }
+    pack_memory_kernel<<<grid1d((long long)h->R * (h->E / 4)), 256, 0, s>>>(src, h->d_row_off.as<int>(), h->d_vlen.as<int>(), h->mem.as<float>(),
+                                                                         h->N, h->L, h->E);
+    h->launches++; CU(h, cudaGetLastError());
+    FFB_TRY(run_cross_cache(h, s, false));
+    FFB_TRY(run_cross_cache_split(h, s));
+    h->decoded = false;
+    return FFB_OK;
+}
+
 static int emit_logits(ffb_handle* h, float* logits, int loc, cudaStream_t s) {
     const size_t bytes = (size_t)h->B_full * h->L * sizeof(float);
     float* dst = logits;
@@ -1548,6 +1611,26 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
     h->decoded = false;
     return emit_logits(h, logits, loc, s);
 }
+
+int ffb_overflowed(ffb_handle* h, int32_t* overflowed, void* stream) {
+    if (!h || !overflowed) return FFB_ERR_ARG;
+    *overflowed = 0;
+    if (!h->decoded) return fail(h, FFB_ERR_STATE, "ffb_overflowed before a decode");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    int ovf[2] = {0, 0};
+    CU(h, cudaMemcpyAsync(ovf, h->state.as<int>() + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (h->tc_fmt == 2 && (ovf[0] || (h->half_pipe && ovf[1]))) {
+        *overflowed = 1;
+        h->tc_fmt = 3; h->fp16_fallbacks++;            // sticky: every later encode / decode on this handle runs in bf16x3
+        h->encoded = false; h->decoded = false;       // the predictions just produced are invalid: the caller must run the batch again
+        FFB_TRY(prepare_tc(h, 3, s));
+    }
+    return FFB_OK;
+}
+
+int ffb_steps_launched(const ffb_handle* h) { return h ? h->steps_launched : 0; }
 
 int64_t ffb_kernel_launches(const ffb_handle* h) { return h ? h->launches : 0; }
 

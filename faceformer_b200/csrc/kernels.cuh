@@ -1035,6 +1035,19 @@ __global__ void unpack_memory_kernel(const float* __restrict__ mem, const int* _
     }
 }
 
+// inverse of unpack_memory_kernel: [N, L, E] -> packed valid rows (parity hook ffb_set_memory)
+__global__ void pack_memory_kernel(const float* __restrict__ in, const int* __restrict__ row_off, const int* __restrict__ v_len,
+                                   float* __restrict__ mem, int n_wf, int L, int E) {
+    const int e4n = E >> 2;
+    for (int w = 0; w < n_wf; ++w) {
+        const long long total = (long long)v_len[w] * e4n;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)(i % e4n), j = (int)(i / e4n);
+            reinterpret_cast<float4*>(mem)[(size_t)(row_off[w] + j) * e4n + c] = reinterpret_cast<const float4*>(in)[((size_t)w * L + j) * e4n + c];
+        }
+    }
+}
+
 // int64 prefix [P, B_full] -> int32 tok [P, B_eff] through seq -> first slot map
 __global__ void load_prefix_kernel(const long long* __restrict__ prefix, const int* __restrict__ seq_slot,
                                    int* __restrict__ tok, int P, int B_full, int B) {

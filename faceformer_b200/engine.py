@@ -278,6 +278,12 @@ class Engine:
         self._check(self._lib.ffb_get_memory(self._h, _ptr(out), self._loc, self._stream()))
         return out
 
+    def set_memory(self, memory):
+        """Error-budget hook: replace the encoder memory [N, L, E] (CUDA tensor or numpy) and recompute the cross K / V cache."""
+        dev = _is_cuda(memory)
+        memory = memory.contiguous().float() if dev else np.ascontiguousarray(memory, dtype=np.float32)
+        self._check(self._lib.ffb_set_memory(self._h, _ptr(memory), FFB_DEVICE if dev else FFB_HOST, self._stream()))
+
     def get_last_logits(self):
         import torch
         info = self.batch_info()
@@ -313,6 +319,16 @@ class Engine:
 
     def fp16_fallbacks(self) -> int:
         return int(self._lib.ffb_fp16_fallbacks(self._h))
+
+    def overflowed(self) -> bool:
+        """After an asynchronous decode (want_steps=False on CUDA tensors): did an activation leave the fp16 range?  True means the
+        predictions are invalid, the handle now runs in bf16x3, and the batch must be run again."""
+        flag = C.c_int32(0)
+        self._check(self._lib.ffb_overflowed(self._h, C.byref(flag), self._stream()))
+        return bool(flag.value)
+
+    def steps_launched(self) -> int:
+        return int(self._lib.ffb_steps_launched(self._h))
 
     def kernel_launches(self) -> int:
         return int(self._lib.ffb_kernel_launches(self._h))

@@ -7,6 +7,7 @@ in-tree with nvcc for sm_100a (cross-compiles on a CPU-only box).
 from __future__ import annotations
 
 import ctypes as C
+import glob
 import os
 import shutil
 import subprocess
@@ -15,8 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libffb200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ffb200.cu")]
-HEADERS = [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "gemm_tc.cuh", "attn_mma.cuh", "attn_f16.cuh")] + \
-          [os.path.join(ROOT, "include", "ffb200.h")]
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join(ROOT, "include", "ffb200.h")]
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
@@ -51,11 +51,14 @@ SIGNATURES = {
     "ffb_featurize": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int, _P]),
     "ffb_parse_faces": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_double, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "ffb_get_memory": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ffb_set_memory": (C.c_int, [_P, _P, C.c_int, _P]),
     "ffb_get_last_logits": (C.c_int, [_P, _P, C.c_int, _P]),
     "ffb_get_last_pointer": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),
     "ffb_forced_prefix_logits": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int, _P]),
     "ffb_kernel_launches": (C.c_int64, [_P]),
     "ffb_fp16_fallbacks": (C.c_int, [_P]),
+    "ffb_overflowed": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
+    "ffb_steps_launched": (C.c_int, [_P]),
     "ffb_phase_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "ffb_profile_read": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ffb_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

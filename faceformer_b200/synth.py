@@ -243,3 +243,37 @@ def polygon_batch(cfg: ModelConfig, n: int, seed: int = 0, max_faces: int = 5):
     out = {k: np.stack([np.asarray(it[k]) for it in items]) for k in items[0]}
     out["id"] = np.arange(n, dtype=np.int64)
     return out
+
+
+# --------------------------------------------------------------------------- checkpoint fixtures
+def quantize_state_dict(sd, bits: int = 8):
+    """Snap every >= 2-d float tensor to a per-tensor symmetric integer grid (w = q * scale) so that a trained checkpoint
+    can be committed as a small fixture.  Returns the npz payload: ``name`` (1-d / int tensors as they are) or
+    ``name::q`` (int8) + ``name::scale`` (fp32 scalar)."""
+    out = {}
+    qmax = float(2 ** (bits - 1) - 1)
+    for k, v in sd.items():
+        v = np.asarray(v)
+        if v.dtype.kind == "f" and v.ndim >= 2:
+            scale = np.float32(np.abs(v).max() / qmax) if np.abs(v).max() > 0 else np.float32(1.0)
+            out[k + "::q"] = np.clip(np.round(v / scale), -qmax, qmax).astype(np.int8)
+            out[k + "::scale"] = scale
+        else:
+            out[k] = v
+    return out
+
+
+def load_state_dict_npz(path):
+    """Inverse of np.savez(**sd) / np.savez(**quantize_state_dict(sd)): fp32 tensors by reference state_dict name."""
+    with np.load(path) as z:
+        raw = {k: z[k] for k in z.files}
+    sd = {}
+    for k, v in raw.items():
+        if k.endswith("::scale"):
+            continue
+        if k.endswith("::q"):
+            name = k[:-3]
+            sd[name] = (v.astype(np.float32) * np.float32(raw[name + "::scale"])).astype(np.float32)
+        else:
+            sd[k] = v
+    return sd

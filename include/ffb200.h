@@ -158,6 +158,11 @@ int ffb_parse_faces(ffb_handle* h, const int64_t* predict, int32_t n_wireframes,
  * edges are written as zeros (the reference computes values there that nothing reads). */
 int ffb_get_memory(ffb_handle* h, float* memory, int loc, void* stream);
 
+/* Error-budget hook: REPLACE the encoder memory of the encoded batch by caller data, float [N, L, E] (rows of padded edges are
+ * ignored), and recompute the cross-attention K / V cache from it.  Feeding the reference's float64 memory isolates the
+ * decoder + pointer-head contribution to the logit error (profiles/logit_noise.py). */
+int ffb_set_memory(ffb_handle* h, const float* memory, int loc, void* stream);
+
 /* Masked pointer logits [B, L] (select_next up to masked_fill, model_para.py:173-177) of the
  * LAST executed decode step, expanded to the reference's B = N*F rows. */
 int ffb_get_last_logits(ffb_handle* h, float* logits, int loc, void* stream);
@@ -172,9 +177,20 @@ int ffb_get_last_pointer(ffb_handle* h, float* pointer, int32_t* P_out, int loc,
 int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, float* logits,
                              int loc, void* stream);
 
-/* Number of decodes that had to be re-run in bf16x3 because an activation left the fp16 range (see FFB_OPT_TC_FORMAT).
- * A fully asynchronous ffb_decode_greedy (device buffers, steps_run == NULL) cannot re-run: poll this afterwards. */
+/* Number of decodes that had to be re-run in bf16x3 because an activation left the fp16 range (see FFB_OPT_TC_FORMAT). */
 int ffb_fp16_fallbacks(const ffb_handle* h);
+
+/* A fully asynchronous ffb_decode_greedy (device buffers, steps_run == NULL) cannot look at the fp16-range flag of the default
+ * operand format and therefore cannot re-run by itself.  After such a call, ffb_overflowed() synchronises `stream` and reports in
+ * *overflowed whether an activation left the fp16 range.  If so the predictions of that decode are INVALID: the handle has been
+ * switched to the bf16x3 format (sticky, ffb_fp16_fallbacks() is incremented) and the batch must be encoded and decoded again.
+ * The syncing forms of ffb_decode_greedy (steps_run != NULL or host buffers) do all of this internally. */
+int ffb_overflowed(ffb_handle* h, int32_t* overflowed, void* stream);
+
+/* Decode steps whose kernels the last ffb_decode_greedy launched: the host watches a pinned mirror of the device-side stop flag and
+ * stops launching once the early-stop predicate (model_para.py:232 / model.py:207-210) has fired; == executed steps + the few
+ * steps that were already queued when the flag arrived. */
+int ffb_steps_launched(const ffb_handle* h);
 
 /* Count of this library's kernels launched on the handle since creation (bench `gpu_launches`). */
 int64_t ffb_kernel_launches(const ffb_handle* h);

@@ -73,8 +73,7 @@ ENCODER_CASES = {
 def load_weights(spec, cfg, mode):
     if spec[0] == "synth":
         return synth.synth_state_dict(cfg, mode, seed=spec[1], recipe=spec[2])
-    with np.load(os.path.join(GOLDEN, spec[1])) as z:
-        return {k: z[k] for k in z.files}
+    return synth.load_state_dict_npz(os.path.join(GOLDEN, spec[1]))
 
 
 def load_inputs(spec, cfg, mode, n):

@@ -30,8 +30,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
-from faceformer_b200.config import MODE_PARALLEL, TINY  # noqa: E402
-from faceformer_b200.synth import polygon_sample  # noqa: E402
+from faceformer_b200.config import MID, MODE_PARALLEL, TINY  # noqa: E402
+from faceformer_b200.synth import load_state_dict_npz, polygon_sample, quantize_state_dict  # noqa: E402
 
 
 def collate(samples):
@@ -59,10 +59,14 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-seconds", type=float, default=1500)
     ap.add_argument("--out", default=os.path.join(ROOT, "tests/golden/tiny_trained_parallel.npz"))
+    ap.add_argument("--cfg", default="tiny", choices=["tiny", "mid"],
+                    help="tiny: E=128 (fp32 checkpoint); mid: E=512/H=8 on the tcgen05 grid, saved on an int8 grid (--quantize 8)")
+    ap.add_argument("--quantize", type=int, default=0, help="snap >= 2-d weights to a per-tensor symmetric N-bit grid before saving")
+    ap.add_argument("--warmup-steps", type=int, default=0, help="linear learning-rate warm-up")
     args = ap.parse_args()
 
     from faceformer.models import SurfaceFormer_Parallel
-    cfg = TINY
+    cfg = MID if args.cfg == "mid" else TINY
     torch.manual_seed(args.seed)
     torch.set_num_threads(os.cpu_count())
     rng = np.random.default_rng(args.seed)
@@ -74,6 +78,9 @@ def main():
         batch = collate([polygon_sample(rng, cfg) for _ in range(args.batch)])
         out = model(batch)
         loss, acc = compute_loss(out)
+        if args.warmup_steps:
+            for g in opt.param_groups:
+                g["lr"] = args.lr * min(1.0, (step + 1) / args.warmup_steps)
         opt.zero_grad(); loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
@@ -83,7 +90,12 @@ def main():
             break
     model.eval()
     sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
-    np.savez_compressed(args.out, **sd)
+    if args.quantize:
+        np.savez_compressed(args.out, **quantize_state_dict(sd, args.quantize))
+        sd = load_state_dict_npz(args.out)          # evaluate what the fixture actually holds
+        model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    else:
+        np.savez_compressed(args.out, **sd)
     # quick look at greedy behaviour
     batch = collate([polygon_sample(rng, cfg) for _ in range(2)])
     with torch.no_grad():

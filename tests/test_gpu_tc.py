@@ -261,3 +261,60 @@ def test_fp16_overflow_falls_back_to_bf16x3():
     for r in res:                                                   # both runs against the reference's logits (noise-floor clause, util.py)
         ok, d = logits_close(r[2], g["last_logits"], b64=g.get("last_logits64"))
         assert ok, d
+
+
+def test_async_decode_reports_fp16_overflow():
+    """a fully asynchronous decode (device buffers, no steps_run) cannot re-run by itself; ffb_overflowed() must report
+    the fp16-range overflow, switch the handle to bf16x3 and the re-run must then match the SIMT path."""
+    g = load_case("ours_parallel_small")
+    sd = {k: v.copy() for k, v in g["sd"].items()}
+    for k in sd:
+        if k.startswith("decoder.") and (k.endswith("linear1.weight") or k.endswith("linear1.bias")):
+            sd[k] = sd[k] * np.float32(65536.0)
+        if k.startswith("decoder.") and k.endswith("linear2.weight"):
+            sd[k] = sd[k] / np.float32(65536.0)
+    b = g["batch"]
+    coords = torch.from_numpy(b["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda()
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(sd)
+    e.set_option(FFB_OPT_TENSOR_CORE, 2)
+    pred, steps = e.forward_eval(coords, mask, ni, want_steps=False)
+    assert steps is None
+    assert e.overflowed() is True and e.fp16_fallbacks() == 1
+    with pytest.raises(Exception):
+        e.get_last_logits()                                       # the invalid decode is no longer readable
+    pred, _ = e.forward_eval(coords, mask, ni, want_steps=False)   # now in bf16x3
+    assert e.overflowed() is False and e.fp16_fallbacks() == 1
+    assert np.array_equal(pred.cpu().numpy(), g["predict"])
+    e.close()
+    # a healthy asynchronous decode reports no overflow
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_TENSOR_CORE, 2)
+    pred, _ = e.forward_eval(coords, mask, ni, want_steps=False)
+    assert e.overflowed() is False and e.fp16_fallbacks() == 0
+    assert np.array_equal(pred.cpu().numpy(), g["predict"])
+    e.close()
+
+
+def test_reload_and_option_change_invalidate_the_encoded_batch():
+    """stale encoder state must not survive a weight reload or an option that feeds the per-batch plan."""
+    from faceformer_b200.lib import FFB_OPT_ATTN_MMA, FFBError
+    g = load_case("ours_parallel_small")
+    b = g["batch"]
+    coords = torch.from_numpy(b["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda()
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.encode(coords, mask, ni)
+    e.load_state_dict(g["sd"])
+    with pytest.raises(FFBError):
+        e.decode_greedy()
+    e.encode(coords, mask, ni)
+    e.set_option(FFB_OPT_ATTN_MMA, 1)
+    with pytest.raises(FFBError):
+        e.decode_greedy()
+    pred, steps = e.forward_eval(coords, mask, ni)
+    assert np.array_equal(pred.cpu().numpy(), g["predict"]) and steps == g["steps"]
+    e.close()

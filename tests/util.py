@@ -23,8 +23,7 @@ def load_case(name):
     if w[0] == "synth":
         sd = synth.synth_state_dict(cfg, mode, seed=w[1], recipe=w[2])
     else:
-        with np.load(os.path.join(GOLDEN, w[1])) as z:
-            sd = {k: z[k] for k in z.files}
+        sd = synth.load_state_dict_npz(os.path.join(GOLDEN, w[1]))
     i = meta["inputs"]
     if i[0] == "synth":
         ne = None if i[2] is None else np.asarray(i[2], np.int64)
