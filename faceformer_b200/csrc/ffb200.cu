@@ -20,6 +20,7 @@
 #include "attn_f16.cuh"
 #include "attn_h.cuh"
 #include "attn_x.cuh"
+#include "enc64.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -74,6 +75,21 @@ struct ffb_handle {
     std::string err;
     bool weights_loaded = false, encoded = false, decoded = false;
     int opt_dedup = 1, opt_prune = 1, opt_timing = 0;
+    int opt_enc_prec = 2;                         // encoder + cross K/V projections: 2 = float64 (default, enc64.cuh), 0 = fp16x2 tcgen05 / fp32 SIMT
+    int opt_head64 = 1;                           // decoder.norm + project + pointer dot of the last position in float64
+    DevBuf x64, y64, yp64, qkv64, att64, h64;
+    DevBuf projT, memW, hy32;                     // folded head: [W_project^T ; b_project] (E+1 x E), memory . projT^T [R, E+4], LN of the last position [B, E]
+    bool enc_used_64 = false;
+    int opt_encode_only = 0;                      // encoder-only use (BASELINE configs[4]): no decode workspaces, no cross K/V cache, no folded head
+    bool encode_only = false;                     // ... of the encoded batch
+    int opt_force_F = 0;                          // F of the GLOBAL batch when this handle decodes a share of it (0 = local max(num_input))
+    // cross-rank stop predicate (batch splitting): flag buffers of all ranks, mapped through CUDA IPC
+    bool xchg_on = false; int xchg_rank = 0, xchg_world = 1, xchg_epoch = 0;
+    int* xchg_buf = nullptr; int* xchg_peers[XCHG_MAXW] = {};
+    int opt_beam = 1;                             // beam width W (parallel mode; 1 = greedy): every anchor owns W consecutive sequences
+    int W = 1;                                    // beam width of the encoded batch
+    int tok_sel = 0;                              // which half of the double-buffered token array is current (beam re-ordering)
+    DevBuf beam_cum;                              // double [B]: cumulative log-probabilities of the hypotheses
     int64_t launches = 0;
 
     DevBuf wblob, wcross;
@@ -118,7 +134,9 @@ struct ffb_handle {
     bool attn_allow_f16 = true;                   // cleared while encoding (an overflow flag raised there would be lost)
     int ovf_slot = 4;                             // state[] slot the fp16-range checks of the kernels raise: 4 = decode, 6 = tensor-core encoder
     int opt_pointer_batched = 1;                  // pointer head batched per wireframe (bit-identical to pointer_kernel)
-    int opt_pdl = 0;                              // programmatic dependent launch for the decode-step kernels (measured 3 % slower: off)
+    int opt_pdl = 2;                              // programmatic dependent launch for the decode-step kernels: 0 off, 1 on, 2 auto (small batches:
+                                                  // measured +5..10 % at N = 1, -3 % on the 32-wireframe bench batch)
+    bool pdl_on = false;                          // decided per batch
     int opt_enc_tc = 1;                           // encoder layers + cross K/V projections on the tcgen05 pipeline when the batch allows it
     bool enc_used_tc = false;
     CUtensorMap mc_kc, mc_vc;                     // fp32 output maps of the cross-attention cache
@@ -167,10 +185,12 @@ int fail(ffb_handle* h, int code, const char* fmt, ...) {
     return fail((h), FFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 #define FFB_TRY(expr) do { int _r = (expr); if (_r != FFB_OK) return _r; } while (0)
 
+inline int* tok_cur(ffb_handle* h) { return h->tok.as<int>() + (size_t)h->tok_sel * h->T * h->B; }
 inline int* ovf_ptr(ffb_handle* h) { return h->state.as<int>() ? h->state.as<int>() + h->ovf_slot : nullptr; }
 
 enum { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_ROWS, PC_ATTN_TILED, PC_POINTER, PC_OTHER, PC_LINEAR_TC, PC_COUNT };
-constexpr int TC_MIN_ROWS = 2048;
+constexpr int TC_MIN_ROWS = 2048;       // encoder: below this many memory rows the tensor-core encoder is not worth its operand formatting
+constexpr int TC_MIN_ROWS_DECODE = 1;    // decode steps: the tcgen05 GEMM beats the SIMT kernel at every M (measured r2: 4x at M <= 258, profiles/probe_small_r2a.json)
 
 inline void prof_begin(ffb_handle* h, int cls, double flops, cudaStream_t s) {
     if (!h->opt_profile) return;
@@ -246,7 +266,7 @@ inline void launch_k(ffb_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 bl
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = h->opt_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = h->pdl_on ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -681,6 +701,10 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             F = std::max<int64_t>(F, num_input[i]);
         }
         if (F < 1) return fail(h, FFB_ERR_ARG, "max(num_input) must be >= 1");
+        if (h->opt_force_F > 0) {
+            if (h->opt_force_F < F) return fail(h, FFB_ERR_ARG, "FFB_OPT_FORCE_F = %d is smaller than this share's max(num_input) = %lld", h->opt_force_F, (long long)F);
+            F = h->opt_force_F;                                     // F = max(num_input) over the whole (split) batch, model_para.py:187
+        }
         h->F = (int)F;
         slot_seq.assign((size_t)N * F, 0);
         for (int i = 0; i < N; ++i) {
@@ -719,6 +743,17 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         h->B_full = N;
     }
     h->h_seq_off[N] = (int)seq_wf.size();
+    h->W = (h->cfg.mode == FFB_MODE_PARALLEL) ? h->opt_beam : 1;
+    if (h->W > 1) {                                // beam search: hypothesis w of anchor sequence a is sequence a*W + w
+        const int W = h->W;
+        std::vector<int> wf2, first2, slot2;
+        for (size_t a = 0; a < seq_wf.size(); ++a)
+            for (int w = 0; w < W; ++w) { wf2.push_back(seq_wf[a]); first2.push_back(seq_first[a]); slot2.push_back(seq_slot[a]); }
+        seq_wf.swap(wf2); seq_first.swap(first2); seq_slot.swap(slot2);
+        for (auto& v : slot_seq) v *= W;           // output slot -> hypothesis 0 (the best one) of its anchor
+        for (auto& v : h->h_seq_off) v *= W;
+        max_spw *= W;
+    }
     h->B = (long long)seq_wf.size();
     h->half_pipe = false; h->attn_x_ok = false;
     h->sum_seq_vlen = 0; h->sum_vlen2 = 0;
@@ -727,7 +762,9 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         h->sum_vlen2 += (double)h->h_vlen[i] * h->h_vlen[i];
     }
     h->max_seq_per_wf = max_spw;
-    const long long Mmax = h->B * (long long)(h->T - 1);
+    h->encode_only = h->opt_encode_only != 0;
+    const long long Mmax = h->encode_only ? 0 : h->B * (long long)(h->T - 1);
+    h->pdl_on = (h->opt_pdl == 1) || (h->opt_pdl == 2 && Mmax <= 32768);      // launch-latency-bound regime
     if (Mmax * (long long)std::max(3 * h->E, h->FF) > 0x7fffffffffLL) return fail(h, FFB_ERR_ARG, "batch too large");
     if (Mmax > 0x7fffffffLL / 4) return fail(h, FFB_ERR_ARG, "batch too large (decode rows)");
 
@@ -749,18 +786,23 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     // rows padded to the GEMM tile height: the TMA epilogue writes whole 32-row blocks (rows >= M hold don't-care values)
     const size_t rows = ((size_t)std::max<long long>(std::max<long long>(R, Mmax), 1) + 127) / 128 * 128;
     CU(h, h->mem.ensure((size_t)R * E * f4));
-    CU(h, h->Kc.ensure((size_t)R * h->Ld * E * f4));
-    CU(h, h->Vc.ensure((size_t)R * h->Ld * E * f4));
-    CU(h, h->tok.ensure((size_t)h->T * h->B * sizeof(int)));
-    CU(h, h->logits.ensure((size_t)h->B * h->L * f4));
+    const size_t Rc = h->encode_only ? 1 : (size_t)R;                       // rows of the decode-side per-wireframe caches
+    const size_t Bd = h->encode_only ? 1 : (size_t)h->B;                    // sequences the decode-side buffers are sized for
+    CU(h, h->Kc.ensure(Rc * h->Ld * E * f4));
+    CU(h, h->Vc.ensure(Rc * h->Ld * E * f4));
+    CU(h, h->tok.ensure(2 * (size_t)h->T * Bd * sizeof(int)));              // double-buffered (beam re-ordering)
+    CU(h, h->beam_cum.ensure(Bd * sizeof(double)));
+    h->tok_sel = 0;
+    CU(h, h->logits.ensure(Bd * h->L * f4));
     CU(h, h->state.ensure(8 * sizeof(int)));
     CU(h, h->x.ensure(rows * E * f4));
     CU(h, h->x2.ensure(rows * E * f4));
     CU(h, h->qkv.ensure(rows * 3 * E * f4));
     CU(h, h->att.ensure(rows * E * f4));
     CU(h, h->hb.ensure(std::max(rows, (size_t)Re) * std::max(FF, E) * f4));
-    const size_t rows_b = ((size_t)std::max<long long>(h->B, 1) + 127) / 128 * 128;
+    const size_t rows_b = ((size_t)std::max<long long>((long long)Bd, 1) + 127) / 128 * 128;
     CU(h, h->xl.ensure(rows_b * E * f4));
+    CU(h, h->hy32.ensure(rows_b * E * f4)); CU(h, h->memW.ensure(Rc * (E + 4) * f4));
     if (h->tc_ok && h->opt_tc) {
         h->cap_rows = (long long)((rows + 127) / 128 * 128);
         const size_t cr = (size_t)h->cap_rows;
@@ -776,25 +818,25 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         h->half_pipe = (h->tc_fmt == 2 && h->opt_attn_mma == 2 && h->opt_tma_out);
         if (h->half_pipe) {
             CU(h, h->a_qkv.ensure(2 * cr * 3 * E * 2)); CU(h, h->a_qc.ensure(2 * cr * E * 2));
-            CU(h, h->kc_h.ensure(2 * (size_t)R * h->Ld * E * 2)); CU(h, h->vc_h.ensure(2 * (size_t)R * h->Ld * E * 2));
+            CU(h, h->kc_h.ensure(2 * Rc * h->Ld * E * 2)); CU(h, h->vc_h.ensure(2 * Rc * h->Ld * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_qkv, h->a_qkv.p, 3 * E, cr));
             FFB_TRY(encode_split_store_map(h, &h->ms_qc, h->a_qc.p, E, cr));
             h->cap_b = (long long)rows_b;
             CU(h, h->a_ql.ensure(2 * rows_b * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_ql, h->a_ql.p, E, rows_b));
             h->m_last.resize(h->T);
-            for (int P = 1; P < h->T; ++P)
+            for (int P = 1; P < h->T && !h->encode_only; ++P)
                 FFB_TRY(encode_operand_map_strided(h, &h->m_last[P], h->a_x2p.as<uint16_t>(), E, (uint64_t)h->B, (uint64_t)P, (uint64_t)(P - 1),
                                                    (uint64_t)h->cap_rows, tc::BM));
             h->attn_x_ok = (h->max_vlen <= ax::KMAX && N <= ax::MAX_GROUPS);
-            if (h->attn_x_ok) {
+            if (h->attn_x_ok && !h->encode_only) {
                 const size_t LdE = (size_t)h->Ld * E;
                 FFB_TRY(encode_operand_map(h, &h->mx_q, h->a_qc.p, E, cr, ax::BQ, 2));
                 FFB_TRY(encode_operand_map(h, &h->mx_k, h->kc_h.p, LdE, (uint64_t)R, ax::KC, 2));
                 FFB_TRY(encode_rows_map(h, &h->mx_vrow, h->vc_h.p, LdE, (uint64_t)R, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
             }
-            FFB_TRY(encode_output_map(h, &h->mc_kc, h->Kc.p, (uint64_t)h->Ld * E, (uint64_t)R));
-            FFB_TRY(encode_output_map(h, &h->mc_vc, h->Vc.p, (uint64_t)h->Ld * E, (uint64_t)R));
+            FFB_TRY(encode_output_map(h, &h->mc_kc, h->Kc.p, (uint64_t)h->Ld * E, (uint64_t)Rc));
+            FFB_TRY(encode_output_map(h, &h->mc_vc, h->Vc.p, (uint64_t)h->Ld * E, (uint64_t)Rc));
             FFB_TRY(encode_rows_map(h, &h->msf_q, h->a_qkv.p, 3 * E, cr, 32, ax::BQ, CU_TENSOR_MAP_SWIZZLE_64B));
             FFB_TRY(encode_rows_map(h, &h->msf_k, h->a_qkv.p, 3 * E, cr, 32, ax::KC, CU_TENSOR_MAP_SWIZZLE_64B));
             FFB_TRY(encode_rows_map(h, &h->msf_v, h->a_qkv.p, 3 * E, cr, 64, ax::KC, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -806,6 +848,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
 // Cross-attention K / V of every decoder layer, once per wireframe: k = W_k (memory + pos), v = W_v memory
 // (transformer.py:248-251; torch functional.py:5866-5873).  use_tc: fp16x2 tcgen05 GEMMs (the tensor-core encoder), else fp32 SIMT.
 int run_cross_cache(ffb_handle* h, cudaStream_t s, bool use_tc) {
+    if (h->encode_only) return FFB_OK;
     const int E = h->E, R = (int)h->R, LdE = h->Ld * E;
     const Weights& w = h->w;
     float* mem = h->mem.as<float>();
@@ -830,13 +873,100 @@ int run_cross_cache(ffb_handle* h, cudaStream_t s, bool use_tc) {
 
 // fp16x2 copy of the cache for the half pipeline's cross-attention (overflow -> state[5], checked after the decode)
 int run_cross_cache_split(ffb_handle* h, cudaStream_t s) {
-    if (!h->half_pipe) return FFB_OK;
+    if (!h->half_pipe || h->encode_only) return FFB_OK;
     const long long n4 = (long long)h->R * h->Ld * h->E / 4;
     CU(h, cudaMemsetAsync(h->state.as<int>() + 5, 0, sizeof(int), s));
     split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Kc.as<float>(), h->kc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
     split_array_kernel<<<grid1d(n4), 256, 0, s>>>(h->Vc.as<float>(), h->vc_h.as<uint16_t>(), n4, 1.0f, 2, h->state.as<int>() + 5);
     h->launches += 2; CU(h, cudaGetLastError());
     return FFB_OK;
+}
+
+// ---- float64 encoder / head (enc64.cuh) -------------------------------------------------------------------
+int launch_dgemm(ffb_handle* h, e64::GemmArgs a, const int* stop, cudaStream_t s) {
+    if (a.M <= 0) return FFB_OK;
+    a.stop = stop;
+    dim3 grid((a.M + e64::GBM - 1) / e64::GBM, (a.N + e64::GBN - 1) / e64::GBN);
+    prof_begin(h, PC_LINEAR, 2.0 * a.M * (double)a.N * a.K, s);
+    e64::dgemm_kernel<<<grid, 256, 0, s>>>(a);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+int launch_ln64(ffb_handle* h, const double* x64, const float* x32, int in_mul, int in_off, const float* g, const float* b, double* y, double* yp,
+                float* y32, const float* pos, const int* pos_idx, int pos_mod, int M, const int* stop, cudaStream_t s) {
+    if (M <= 0) return FFB_OK;
+    prof_begin(h, PC_LAYERNORM, 8.0 * M * (double)h->E, s);
+    e64::layernorm64_kernel<<<(M + 7) / 8, 256, 0, s>>>(x64, x32, in_mul, in_off, g, b, y, yp, y32, pos, pos_idx, pos_mod, M, h->E, stop);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
+// Folded pointer head: logits = memory . (W_p y + b_p) = (memory . [W_p^T ; b_p]^T) . [y ; 1]  (model_para.py:225 + 173-177).  The
+// left factor depends on the wireframe only: one float64 GEMM per batch (from the float64 memory when the float64 encoder ran),
+// rounded to fp32 [R, E + 4] (column E = memory . b_p).  The per-step head is then LayerNorm + one dot product per (row, sequence).
+int run_head_fold(ffb_handle* h, cudaStream_t s, bool mem_is_64) {
+    if (!h->opt_head64 || h->encode_only) return FFB_OK;
+    e64::GemmArgs a{};
+    if (mem_is_64) { a.A = h->y64.as<double>(); a.a_f32 = 0; } else { a.A = h->mem.as<float>(); a.a_f32 = 1; }
+    a.lda = h->E; a.W = h->projT.as<float>(); a.ldw = h->E; a.C32 = h->memW.as<float>(); a.ldc32 = h->E + 4;
+    a.M = (int)h->R; a.N = h->E + 1; a.K = h->E;
+    return launch_dgemm(h, a, nullptr, s);
+}
+
+constexpr int ENC64_MAX_VLEN = 320;      // attn64_kernel keeps one row of scores per warp in (default-sized) shared memory: 8 * (320 + 64) * 8 B + the K/V tile < 48 KB
+
+// The whole encoder and the cross-attention K / V cache in float64 (embedding.py:23-38; transformer.py:70-83,164-176,248-251).
+int run_encoder64(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
+    const int E = h->E, FF = h->FF, R = (int)h->R, Re = (int)h->Re, N = h->N, LdE = h->Ld * E;
+    const Weights& w = h->w;
+    const size_t d8 = sizeof(double);
+    CU(h, h->x64.ensure((size_t)R * E * d8)); CU(h, h->y64.ensure((size_t)R * E * d8)); CU(h, h->yp64.ensure((size_t)R * E * d8));
+    CU(h, h->qkv64.ensure((size_t)R * 3 * E * d8)); CU(h, h->att64.ensure((size_t)R * E * d8));
+    CU(h, h->h64.ensure((size_t)std::max(R, Re) * std::max(FF, E) * d8));
+    double* x = h->x64.as<double>(); double* y = h->y64.as<double>(); double* yp = h->yp64.as<double>();
+    double* qkv = h->qkv64.as<double>(); double* att = h->att64.as<double>(); double* hb = h->h64.as<double>();
+    const int* row_off = h->d_row_off.as<int>(); const int* vlen = h->d_vlen.as<int>(); const int* pos_idx = h->d_pos_idx.as<int>();
+    // value embedding on the valid edges, token rows
+    { e64::GemmArgs a{}; a.A = coords_dev; a.lda = h->cfg.in_dim; a.a_f32 = 1; a.a_rows = h->d_edge_src.as<int>(); a.W = w.e0w; a.ldw = h->cfg.in_dim;
+      a.bias = w.e0b; a.C = hb; a.ldc = E; a.M = Re; a.N = E; a.K = h->cfg.in_dim; a.relu = 1; FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    { e64::GemmArgs a{}; a.A = hb; a.lda = E; a.W = w.e2w; a.ldw = E; a.bias = w.e2b; a.C = x; a.ldc = E; a.c_rows = h->d_edge_dst.as<int>();
+      a.M = Re; a.N = E; a.K = E; FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    e64::token_rows64_kernel<<<grid1d((long long)N * h->cfg.num_token * E), 256, 0, s>>>(w.tok_table, row_off, x, N, h->cfg.num_token, E);
+    h->launches++; CU(h, cudaGetLastError());
+    const size_t a_smem = e64::A64_ROWS * (size_t)(h->max_vlen + 64) * d8;
+    for (int li = 0; li < h->Le; ++li) {                                  // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
+        const EncLayerW& L = w.enc[li];
+        FFB_TRY(launch_ln64(h, x, nullptr, 1, 0, L.n1w, L.n1b, y, yp, nullptr, w.pos, pos_idx, 1, R, nullptr, s));     // q = k = LN(x) + pos, v = LN(x)
+        { e64::GemmArgs a{}; a.A = yp; a.lda = E; a.W = L.sa.in_w; a.ldw = E; a.bias = L.sa.in_b; a.C = qkv; a.ldc = 3 * E; a.M = R; a.N = 2 * E; a.K = E;
+          FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+        { e64::GemmArgs a{}; a.A = y; a.lda = E; a.W = L.sa.in_w + (size_t)2 * E * E; a.ldw = E; a.bias = L.sa.in_b + 2 * E; a.C = qkv + 2 * E; a.ldc = 3 * E;
+          a.M = R; a.N = E; a.K = E; FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+        prof_begin(h, PC_ATTN_TILED, 4.0 * 64 * h->H * h->sum_vlen2, s);
+        e64::attn64_kernel<<<dim3((h->max_vlen + e64::A64_ROWS - 1) / e64::A64_ROWS, h->H, N), 32 * e64::A64_ROWS, a_smem, s>>>(qkv, att, row_off, vlen, E, h->max_vlen);
+        prof_end(h, s);
+        h->launches++; CU(h, cudaGetLastError());
+        { e64::GemmArgs a{}; a.A = att; a.lda = E; a.W = L.sa.out_w; a.ldw = E; a.bias = L.sa.out_b; a.C = x; a.ldc = E; a.R = x; a.ldr = E;
+          a.M = R; a.N = E; a.K = E; FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+        FFB_TRY(launch_ln64(h, x, nullptr, 1, 0, L.n2w, L.n2b, y, nullptr, nullptr, nullptr, nullptr, 1, R, nullptr, s));
+        { e64::GemmArgs a{}; a.A = y; a.lda = E; a.W = L.l1w; a.ldw = E; a.bias = L.l1b; a.C = hb; a.ldc = FF; a.M = R; a.N = FF; a.K = E; a.relu = 1;
+          FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+        { e64::GemmArgs a{}; a.A = hb; a.lda = FF; a.W = L.l2w; a.ldw = FF; a.bias = L.l2b; a.C = x; a.ldc = E; a.R = x; a.ldr = E;
+          a.M = R; a.N = E; a.K = FF; FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    }
+    // encoder.norm (transformer.py:80-81): memory in float64 (y), memory + pos (yp) and its fp32 rounding (what the decode gathers and scores)
+    FFB_TRY(launch_ln64(h, x, nullptr, 1, 0, w.enc_nw, w.enc_nb, y, yp, h->mem.as<float>(), w.pos, pos_idx, 1, R, nullptr, s));
+    // cross-attention K / V of every decoder layer from the float64 memory, rounded to fp32 once
+    { e64::GemmArgs a{}; a.A = yp; a.lda = E; a.W = w.ckw; a.ldw = E; a.bias = w.ckb; a.C32 = h->Kc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
+      FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    { e64::GemmArgs a{}; a.A = y; a.lda = E; a.W = w.cvw; a.ldw = E; a.bias = w.cvb; a.C32 = h->Vc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
+      FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    FFB_TRY(run_head_fold(h, s, true));
+    return run_cross_cache_split(h, s);
 }
 
 int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool allow_tc) {
@@ -920,6 +1050,7 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
     FFB_TRY(launch_ln(h, x, w.enc_nw, w.enc_nb, mem, R, E, nullptr, s));   // encoder.norm (transformer.py:80-81)
     FFB_TRY(run_cross_cache(h, s, false));
     }
+    FFB_TRY(run_head_fold(h, s, false));
     return run_cross_cache_split(h, s);
 }
 
@@ -939,13 +1070,13 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
 
     prof_begin(h, PC_OTHER, 0.0, s);
     launch_k(h, gather_tgt_kernel, dim3(grid1d((long long)M * (E / 4))), dim3(256), 0, s, (const float*)h->mem.as<float>(), row_off,
-             (const int*)h->d_seq_wf.as<int>(), (const int*)h->tok.as<int>(), x, B, P, E, stop);
+             (const int*)h->d_seq_wf.as<int>(), (const int*)tok_cur(h), x, B, P, E, stop);
     prof_end(h, s);
     h->launches++; CU(h, cudaGetLastError());
 
     float* cur = x; int rows = M; int Pq = P;            // rows carried through the rest of the layer
     const ffb_handle::TcSet& TS = h->tcs[h->tc_fmt - 2];
-    const bool tc = h->tc_ok && h->opt_tc && TS.ready && (int)TS.layers.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS);
+    const bool tc = h->tc_ok && h->opt_tc && TS.ready && (int)TS.layers.size() == Ld && (h->opt_tc == 2 || M >= TC_MIN_ROWS_DECODE);
     uint16_t* ax2 = h->a_x2.as<uint16_t>(); uint16_t* ax2p = h->a_x2p.as<uint16_t>();
     uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>();
     uint16_t* aqkv = h->a_qkv.as<uint16_t>(); uint16_t* aqc = h->a_qc.as<uint16_t>();
@@ -1004,7 +1135,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                   l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = M; l.N = 2 * E; l.K = E;
                   l.Cs = aqkv; l.cs_stride = h->cap_rows * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv;
                   FFB_TRY(launch_tc(h, l, stop, s)); }
-                { TcLin l; l.A0 = &h->m_last[P];                      // encoded once per batch (plan_batch) l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = B; l.N = E; l.K = E;
+                { TcLin l; l.A0 = &h->m_last[P]; /* encoded once per batch (plan_batch) */ l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b; l.M = B; l.N = E; l.K = E;
                   l.Cs = h->a_ql.as<uint16_t>(); l.cs_stride = h->cap_b * E; l.ldcs = E; l.Cmap = &h->ms_ql;
                   FFB_TRY(launch_tc(h, l, stop, s)); }
             } else
@@ -1074,7 +1205,11 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
         }
     }
     // decoder.norm (transformer.py:115-116) + project (model_para.py:225) + select_next (model_para.py:173-179)
-    if (!tc) {
+    const bool head64 = h->opt_head64 != 0;
+    if (head64)        // last position of every sequence: LayerNorm in float64 (rounded to fp32); project is folded into memW (run_head_fold)
+        FFB_TRY(launch_ln64(h, nullptr, cur, Pq, Pq - 1, w.dec_nw, w.dec_nb, nullptr, nullptr, h->hy32.as<float>(), nullptr, nullptr, 1, B, stop, s));
+    if (head64 && h->opt_prune) {
+    } else if (!tc) {
         FFB_TRY(launch_ln(h, cur, w.dec_nw, w.dec_nb, x2, rows, E, stop, s));
         { Lin l; l.A = x2; l.lda = E; l.W = w.proj_w; l.ldw = E; l.bias = w.proj_b; l.C = att; l.ldc = E; l.M = rows; l.N = E; l.K = E;
           FFB_TRY(launch_linear(h, l, stop, s)); }
@@ -1085,21 +1220,39 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     }
     PointerArgs pa{};
     pa.mem = h->mem.as<float>(); pa.ptr = att; pa.ptr_stride_rows = Pq; pa.ptr_off = Pq - 1;
+    pa.ldm = E; pa.bias_col = 0;
+    if (head64) { pa.mem = h->memW.as<float>(); pa.ldm = E + 4; pa.bias_col = E; pa.ptr = h->hy32.as<float>(); pa.ptr_stride_rows = 1; pa.ptr_off = 0; }
     pa.row_off = row_off; pa.v_len = vlen; pa.seq_wf = h->d_seq_wf.as<int>();
     pa.logits = h->logits.as<float>(); pa.L = h->L;
-    pa.tok_out = append ? h->tok.as<int>() + (size_t)P * B : nullptr;
+    const bool beam = append && h->W > 1;
+    pa.tok_out = (append && !beam) ? tok_cur(h) + (size_t)P * B : nullptr;
     pa.B = B; pa.E = E; pa.num_token = h->cfg.num_token;
-    pa.nonstop_count = (h->cfg.mode == FFB_MODE_PARALLEL) ? st + 2 : nullptr;
+    pa.nonstop_count = (h->cfg.mode == FFB_MODE_PARALLEL && !beam) ? st + 2 : nullptr;
     pa.eos_count = (h->cfg.mode == FFB_MODE_SEQ2SEQ) ? st + 3 : nullptr;
     pa.stop = stop;
     prof_begin(h, PC_POINTER, 2.0 * E * h->sum_seq_vlen, s);
-    if (h->opt_pointer_batched && h->E % 128 == 0 && h->E <= 1024)   // the sequences of a wireframe share its memory rows: stream them once per 16 sequences
-        launch_k(h, pointer_batched_kernel, dim3((h->max_seq_per_wf + PB_SEQ - 1) / PB_SEQ, N), dim3(256), (size_t)PB_SEQ * E * sizeof(float), s, pa, seq_off);
-    else
-        launch_k(h, pointer_kernel, dim3(B), dim3(256), 0, s, pa);
+    const dim3 pb_grid((h->max_seq_per_wf + PB_SEQ - 1) / PB_SEQ, N);
+    if (h->opt_pointer_batched && h->E % 128 == 0 && h->E <= 1024) {  // the sequences of a wireframe share its memory rows: stream them once per PB_SEQ sequences
+        if (head64) launch_k(h, pointer_batched_kernel<true>, pb_grid, dim3(256), (size_t)PB_SEQ * E * sizeof(float), s, pa, seq_off);
+        else launch_k(h, pointer_batched_kernel<false>, pb_grid, dim3(256), (size_t)PB_SEQ * E * sizeof(float), s, pa, seq_off);
+    } else if (head64) launch_k(h, pointer_kernel<true>, dim3(B), dim3(256), 0, s, pa);
+    else launch_k(h, pointer_kernel<false>, dim3(B), dim3(256), 0, s, pa);
     prof_end(h, s);
     h->launches++; CU(h, cudaGetLastError());
-    if (append) {
+    if (beam) {      // select the W best continuations per anchor, re-order the token histories into the other buffer
+        int* tok_new = h->tok.as<int>() + (size_t)(h->tok_sel ^ 1) * h->T * B;
+        launch_k(h, beam_step_kernel, dim3(B / h->W), dim3(32 * h->W), 0, s, (const float*)h->logits.as<float>(), h->L, (const int*)h->d_seq_wf.as<int>(),
+                 vlen, h->beam_cum.as<double>(), (const int*)tok_cur(h), tok_new, P, h->T, B, h->W, h->cfg.num_token, st + 2, stop);
+        h->launches++; CU(h, cudaGetLastError());
+        h->tok_sel ^= 1;
+    }
+    if (append && h->xchg_on) {
+        XchgArgs xa{};
+        for (int r = 0; r < h->xchg_world; ++r) xa.peers[r] = h->xchg_peers[r];
+        xa.rank = h->xchg_rank; xa.world = h->xchg_world; xa.T = h->T;
+        launch_k(h, step_end_xchg_kernel, dim3(1), dim3(32), 0, s, st + 2, st, st + 1, xa, P - 1, h->xchg_epoch, st + 7);
+        h->launches++; CU(h, cudaGetLastError());
+    } else if (append) {
         launch_k(h, step_end_kernel, dim3(1), dim3(1), 0, s, h->cfg.mode, B, st + 2, st + 3, st, st + 1);
         h->launches++; CU(h, cudaGetLastError());
     }
@@ -1151,7 +1304,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc2::gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(pointer_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SEQ * 1024 * (int)sizeof(float));
+    e = cudaFuncSetAttribute(pointer_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SEQ * 1024 * (int)sizeof(float));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pointer_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SEQ * 1024 * (int)sizeof(float));
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(pointer_batched_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(ax::attn_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ax::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_x_kernel): %s", cudaGetErrorString(e));
@@ -1184,11 +1338,13 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
     if (h->h_stop) cudaFreeHost((void*)h->h_stop);
+    ffb_stop_exchange_disconnect(h);
+    if (h->xchg_buf) cudaFree(h->xchg_buf);
     delete h;
     return FFB_OK;
 }
@@ -1198,6 +1354,18 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
     switch (option) {
         case FFB_OPT_DEDUP_PAD: h->opt_dedup = value ? 1 : 0; h->encoded = false; return FFB_OK;
         case FFB_OPT_PRUNE_LAST: h->opt_prune = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_ENCODER_PRECISION:
+            if (value != 0 && value != 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ENCODER_PRECISION: 0 = fp16x2 tcgen05 / fp32, 2 = float64");
+            h->opt_enc_prec = value; h->encoded = false; return FFB_OK;
+        case FFB_OPT_HEAD_FP64: h->opt_head64 = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_ENCODE_ONLY: h->opt_encode_only = value ? 1 : 0; h->encoded = false; return FFB_OK;
+        case FFB_OPT_FORCE_F:
+            if (value < 0 || value > h->cfg.num_lines) return fail(h, FFB_ERR_ARG, "FFB_OPT_FORCE_F must be in [0, num_lines]");
+            h->opt_force_F = value; h->encoded = false; return FFB_OK;
+        case FFB_OPT_BEAM:
+            if (value < 1 || value > BEAM_MAX) return fail(h, FFB_ERR_ARG, "FFB_OPT_BEAM: beam width must be in [1, %d]", BEAM_MAX);
+            if (value > 1 && h->cfg.mode != FFB_MODE_PARALLEL) return fail(h, FFB_ERR_UNSUPPORTED, "beam search is specified for the parallel model only");
+            h->opt_beam = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_TIMING: h->opt_timing = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; h->prof_recs.clear(); return FFB_OK;
         case FFB_OPT_TC_FORMAT:
@@ -1212,7 +1380,9 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             h->opt_attn_mma = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_ATTN_X: h->opt_attn_x = value & 3; return FFB_OK;
         case FFB_OPT_ENCODER_TC: h->opt_enc_tc = value ? 1 : 0; return FFB_OK;
-        case FFB_OPT_PDL: h->opt_pdl = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_PDL:
+            if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_PDL: 0 off, 1 on, 2 auto");
+            h->opt_pdl = value; h->pdl_on = (value == 1); return FFB_OK;
         case FFB_OPT_POINTER_BATCHED: h->opt_pointer_batched = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_GEMM_VARIANT: if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_GEMM_VARIANT: 0, 1, 2 (auto) or 3 (CTA pairs)"); h->opt_gemm_variant = value; return FFB_OK;
         case FFB_OPT_TENSOR_CORE:
@@ -1245,6 +1415,10 @@ int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, vo
         CU(h, cudaMemcpyAsync(cvb + l * E, ca.in_b + 2 * E, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     h->w.ckw = ckw; h->w.cvw = cvw; h->w.ckb = ckb; h->w.cvb = cvb;
+    CU(h, h->projT.ensure((E + 1) * E * sizeof(float)));            // rows 0..E-1 = W_project^T, row E = b_project (folded head)
+    transpose_kernel<<<grid1d((long long)(E * E)), 256, 0, s>>>(h->w.proj_w, h->projT.as<float>(), (int)E, (int)E);
+    h->launches++; CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->projT.as<float>() + E * E, h->w.proj_b, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
     for (auto& T : h->tcs) T.ready = false;                 // split weights are rebuilt lazily per operand format
     if (h->tc_ok && h->opt_tc) FFB_TRY(prepare_tc(h, h->tc_fmt, s));
     CU(h, cudaStreamSynchronize(s));
@@ -1285,7 +1459,9 @@ int ffb_encode(ffb_handle* h, const float* coords, const uint8_t* pad_mask, cons
         coords_dev = h->d_coords.as<float>();
     }
     h->attn_allow_f16 = false;
-    int enc_rc = run_encoder(h, coords_dev, s, true);
+    h->enc_used_64 = (h->opt_enc_prec == 2 && h->max_vlen <= ENC64_MAX_VLEN);
+    int enc_rc = h->enc_used_64 ? run_encoder64(h, coords_dev, s) : run_encoder(h, coords_dev, s, true);
+    if (h->enc_used_64) h->enc_used_tc = false;
     if (enc_rc == FFB_OK && h->enc_used_tc) {          // an activation left the fp16 range in the tensor-core encoder: redo it in fp32
         int ovf = 0;
         cudaError_t ce = cudaMemcpyAsync(&ovf, h->state.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -1313,6 +1489,7 @@ int ffb_batch_info(const ffb_handle* h, int32_t* N, int32_t* F, int64_t* B, int6
 int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_run, void* stream) {
     if (!h) return FFB_ERR_ARG;
     if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_decode_greedy before ffb_encode");
+    if (h->encode_only) return fail(h, FFB_ERR_STATE, "the batch was encoded with FFB_OPT_ENCODE_ONLY: no decode workspaces exist");
     if (!predict) return fail(h, FFB_ERR_ARG, "predict is NULL");
     FFB_TRY(set_device(h));
     cudaStream_t s = (cudaStream_t)stream;
@@ -1326,10 +1503,20 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         out_dev = h->d_predict.as<long long>();
     }
     const bool syncing = (steps_run != nullptr) || (loc == FFB_HOST);
+    if (h->xchg_on) {
+        if (h->cfg.mode != FFB_MODE_PARALLEL) return fail(h, FFB_ERR_UNSUPPORTED, "batch splitting is implemented for the parallel model");
+        h->xchg_epoch++;                           // every rank decodes the same number of times: epochs stay aligned
+        CU(h, cudaMemsetAsync(st + 7, 0, sizeof(int), s));
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         CU(h, cudaMemsetAsync(st, 0, 5 * sizeof(int), s));          // [5] = overflow seen while encoding: survives
+        h->tok_sel = 0;
         init_tokens_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->d_seq_first.as<int>(), h->tok.as<int>(), B, st, st + 1, st + 3);
         h->launches++; CU(h, cudaGetLastError());
+        if (h->W > 1) {
+            beam_init_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->beam_cum.as<double>(), B, h->W);
+            h->launches++; CU(h, cudaGetLastError());
+        }
         // No host sync inside the loop.  The stop flag is mirrored into pinned host memory after every step; once a copy that has
         // already landed shows it set, the remaining steps (whose kernels would all exit at once) are not launched at all.
         if (h->h_stop_cap < T) {
@@ -1349,7 +1536,7 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
             CU(h, cudaMemcpyAsync((void*)(h->h_stop + step), st, sizeof(int), cudaMemcpyDeviceToHost, s));
             h->steps_launched = step + 1;
         }
-        expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(h->tok.as<int>(), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
+        expand_predict_kernel<<<grid1d(n_slots * T), 256, 0, s>>>(tok_cur(h), h->d_slot_seq.as<int>(), st + 1, out_dev, n_slots, B, T);
         h->launches++; CU(h, cudaGetLastError());
         if (!syncing) break;                      // fully asynchronous call: the caller must check ffb_overflowed() after its own sync
         int host_state[3] = {0, 0, 0};            // executed steps, fp16 overflow flag (decode), fp16 overflow flag (K/V cache split)
@@ -1357,7 +1544,14 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         CU(h, cudaMemcpyAsync(&host_state[1], st + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         if (steps_run) *steps_run = host_state[0];
+        if (h->xchg_on) {
+            int xerr = 0;
+            CU(h, cudaMemcpy(&xerr, st + 7, sizeof(int), cudaMemcpyDeviceToHost));
+            if (xerr) return fail(h, FFB_ERR_CUDA, "stop-predicate exchange timed out: a peer rank did not reach decode step %d", host_state[0]);
+        }
         if ((host_state[1] == 0 && !(h->half_pipe && host_state[2])) || h->tc_fmt != 2) break;
+        if (h->xchg_on)      // a private re-run would desynchronise the ranks' step barriers
+            return fail(h, FFB_ERR_UNSUPPORTED, "fp16 range overflow while decoding a split batch: set FFB_OPT_TC_FORMAT = 3 on every rank and run the batch again");
         // an activation left the fp16 range: switch this handle to the bf16x3 operand format (sticky) and decode again
         h->tc_fmt = 3; h->fp16_fallbacks++;
         FFB_TRY(prepare_tc(h, 3, s));
@@ -1528,6 +1722,7 @@ int ffb_set_memory(ffb_handle* h, const float* memory, int loc, void* stream) {
                                                                          h->N, h->L, h->E);
     h->launches++; CU(h, cudaGetLastError());
     FFB_TRY(run_cross_cache(h, s, false));
+    FFB_TRY(run_head_fold(h, s, false));
     FFB_TRY(run_cross_cache_split(h, s));
     h->decoded = false;
     return FFB_OK;
@@ -1570,9 +1765,12 @@ int ffb_get_last_pointer(ffb_handle* h, float* pointer, int32_t* P_out, int loc,
 int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, float* logits, int loc, void* stream) {
     if (!h) return FFB_ERR_ARG;
     if (!h->encoded) return fail(h, FFB_ERR_STATE, "ffb_forced_prefix_logits before ffb_encode");
+    if (h->encode_only) return fail(h, FFB_ERR_STATE, "the batch was encoded with FFB_OPT_ENCODE_ONLY");
     if (!prefix || !logits) return fail(h, FFB_ERR_ARG, "prefix / logits is NULL");
     if (P < 1 || P > h->T - 1) return fail(h, FFB_ERR_ARG, "P must be in [1, T-1]");
+    if (h->W > 1) return fail(h, FFB_ERR_STATE, "forced prefixes need FFB_OPT_BEAM = 1");
     if (h->B != h->B_full) return fail(h, FFB_ERR_STATE, "forced prefixes need FFB_OPT_DEDUP_PAD = 0 before ffb_encode");
+    h->tok_sel = 0;
     FFB_TRY(set_device(h));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t pbytes = (size_t)P * h->B_full * sizeof(int64_t);
@@ -1610,6 +1808,81 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
     }
     h->decoded = false;
     return emit_logits(h, logits, loc, s);
+}
+
+int ffb_stop_exchange_export(ffb_handle* h, void* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return FFB_ERR_ARG;
+    FFB_TRY(set_device(h));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!h->xchg_buf) {
+        const size_t bytes = 2 * (size_t)h->T * XCHG_MAXW * sizeof(int);
+        CU(h, cudaMalloc(&h->xchg_buf, bytes));
+        CU(h, cudaMemset(h->xchg_buf, 0, bytes));
+    }
+    cudaIpcMemHandle_t hd;
+    CU(h, cudaIpcGetMemHandle(&hd, h->xchg_buf));
+    memcpy(ipc_handle_out, &hd, sizeof hd);
+    return FFB_OK;
+}
+
+int ffb_stop_exchange_connect(ffb_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
+    if (!h || !ipc_handles) return FFB_ERR_ARG;
+    if (world < 1 || world > XCHG_MAXW || rank < 0 || rank >= world) return fail(h, FFB_ERR_ARG, "stop exchange: need 0 <= rank < world <= %d", XCHG_MAXW);
+    if (!h->xchg_buf) return fail(h, FFB_ERR_STATE, "ffb_stop_exchange_connect before ffb_stop_exchange_export");
+    if (h->xchg_on) return fail(h, FFB_ERR_STATE, "stop exchange is already connected");
+    FFB_TRY(set_device(h));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->xchg_peers[r] = h->xchg_buf; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, reinterpret_cast<const uint8_t*>(ipc_handles) + (size_t)r * sizeof hd, sizeof hd);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != rank && h->xchg_peers[q]) { cudaIpcCloseMemHandle(h->xchg_peers[q]); h->xchg_peers[q] = nullptr; }
+            return fail(h, FFB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        h->xchg_peers[r] = static_cast<int*>(p);
+    }
+    h->xchg_rank = rank; h->xchg_world = world; h->xchg_epoch = 0; h->xchg_on = true;
+    return FFB_OK;
+}
+
+int ffb_stop_exchange_disconnect(ffb_handle* h) {
+    if (!h) return FFB_ERR_ARG;
+    if (h->xchg_on) {
+        cudaSetDevice(h->cfg.device);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < h->xchg_world; ++r)
+            if (r != h->xchg_rank && h->xchg_peers[r]) cudaIpcCloseMemHandle(h->xchg_peers[r]);
+        for (auto& p : h->xchg_peers) p = nullptr;
+        h->xchg_on = false;
+    }
+    return FFB_OK;
+}
+
+int ffb_get_beams(ffb_handle* h, int64_t* beams, double* scores, int loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (!h->decoded) return fail(h, FFB_ERR_STATE, "ffb_get_beams before a decode");
+    if (!beams || !scores) return fail(h, FFB_ERR_ARG, "beams / scores is NULL");
+    if (h->W < 2) return fail(h, FFB_ERR_STATE, "ffb_get_beams needs FFB_OPT_BEAM > 1");
+    FFB_TRY(set_device(h));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n_slots = h->B_full;
+    const size_t nb = (size_t)n_slots * h->W * h->T * sizeof(long long), ns = (size_t)n_slots * h->W * sizeof(double);
+    long long* bd = reinterpret_cast<long long*>(beams); double* sd = scores;
+    if (loc == FFB_HOST) {
+        CU(h, h->d_out_stage.ensure(nb + ns));
+        bd = h->d_out_stage.as<long long>(); sd = reinterpret_cast<double*>(h->d_out_stage.as<uint8_t>() + nb);
+    }
+    expand_beams_kernel<<<grid1d(n_slots * h->W * h->T), 256, 0, s>>>(tok_cur(h), h->beam_cum.as<double>(), h->d_slot_seq.as<int>(), h->state.as<int>() + 1,
+                                                                     bd, sd, n_slots, (int)h->B, h->W, h->T);
+    h->launches++; CU(h, cudaGetLastError());
+    if (loc == FFB_HOST) {
+        CU(h, cudaMemcpyAsync(beams, bd, nb, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(scores, sd, ns, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+    }
+    return FFB_OK;
 }
 
 int ffb_overflowed(ffb_handle* h, int32_t* overflowed, void* stream) {

@@ -849,6 +849,8 @@ __global__ void init_tokens_kernel(const int* __restrict__ seq_first, int* __res
 struct PointerArgs {
     const float* mem;            // packed memory [R,E]
     const float* ptr; int ptr_stride_rows; int ptr_off;   // pointer row of sequence b: ptr[(b*stride + off) * E]
+    int ldm;                     // row stride of `mem` in floats (E, or E + 4 for the folded head)
+    int bias_col;                // HD instantiations: logit += mem[row][bias_col] (the folded project bias), cross-lane reduction in float64
     const int* row_off; const int* v_len; const int* seq_wf;
     float* logits; int L;        // [B, L] masked logits (finfo.min beyond v_len), or null
     int* tok_out;                // tok[(P)*B + b] slot for the new token, or null (forced-prefix mode)
@@ -859,6 +861,16 @@ struct PointerArgs {
     const int* stop;
 };
 
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// HD ("folded head"): mem = memory . [W_project^T ; b_project] precomputed per wireframe in float64 (rounded to fp32),
+// ptr = the float64 LayerNorm of the last position (rounded to fp32): logit = <mem[row, :E], ptr> + mem[row, E].  The 16-term per-lane
+// chains stay fp32 FMAs on small partial sums; the cross-lane reduction runs in float64.
+template <bool HD>
 __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
     FFB_PDL_SYNC();
     FFB_STOP_CHECK(a.stop);
@@ -873,14 +885,14 @@ __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
     const int r0 = a.row_off[wf], vl = a.v_len[wf];
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int j = w; j < vl; j += 8) {
-        const float* mr = a.mem + (size_t)(r0 + j) * a.E;
-        float s = 0.f;
+        const float* mr = a.mem + (size_t)(r0 + j) * a.ldm;
+        float sd = 0.f;
         for (int c = lane * 4; c < a.E; c += 128) {
             const float4 mv = *reinterpret_cast<const float4*>(mr + c);
             const float4 pv = *reinterpret_cast<const float4*>(&ps[c]);
-            s = fmaf(mv.x, pv.x, s); s = fmaf(mv.y, pv.y, s); s = fmaf(mv.z, pv.z, s); s = fmaf(mv.w, pv.w, s);
+            sd = fmaf(mv.x, pv.x, sd); sd = fmaf(mv.y, pv.y, sd); sd = fmaf(mv.z, pv.z, sd); sd = fmaf(mv.w, pv.w, sd);
         }
-        s = warp_sum(s);
+        const float s = HD ? (float)(warp_sum((double)sd) + (double)mr[a.bias_col]) : warp_sum(sd);
         if (a.logits && lane == 0) a.logits[(size_t)b * a.L + j] = s;
         // strictly greater: first max within this warp's rows; like torch.argmax a NaN counts as the maximum (first NaN wins)
         if (bi == 0x7fffffff || s > bv || (s != s && bv == bv)) { bv = s; bi = j; }
@@ -911,6 +923,7 @@ __global__ void __launch_bounds__(256) pointer_kernel(const PointerArgs a) {
 // (row, sequence) the dot product is evaluated in exactly the order of pointer_kernel (per-lane fmaf chain, then warp_sum), so logits and
 // tokens are bit-identical to it.  grid (ceil(max sequences per wireframe / PB_SEQ), N), 256 threads, dynamic smem PB_SEQ * E floats.
 constexpr int PB_SEQ = 4;
+template <bool HD>
 __global__ void __launch_bounds__(256) pointer_batched_kernel(const PointerArgs a, const int* __restrict__ seq_off) {
     FFB_PDL_SYNC();
     FFB_STOP_CHECK(a.stop);
@@ -931,7 +944,7 @@ __global__ void __launch_bounds__(256) pointer_batched_kernel(const PointerArgs 
     const int nv = a.E >> 7;                                 // float4 chunks per lane (E multiple of 128, <= 1024)
     float bv = -INFINITY; int bi = 0x7fffffff;               // lane q < nq tracks the running best of sequence q over this warp's rows
     for (int j = w; j < vl; j += 8) {
-        const float* mr = a.mem + (size_t)(r0 + j) * a.E;
+        const float* mr = a.mem + (size_t)(r0 + j) * a.ldm;
         float4 mv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) if (i < nv) mv[i] = *reinterpret_cast<const float4*>(mr + lane * 4 + i * 128);
@@ -951,8 +964,9 @@ __global__ void __launch_bounds__(256) pointer_batched_kernel(const PointerArgs 
                 }
             }
         }
+        const float mbias = HD ? mr[a.bias_col] : 0.f;
 #pragma unroll
-        for (int q = 0; q < PB_SEQ; ++q) sacc[q] = warp_sum(sacc[q]);
+        for (int q = 0; q < PB_SEQ; ++q) sacc[q] = HD ? (float)(warp_sum((double)sacc[q]) + (double)mbias) : warp_sum(sacc[q]);
 #pragma unroll
         for (int q = 0; q < PB_SEQ; ++q) {
             if (q < nq && lane == q) {
@@ -980,6 +994,154 @@ __global__ void __launch_bounds__(256) pointer_batched_kernel(const PointerArgs 
             if (a.nonstop_count && idx >= a.num_token) atomicAdd(a.nonstop_count, 1);
             if (a.eos_count && idx == 3) atomicAdd(a.eos_count, 1);        // token.EOS == 3 (config.py:44)
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// beam search step (BASELINE.json configs[3]; specification: oracle/beam_oracle.py -- the reference has no beam search).
+// One CTA per anchor, one warp per hypothesis w < W: float64 log-sum-exp over the un-masked logits, the W best rows by
+// (logit desc, row asc); thread 0 merges the <= W*W candidates by (cum + logp desc, hypothesis asc, rank asc); then the token
+// histories are re-ordered into the other token buffer and the new tokens appended.  W = 1 degenerates to first-max argmax.
+// ------------------------------------------------------------------------------------------------
+constexpr int BEAM_MAX = 8;
+__global__ void beam_init_kernel(double* __restrict__ cum, int n, int W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cum[i] = (i % W == 0) ? 0.0 : -INFINITY;
+}
+
+__global__ void __launch_bounds__(32 * BEAM_MAX) beam_step_kernel(const float* __restrict__ logits, int L, const int* __restrict__ seq_wf,
+                                                                  const int* __restrict__ v_len, double* __restrict__ cum,
+                                                                  const int* __restrict__ tok_old, int* __restrict__ tok_new, int P, int T,
+                                                                  int Btot, int W, int num_token, int* nonstop_count, const int* stop) {
+    FFB_PDL_SYNC();
+    const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (stop != nullptr && *stop != 0) {            // after an early stop both token buffers are kept identical (the host keeps flipping them)
+        for (int i = tid; i < T * W; i += blockDim.x) { const int p = i / W, j = i % W; tok_new[(size_t)p * Btot + a * W + j] = tok_old[(size_t)p * Btot + a * W + j]; }
+        return;
+    }
+    __shared__ double c_score[BEAM_MAX][BEAM_MAX];
+    __shared__ int c_tok[BEAM_MAX][BEAM_MAX];
+    __shared__ int c_n[BEAM_MAX];
+    __shared__ int s_parent[BEAM_MAX], s_token[BEAM_MAX];
+    __shared__ double s_cum[BEAM_MAX];
+    const int sq = a * W + w;
+    const double cumw = cum[sq];
+    const int vl = v_len[seq_wf[sq]];
+    const float* lg = logits + (size_t)sq * L;
+    int n_c = 0;
+    if (cumw > -INFINITY) {
+        float m = -INFINITY;
+        for (int j = lane; j < vl; j += 32) m = fmaxf(m, lg[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        double sum = 0.0;
+        for (int j = lane; j < vl; j += 32) sum += exp((double)lg[j] - (double)m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const double lse = (double)m + log(sum);
+        int taken[BEAM_MAX];
+        for (int r = 0; r < W && r < vl; ++r) {
+            float bv = -INFINITY; int bi = 0x7fffffff;
+            for (int j = lane; j < vl; j += 32) {
+                bool skip = false;
+                for (int q = 0; q < r; ++q) skip |= (taken[q] == j);
+                const float v = lg[j];
+                if (!skip && (bi == 0x7fffffff || v > bv)) { bv = v; bi = j; }       // lane-local: ascending j, strict > keeps the first
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+            }
+            taken[r] = bi;
+            if (lane == 0) { c_score[w][r] = cumw + ((double)bv - lse); c_tok[w][r] = bi; }
+            ++n_c;
+        }
+    }
+    if (lane == 0) c_n[w] = n_c;
+    __syncthreads();
+    if (tid == 0) {
+        bool used[BEAM_MAX][BEAM_MAX];
+        for (int i = 0; i < W; ++i) for (int r = 0; r < W; ++r) used[i][r] = false;
+        for (int j = 0; j < W; ++j) {
+            int bw = -1, br = -1; double bs = 0.0;
+            for (int i = 0; i < W; ++i)
+                for (int r = 0; r < c_n[i]; ++r)
+                    if (!used[i][r] && (bw < 0 || c_score[i][r] > bs)) { bw = i; br = r; bs = c_score[i][r]; }
+            if (bw < 0) { s_parent[j] = 0; s_token[j] = 0; s_cum[j] = -INFINITY; continue; }     // fewer candidates than beams: dead hypothesis
+            used[bw][br] = true;
+            s_parent[j] = bw; s_token[j] = c_tok[bw][br]; s_cum[j] = bs;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < P * W; i += blockDim.x) {
+        const int p = i / W, j = i % W;
+        tok_new[(size_t)p * Btot + a * W + j] = tok_old[(size_t)p * Btot + a * W + s_parent[j]];
+    }
+    if (tid < W) {
+        tok_new[(size_t)P * Btot + a * W + tid] = s_token[tid];
+        cum[a * W + tid] = s_cum[tid];
+        if (nonstop_count && s_token[tid] >= num_token) atomicAdd(nonstop_count, 1);
+    }
+}
+
+// beams [slot, w, t] (int64) and scores [slot, w] from the token buffer: slot_seq[slot] = hypothesis 0 of the anchor feeding the slot
+__global__ void expand_beams_kernel(const int* __restrict__ tok, const double* __restrict__ cum, const int* __restrict__ slot_seq,
+                                    const int* __restrict__ steps_run, long long* __restrict__ beams, double* __restrict__ scores,
+                                    long long n_slots, int Btot, int W, int T) {
+    const long long total = n_slots * W * T;
+    const int filled = *steps_run + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const int w = (int)((i / T) % W);
+        const long long s = i / ((long long)T * W);
+        beams[i] = (t < filled) ? (long long)tok[(size_t)t * Btot + slot_seq[s] + w] : 0ll;
+        if (t == 0) scores[s * W + w] = cum[slot_seq[s] + w];
+    }
+}
+
+// Batch splitting over GPUs (BASELINE.json configs[2]): the reference's stop predicate `all(next < 4)` (model_para.py:232) ranges over
+// the WHOLE batch, whose wireframes are now spread over `world` ranks.  Every rank publishes its local verdict for this step into the
+// flag buffer of every rank (plain stores through peer mappings: NVLink P2P / CUDA IPC), waits until all verdicts of the step have
+// arrived in its own buffer and combines them -- one word per rank and step, no host round trip, no NCCL call on the data path.
+//   slot value = (epoch << 2) | (1 = some sequence of the rank continues, 2 = all of them emitted special tokens)
+//   buffers are double-buffered by epoch parity (a rank can be at most one decode ahead of its slowest peer)
+constexpr int XCHG_MAXW = 16;
+struct XchgArgs { int* peers[XCHG_MAXW]; int rank, world, T; };
+__global__ void step_end_xchg_kernel(int* nonstop_count, int* stop, int* steps_run, const XchgArgs x, int step, int epoch, int* err) {
+    FFB_PDL_SYNC();
+    if (*stop) return;
+    const int lane = threadIdx.x;
+    const int local = (*nonstop_count == 0) ? 2 : 1;
+    const int slot = ((epoch & 1) * x.T + step) * XCHG_MAXW;
+    if (lane < x.world) {
+        volatile int* dst = x.peers[lane] + slot + x.rank;
+        *dst = (epoch << 2) | local;
+    }
+    __threadfence_system();
+    bool all = true, timed_out = false;
+    if (lane < x.world) {
+        volatile int* src = x.peers[x.rank] + slot + lane;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        int v = *src;
+        while ((v >> 2) != epoch) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { timed_out = true; break; }      // 20 s: a peer died; fail instead of hanging the GPU
+            __nanosleep(200);
+            v = *src;
+        }
+        all = ((v & 3) == 2);
+    }
+    all = __all_sync(0xffffffffu, all);
+    timed_out = __any_sync(0xffffffffu, timed_out);
+    if (lane == 0) {
+        *nonstop_count = 0;
+        *steps_run += 1;
+        if (timed_out) { *err = 1; *stop = 1; }
+        else if (all) *stop = 1;
     }
 }
 
@@ -1032,6 +1194,15 @@ __global__ void unpack_memory_kernel(const float* __restrict__ mem, const int* _
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < v_len[w]) v = reinterpret_cast<const float4*>(mem)[(size_t)(row_off[w] + j) * e4n + c];
         reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// dst[c][r] = src[r][c]  (src [rows, cols])
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    const long long total = (long long)rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / rows), r = (int)(i % rows);
+        dst[i] = src[(size_t)r * cols + c];
     }
 }
 

@@ -320,6 +320,34 @@ class Engine:
     def fp16_fallbacks(self) -> int:
         return int(self._lib.ffb_fp16_fallbacks(self._h))
 
+    def get_beams(self, width: int):
+        """After a decode with FFB_OPT_BEAM = width: (beams int64 [N,F,W,T], scores float64 [N,F,W]), best hypothesis first."""
+        import torch
+        info = self.batch_info()
+        T = self.cfg.seq_len(self.mode)
+        if self._loc == FFB_DEVICE:
+            beams = torch.empty((info["N"], info["F"], width, T), dtype=torch.int64, device=f"cuda:{self.device}")
+            scores = torch.empty((info["N"], info["F"], width), dtype=torch.float64, device=f"cuda:{self.device}")
+        else:
+            beams = np.empty((info["N"], info["F"], width, T), np.int64)
+            scores = np.empty((info["N"], info["F"], width), np.float64)
+        self._check(self._lib.ffb_get_beams(self._h, _ptr(beams), _ptr(scores), self._loc, self._stream()))
+        return beams, scores
+
+    # -- one batch split over several GPUs ------------------------------------------------------
+    def stop_exchange_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.ffb_stop_exchange_export(self._h, buf))
+        return buf.raw
+
+    def stop_exchange_connect(self, rank: int, world: int, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._check(self._lib.ffb_stop_exchange_connect(self._h, rank, world, C.c_char_p(blob)))
+
+    def stop_exchange_disconnect(self):
+        self._check(self._lib.ffb_stop_exchange_disconnect(self._h))
+
     def overflowed(self) -> bool:
         """After an asynchronous decode (want_steps=False on CUDA tensors): did an activation leave the fp16 range?  True means the
         predictions are invalid, the handle now runs in bf16x3, and the batch must be run again."""

@@ -1,4 +1,10 @@
-"""Wireframe-level data parallelism: one process per GPU, whole batches per rank.
+"""Wireframe-level data parallelism: one process per GPU.
+
+Two partitionings, both tensor-identical to a single-GPU run:
+  * whole batches per rank (``plan_batches`` / ``assign_batches`` / ``run_sharded``): no coupling between ranks at all;
+  * ONE batch split over all ranks (``split_batch`` / ``SplitDecoder``; BASELINE.json configs[2], batch=128 over 8 GPUs): the two
+    per-batch couplings are carried across ranks -- F is fixed on the host (FFB_OPT_FORCE_F) and the per-step stop predicate crosses
+    NVLink inside the step-end kernel (ffb_stop_exchange_*), so a test split of 507 wireframes at batch 128 keeps all 8 GPUs busy.
 
 The reference has no distributed code.  Wireframes are independent
 units of ``forward_eval`` -- the only cross-sample couplings are per BATCH: F = max(num_input)
@@ -115,3 +121,79 @@ def run_sharded(decode_batch: Callable[[Batch], np.ndarray], batches: Sequence[B
     if not gather:
         return local, assignment
     return gather_predictions(local, batches, assignment, num_lines, seq_len, device), assignment
+
+
+# ---- one batch split over all ranks -------------------------------------------------------------------------------------------------
+def split_batch(num_input: Sequence[int], world_size: int) -> List[np.ndarray]:
+    """Deal the wireframes of ONE batch to ranks, longest-processing-time first on the number of distinct sequences (n_i real anchors
+    + the shared padded-anchor sequence), ties to the lower rank.  Deterministic; returns per-rank ascending index arrays (a rank may
+    get none when the batch has fewer wireframes than ranks)."""
+    ne = np.asarray(num_input, dtype=np.int64)
+    load = [0] * world_size
+    mine: List[List[int]] = [[] for _ in range(world_size)]
+    for i in sorted(range(len(ne)), key=lambda j: (-int(ne[j]), j)):
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        load[r] += int(ne[i]) + 1
+        mine[r].append(i)
+    return [np.asarray(sorted(m), dtype=np.int64) for m in mine]
+
+
+def merge_split(shares: Sequence[np.ndarray], parts: Sequence[np.ndarray], n: int) -> np.ndarray:
+    """Inverse of split_batch on the outputs: shares[r] = predict [len(parts[r]), F, T] of rank r -> predict [n, F, T]."""
+    ref = next(s for s in shares if s.shape[0] > 0)
+    out = np.zeros((n,) + tuple(ref.shape[1:]), dtype=ref.dtype)
+    for idx, sh in zip(parts, shares):
+        if len(idx):
+            out[idx] = sh[:len(idx)]
+    return out
+
+
+class SplitDecoder:
+    """model(batch) for one global batch spread over all ranks of the default process group (one Engine per rank)."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.eng = engine
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.connected = False
+
+    def connect(self):
+        """Exchange the CUDA IPC handles of the ranks' stop-flag buffers (the only set-up collective)."""
+        import torch.distributed as dist
+        if self.world == 1 or self.connected:
+            return
+        mine = self.eng.stop_exchange_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        self.eng.stop_exchange_connect(self.rank, self.world, handles)
+        self.connected = True
+
+    def forward_eval(self, coords, pad_mask, num_input, gather: bool = True):
+        """coords / pad_mask / num_input: the WHOLE batch (CUDA tensors, identical on every rank).  Returns (predict [N,F,T] int64 CUDA
+        tensor -- complete on every rank when gather, else only this rank's rows filled --, executed steps)."""
+        import torch
+        import torch.distributed as dist
+        from .lib import FFB_OPT_FORCE_F
+        ni = num_input.cpu().numpy() if hasattr(num_input, "cpu") else np.asarray(num_input)
+        n, F = len(ni), int(ni.max())
+        T = self.eng.cfg.seq_len(self.eng.mode)
+        parts = split_batch(ni, self.world)
+        if min(len(p) for p in parts) == 0:
+            raise ValueError("batch has fewer wireframes than ranks")
+        idx = torch.as_tensor(parts[self.rank], device=coords.device)
+        self.eng.set_option(FFB_OPT_FORCE_F, F if self.world > 1 else 0)
+        local, steps = self.eng.forward_eval(coords.index_select(0, idx), pad_mask.index_select(0, idx), num_input.index_select(0, idx))
+        out = torch.zeros((n, F, T), dtype=torch.int64, device=coords.device)
+        if self.world == 1 or not gather:
+            out[idx] = local
+            return out, steps
+        cap = max(len(p) for p in parts)
+        send = torch.zeros((cap, F, T), dtype=torch.int32, device=coords.device)
+        send[:len(idx)] = local.to(torch.int32)
+        recv = torch.empty((self.world, cap, F, T), dtype=torch.int32, device=coords.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)          # predicted face loops of every rank (NCCL over NVLink)
+        for r, p in enumerate(parts):
+            out[torch.as_tensor(p, device=coords.device)] = recv[r, :len(p)].to(torch.int64)
+        return out, steps

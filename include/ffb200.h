@@ -75,6 +75,41 @@ enum {
                                 default, so that 'pointer' [N,P,E] of model.py:217 is complete). */
 };
 
+/* Beam search (BASELINE.json configs[3], "beam=4"; parallel mode only).  The reference has NO beam search: the semantics are
+ * specified by this build (oracle/beam_oracle.py) -- W hypotheses per anchor sequence scored by cumulative
+ * log-softmax over the un-masked rows in float64, ties to the lowest (hypothesis, row) index, no per-sequence termination, the
+ * reference's global stop predicate over all hypotheses.  value = W in [1, 8]; 1 (default) is exactly the greedy loop
+ * (model_para.py:216-233).  `predict` then holds the best hypothesis of every anchor. */
+enum { FFB_OPT_BEAM = 15 };
+
+/* Precision of the two stages that dominate the pointer-logit error budget (both are ~1 % of a decode's FLOPs).
+ * FFB_OPT_ENCODER_PRECISION: 2 (default) = embedding, encoder and the once-per-wireframe cross-attention K / V projections in
+ *   float64 on the FP64 pipe (wireframes of <= 1024 memory rows; larger ones use mode 0); 0 = fp16x2 tcgen05 pipeline when the batch has
+ *   >= 2048 memory rows (FFB_OPT_ENCODER_TC), else fp32 SIMT -- the throughput mode of the encoder-only workload (BASELINE configs[4]).
+ * FFB_OPT_HEAD_FP64: 1 (default) = decoder.norm + project + the pointer dot product of the last position in float64; 0 = fp32. */
+enum { FFB_OPT_ENCODER_PRECISION = 16, FFB_OPT_HEAD_FP64 = 17 };
+
+/* ---- one batch split over several GPUs (BASELINE.json configs[2]: "batch=128 sharded over 8xB200") -------------------------------
+ * One process per GPU decodes a SHARE of the wireframes of one global batch.  forward_eval couples the wireframes of a batch in two
+ * places only: F = max(num_input) (model_para.py:187) and the stop predicate all(next < 4) (model_para.py:232).  With
+ *   FFB_OPT_FORCE_F = F of the global batch (set before ffb_encode; the share's predict is then [n_share, F, T]), and
+ *   a connected stop exchange (every decode step ends with the ranks' local verdicts crossing NVLink through peer-mapped flag words;
+ *   no host synchronisation, no collective call),
+ * the shares concatenate to exactly the tensor a single GPU produces for the whole batch.  Protocol: every rank calls
+ * ffb_stop_exchange_export (a 64-byte CUDA IPC handle of its flag buffer), the handles are all-gathered by the host framework
+ * (torch.distributed), every rank calls ffb_stop_exchange_connect with all of them.  From then on every rank must call
+ * ffb_decode_greedy the same number of times.  An fp16-range overflow cannot be re-run privately in this mode: it is reported as
+ * FFB_ERR_UNSUPPORTED (use FFB_OPT_TC_FORMAT = 3 on every rank). */
+enum { FFB_OPT_FORCE_F = 18 };
+int ffb_stop_exchange_export(ffb_handle* h, void* ipc_handle_out /* 64 bytes */);
+int ffb_stop_exchange_connect(ffb_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
+int ffb_stop_exchange_disconnect(ffb_handle* h);
+
+/* 1: ffb_encode computes the encoder memory only (embedding, encoder layers, final norm; ffb_get_memory reads it) -- no decode
+ * workspaces are sized, the cross-attention K / V cache and the folded pointer head are skipped and ffb_decode_greedy is refused.
+ * The encoder-only throughput workload of BASELINE.json configs[4] (2048-edge wireframes, batch 256). */
+enum { FFB_OPT_ENCODE_ONLY = 19 };
+
 /* Number of fp32 elements ffb_load_weights expects for this config: the reference
  * state_dict's float tensors, concatenated in state_dict order;
  * the two int64 `position` buffers are skipped.  Returns 0 for an invalid config. */
@@ -180,6 +215,10 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
 /* Number of decodes that had to be re-run in bf16x3 because an activation left the fp16 range (see FFB_OPT_TC_FORMAT). */
 int ffb_fp16_fallbacks(const ffb_handle* h);
 
+/* After a decode with FFB_OPT_BEAM = W > 1: all hypotheses, best first.
+ *   beams  int64  [N, F, W, T]    scores double [N, F, W] (cumulative log-probability; -inf = dead hypothesis) */
+int ffb_get_beams(ffb_handle* h, int64_t* beams, double* scores, int loc, void* stream);
+
 /* A fully asynchronous ffb_decode_greedy (device buffers, steps_run == NULL) cannot look at the fp16-range flag of the default
  * operand format and therefore cannot re-run by itself.  After such a call, ffb_overflowed() synchronises `stream` and reports in
  * *overflowed whether an activation left the fp16 range.  If so the predictions of that decode are INVALID: the handle has been
@@ -235,9 +274,9 @@ enum { FFB_OPT_GEMM_VARIANT = 11 };
 /* 1 (default): encoder layers and the once-per-wireframe cross-attention K / V projections run on the tcgen05 pipeline (fp16x2 GEMMs,
  * tcgen05 attention) when the batch has >= 2048 memory rows and <= 256 rows per wireframe; 0 = always fp32 SIMT + 3xTF32 mma.sync. */
 enum { FFB_OPT_ENCODER_TC = 12 };
-/* 1: the decode-step kernels are launched with programmatic stream serialization (programmatic dependent launch): each kernel's
- * CTAs are scheduled as its predecessor's retire and wait (griddepcontrol.wait) before touching memory.  Default 0: measured 3 %
- * SLOWER on the bench step (344 vs 333 ms), results identical. */
+/* Programmatic dependent launch (programmatic stream serialization) for the decode-step kernels: each kernel's CTAs are scheduled as
+ * its predecessor's retire and wait (griddepcontrol.wait) before touching memory.  0 = off, 1 = on, 2 (default) = on for batches of
+ * <= 32768 decode rows (launch-latency bound: measured +5..10 % at one wireframe per batch, -3 % on the 32-wireframe bench batch). */
 enum { FFB_OPT_PDL = 13 };
 /* 1 (default): the pointer head (select_next) streams a wireframe's memory rows once per 16 of its sequences
  * (pointer_batched_kernel; logits and tokens bit-identical to the per-sequence kernel); 0 = one CTA per sequence. */

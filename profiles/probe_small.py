@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from faceformer_b200 import synth  # noqa: E402
 from faceformer_b200.config import MODE_PARALLEL, MODE_SEQ2SEQ, OURS, SEQ2SEQ  # noqa: E402
 from faceformer_b200.engine import Engine  # noqa: E402
-from faceformer_b200.lib import FFB_OPT_TENSOR_CORE  # noqa: E402
+from faceformer_b200.lib import FFB_OPT_PDL, FFB_OPT_TENSOR_CORE  # noqa: E402
 
 OUT = []
 
@@ -41,17 +41,18 @@ def timed(eng, args, reps=3):
 
 
 def main():
-    for tc in (0, 1, 2):
+    for tc, pdl in ((0, 0), (1, 0), (1, 1)):
         # seq2seq, one 64-edge wireframe, 258 steps (the golden's weights: no early EOS)
         from util import load_case
         g = load_case("seq2seq_single64")
         e = Engine(g["cfg"], g["mode"], 0)
         e.load_state_dict(g["sd"])
         e.set_option(FFB_OPT_TENSOR_CORE, tc)
+        e.set_option(FFB_OPT_PDL, pdl)
         b = g["batch"]
         args = (torch.from_numpy(b["input"]).cuda().flatten(2), torch.from_numpy(b["input_mask"]).cuda(), None)
         ms, wall, launches, steps = timed(e, args)
-        rec = dict(workload="seq2seq_n1_64", tc=tc, ms=ms, wall_ms=wall, launches=launches, steps=steps, edges_per_s=steps / ms * 1e3,
+        rec = dict(workload="seq2seq_n1_64", tc=tc, pdl=pdl, ms=ms, wall_ms=wall, launches=launches, steps=steps, edges_per_s=steps / ms * 1e3,
                    us_per_step=ms / steps * 1e3)
         print(json.dumps(rec), flush=True)
         OUT.append(rec)
@@ -61,11 +62,12 @@ def main():
         e = Engine(OURS, MODE_PARALLEL, 0)
         e.load_state_dict(sd)
         e.set_option(FFB_OPT_TENSOR_CORE, tc)
+        e.set_option(FFB_OPT_PDL, pdl)
         for n in (24, 64, 120, 216):
             bt = synth.synth_batch(OURS, MODE_PARALLEL, 1, seed=n, num_edges=np.array([n], np.int64))
             args = (torch.from_numpy(bt["input"]).cuda().flatten(2), torch.from_numpy(bt["input_mask"]).cuda(), torch.from_numpy(bt["num_input"]).cuda())
             ms, wall, launches, steps = timed(e, args)
-            rec = dict(workload=f"ours_n1_{n}", tc=tc, ms=ms, wall_ms=wall, launches=launches, steps=steps, edges_per_s=n * steps / ms * 1e3,
+            rec = dict(workload=f"ours_n1_{n}", tc=tc, pdl=pdl, ms=ms, wall_ms=wall, launches=launches, steps=steps, edges_per_s=n * steps / ms * 1e3,
                        us_per_step=ms / steps * 1e3)
             print(json.dumps(rec), flush=True)
             OUT.append(rec)

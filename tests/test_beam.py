@@ -44,3 +44,66 @@ def test_beam_select_tie_break_and_dead_hypotheses():
     # hypothesis 1 is uniform over 4 rows (logp = -log 4 = -1.386); hypothesis 0's best rows have logp = -0.98
     assert parent.tolist() == [0, 0] and token.tolist() == [1, 2]
     assert np.all(np.diff(cum) <= 0)
+
+
+# ---- GPU: the CUDA beam step against the specification ------------------------------------------------------------------------------
+def _run_gpu(g, width, tc=None):
+    import torch
+    from faceformer_b200.engine import Engine
+    from faceformer_b200.lib import FFB_OPT_BEAM, FFB_OPT_TENSOR_CORE
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_BEAM, width)
+    if tc is not None:
+        e.set_option(FFB_OPT_TENSOR_CORE, tc)
+    b = g["batch"]
+    pred, steps = e.forward_eval(torch.from_numpy(b["input"]).cuda().flatten(2), torch.from_numpy(b["input_mask"]).cuda(),
+                                 torch.from_numpy(b["num_input"]).cuda())
+    out = dict(predict=pred.cpu().numpy(), steps=steps)
+    if width > 1:
+        beams, scores = e.get_beams(width)
+        out.update(beams=beams.cpu().numpy(), scores=scores.cpu().numpy())
+    e.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny_parallel_trained", "tiny_parallel_ragged", "perspective_small"])
+def test_gpu_beam1_is_greedy(name):
+    g = load_case(name)
+    out = _run_gpu(g, 1)
+    assert out["steps"] == g["steps"] and np.array_equal(out["predict"], g["predict"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,width", [("tiny_parallel_trained", 4), ("tiny_parallel_trained", 2), ("tiny_parallel_trained_b", 4),
+                                        ("tiny_parallel_ragged", 4), ("tiny_parallel_ragged", 3)])
+def test_gpu_beam_matches_the_specification(name, width):
+    g = load_case(name)
+    want = beam_oracle.forward_eval_beam(g["sd"], g["cfg"].to_dict(), g["batch"], width)
+    got = _run_gpu(g, width)
+    assert got["steps"] == want["steps"]
+    assert np.array_equal(got["beams"], want["beams"]), f"{(got['beams'] != want['beams']).sum()} token mismatches"
+    assert np.array_equal(got["predict"], want["predict"])
+    fin = np.isfinite(want["scores"])
+    assert np.array_equal(np.isfinite(got["scores"]), fin)
+    assert np.max(np.abs(got["scores"][fin] - want["scores"][fin])) < 2e-3       # sums of <= T-1 log-probabilities of fp32 logits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tc", [0, 2])
+def test_gpu_beam4_full_size_properties(tc):
+    """ours-perspective.yml geometry (BASELINE.json configs[3]), SIMT and forced tcgen05: both pipelines give the same beams; scores are
+    sorted; beams of a real anchor are distinct; the best beam is at least as likely as the greedy path."""
+    g = load_case("perspective_small")
+    o4 = _run_gpu(g, 4, tc)
+    s = o4["scores"]
+    assert np.all(np.diff(s, axis=-1) <= 0) and np.all(np.isfinite(s))
+    b = o4["beams"]
+    assert np.array_equal(b[:, :, 0], o4["predict"])
+    for n in range(b.shape[0]):
+        for f in range(int(g["batch"]["num_input"][n])):
+            assert len({tuple(b[n, f, w]) for w in range(4)}) == 4
+    if tc == 2:
+        ref = _run_gpu(g, 4, 0)
+        assert np.array_equal(ref["beams"], b)

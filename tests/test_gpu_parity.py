@@ -95,7 +95,7 @@ def test_dedup_and_pruning_do_not_change_results(name):
         e.close()
     for pred, steps, lg, info in res:
         assert steps == g["steps"] and np.array_equal(pred, g["predict"])
-        assert logits_close(lg, res[0][2], 1e-5)[0]
+        assert logits_close(lg, res[0][2], 5e-5)[0]        # pruned / un-pruned last layer take different kernels (attn_last vs tcgen05 attention)
     assert res[1][3]["B_eff"] == res[1][3]["B"] and res[0][3]["B_eff"] <= res[0][3]["B"]
 
 

@@ -50,7 +50,8 @@ def logits_close(a, b, tol=LOGIT_TOL, b64=None):
     Noise-floor clause (b64 = the reference evaluated in float64, stored in the fixture): two correct fp32 evaluations of
     the same function can be farther apart than 1e-4 when the reference's own fp32 result is ~1e-4 from the exact one
     (measured 0.8e-4 on the ours.yml-size fixtures, profiles/logit_noise.py).  Such a comparison passes if our logits are no
-    farther from the float64 evaluation than NOISE_FACTOR x the reference's own fp32 logits are."""
+    farther from the float64 evaluation than NOISE_FACTOR x the reference's own fp32 logits are (NOISE_FACTOR = 1: at least as close to
+    the exact result as the reference itself)."""
     a, b = np.asarray(a), np.asarray(b)
     fmin = np.finfo(np.float32).min
     ma, mb = a == fmin, b == fmin
@@ -70,7 +71,7 @@ def logits_close(a, b, tol=LOGIT_TOL, b64=None):
     return False, d
 
 
-NOISE_FACTOR = 3.0        # measured: 0.7x - 2.3x over all fixtures and pipelines
+NOISE_FACTOR = 1.0        # r2 (float64 encoder + folded float64 head): 0.3x - 0.9x over all fixtures and pipelines
 
 CASES_ALL = ["tiny_parallel_trained", "tiny_parallel_trained_b", "tiny_parallel_ragged", "tiny_seq2seq",
              "ours_parallel_small", "seq2seq_single64",
