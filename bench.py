@@ -471,6 +471,11 @@ def run_small(args, name):
     step_host()
     e2e_steps = max(1, min(args.steps, 3))
     ms_e, _ = _timed(torch, dist, world, dev, step_host, e2e_steps)
+    from faceformer_b200.lib import FFB_OPT_PROFILE
+    eng.set_option(FFB_OPT_PROFILE, 1)                       # event pair around every launch: kernel time without the launch gaps
+    step_device()
+    prof = eng.profile_read()
+    eng.set_option(FFB_OPT_PROFILE, 0)
     peaks = load_peaks()
     value = edges * args.steps / (ms / 1e3)
     h2d = sum(c.nbytes + m.nbytes + (0 if ni is None else ni.nbytes) for c, m, ni in w["host_calls"])
@@ -491,6 +496,8 @@ def run_small(args, name):
         "roofline": {"bound": "hbm", "kernel": "decode step (all kernels of one greedy step; launch-latency bound at this size)",
                      "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                      "algorithmic_bytes_per_decode_step": bytes_total / steps_total, "launches_per_decode_step": launches / args.steps / steps_total,
+                     "kernel_ms_by_class": {k: round(v["ms"], 3) for k, v in prof.items()},
+                     "kernel_ms_sum_vs_step_ms": [round(sum(v["ms"] for v in prof.values()), 3), round(ms / args.steps, 3)],
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"},
         "cpu_baseline": None}
     print(json.dumps(line))

@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from faceformer_b200 import synth  # noqa: E402
-from faceformer_b200.config import (MODE_PARALLEL, MODE_SEQ2SEQ, OURS, OURS_PERSPECTIVE, SEQ2SEQ, TINY, ModelConfig)  # noqa: E402
+from faceformer_b200.config import (MID, MODE_PARALLEL, MODE_SEQ2SEQ, OURS, OURS_PERSPECTIVE, SEQ2SEQ, TINY, ModelConfig)  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -47,6 +47,12 @@ CASES = {
                                   inputs=("polygon", 11), prefix_P=5),
     "tiny_parallel_trained_b": dict(cfg=TINY, mode=MODE_PARALLEL, n=7, weights=("file", "tiny_trained_parallel.npz"),
                                     inputs=("polygon", 12), prefix_P=9),
+    # E = 512 / H = 8 checkpoint TRAINED with the reference's forward_train (oracle/train_fixture.py --cfg mid): non-degenerate weights on the
+    # tcgen05 grid, 16 / 24 polygon wireframes (diverse tokens, early stop)
+    "mid_parallel_trained": dict(cfg=MID, mode=MODE_PARALLEL, n=16, weights=("file", "mid_trained_parallel.npz"),
+                                 inputs=("polygon", 21), prefix_P=6),
+    "mid_parallel_trained_b": dict(cfg=MID, mode=MODE_PARALLEL, n=24, weights=("file", "mid_trained_parallel.npz"),
+                                   inputs=("polygon", 22), prefix_P=8),
     "tiny_parallel_ragged": dict(cfg=TINY, mode=MODE_PARALLEL, n=5, weights=("synth", 3, "diverse"),
                                  inputs=("synth", 5, [1, 28, 3, 17, 9]), prefix_P=7),
     "tiny_seq2seq": dict(cfg=TINY, mode=MODE_SEQ2SEQ, n=3, weights=("synth", 4, "diverse"),

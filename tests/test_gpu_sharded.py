@@ -98,7 +98,7 @@ def _split_worker(rank, world, port, case, q):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("case", ["tiny_parallel_trained_b", "tiny_parallel_ragged"])
+@pytest.mark.parametrize("case", ["tiny_parallel_trained", "tiny_parallel_ragged"])
 def test_one_batch_split_over_two_ranks_equals_the_single_gpu_tensor(case):
     """BASELINE.json configs[2] mechanism: the wireframes of ONE batch on two ranks (two processes; on a one-GPU box they share cuda:0),
     F fixed globally, the stop predicate exchanged per step through peer-mapped flag words (CUDA IPC).  The merged shares must equal the

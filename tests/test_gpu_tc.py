@@ -321,3 +321,32 @@ def test_reload_and_option_change_invalidate_the_encoded_batch():
     pred, steps = e.forward_eval(coords, mask, ni)
     assert np.array_equal(pred.cpu().numpy(), g["predict"]) and steps == g["steps"]
     e.close()
+
+
+@pytest.mark.parametrize("name", ["mid_parallel_trained", "mid_parallel_trained_b"])
+@pytest.mark.parametrize("fmt", [2, 3])
+def test_trained_e512_checkpoint_through_forced_tcgen05(name, fmt):
+    """non-degenerate (trained) weights on the tensor path.  An E = 512 / H = 8 checkpoint trained with the reference's
+    own forward_train (oracle/train_fixture.py --cfg mid; 27 distinct tokens in the goldens), 16 / 24 wireframes, EVERY decode step forced
+    through tc::gemm_kernel / ax::attn_x_kernel, against the unmodified reference's output: tokens exact, logits within 1e-4."""
+    g = load_case(name)
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_TC_FORMAT, fmt)
+    e.set_option(FFB_OPT_TENSOR_CORE, 2)
+    b = g["batch"]
+    coords = torch.from_numpy(b["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda()
+    from faceformer_b200.lib import FFB_OPT_PROFILE
+    e.set_option(FFB_OPT_PROFILE, 1)
+    pred, steps = e.forward_eval(coords, mask, ni)
+    prof = e.profile_read()
+    e.set_option(FFB_OPT_PROFILE, 0)
+    assert prof["linear_tc"]["launches"] > 0 and e.fp16_fallbacks() == 0
+    assert steps == g["steps"] and np.array_equal(pred.cpu().numpy(), g["predict"])
+    assert len(np.unique(g["predict"])) >= 20                                          # the fixture is not degenerate
+    ok, d = logits_close(e.get_last_logits().cpu().numpy(), g["last_logits"], b64=g.get("last_logits64"))
+    assert ok, d
+    vm = valid_rows_mask(b, g["cfg"])
+    assert np.max(np.abs(e.get_memory().cpu().numpy()[vm] - g["memory"][vm])) <= LOGIT_TOL
+    e.close()

@@ -76,4 +76,6 @@ NOISE_FACTOR = 1.0        # r2 (float64 encoder + folded float64 head): 0.3x - 0
 CASES_ALL = ["tiny_parallel_trained", "tiny_parallel_trained_b", "tiny_parallel_ragged", "tiny_seq2seq",
              "ours_parallel_small", "seq2seq_single64",
              "perspective_small",     # BASELINE.json configs[3] geometry (ours-perspective.yml), greedy
-             "ours_wide300"]          # configs[1] "<= 512 edges": 274 memory rows (> 256: mma.sync cross-attention)
+             "ours_wide300",          # configs[1] "<= 512 edges": 274 memory rows (> 256: mma.sync cross-attention)
+             "mid_parallel_trained",  # E = 512 / H = 8 TRAINED checkpoint (non-degenerate weights on the tcgen05 grid), 16 and 24 wireframes
+             "mid_parallel_trained_b"]
