@@ -170,6 +170,47 @@ def test_full_size_properties():
 
 
 @pytest.mark.timeout(300)
+def test_bench_batch_equals_the_reference_golden():
+    """the EXACT bench.py batch (BASELINE.json configs[1]: seed 0, 32 wireframes, 6912 sequences, 36 steps) on the
+    DEFAULT path against the unmodified reference (tests/golden/bench_batch.npz, oracle/make_golden_bench.py: the reference decoded the
+    batch one wireframe at a time, ~50 CPU-minutes, and the assembly rule was checked against a batched reference call): the whole
+    [32, 216, 37] tensor, S = 36, and the last-step logits of two wireframes within 1e-4."""
+    import json
+    from faceformer_b200.engine import Engine
+    from util import GOLDEN, logits_close
+    with np.load(os.path.join(GOLDEN, "bench_batch.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    meta = json.loads(str(g["meta"]))
+    assert meta["n"] == 32 and meta["weights"] == ["synth", 0, "diverse"]
+    cfg = OURS
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 32, seed=0)                   # exactly what bench.py decodes on rank 0
+    eng = Engine(cfg, MODE_PARALLEL, 0)
+    eng.load_state_dict(sd)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    for host in (False, True):
+        if host:
+            pred, steps = eng.forward_eval(batch["input"].reshape(32, cfg.num_lines, -1), batch["input_mask"], batch["num_input"])
+        else:
+            pred, steps = eng.forward_eval(coords, mask, ni)
+            pred = pred.cpu().numpy()
+        assert steps == int(g["steps"]) == cfg.max_face_length - 1
+        want = g["predict"].astype(np.int64)
+        assert pred.shape == want.shape == (32, int(batch["num_input"].max()), cfg.max_face_length)
+        assert np.array_equal(pred, want), f"{(pred != want).sum()} of {want.size} tokens differ from the reference"
+    assert eng.fp16_fallbacks() == 0
+    F = int(batch["num_input"].max())
+    lg = eng.get_last_logits()
+    lg = (lg if isinstance(lg, np.ndarray) else lg.cpu().numpy()).reshape(32, F, cfg.mem_len)
+    for tag, w in zip("ab", g["logit_wireframes"]):
+        n = int(batch["num_input"][w])
+        ok, d = logits_close(lg[w, :n], g[f"last_logits_{tag}"], b64=g[f"last_logits64_{tag}"])
+        assert ok, f"wireframe {w}: last-step logits differ from the reference by {d}"
+    eng.close()
+
+
+@pytest.mark.timeout(300)
 def test_bench_workload_properties_and_seq2seq_latency():
     """BASELINE.json configs[1] at full size (32 wireframes, 6912 sequences, 36 steps): size-independent properties only
     (the oracle would need hours).  Also times configs[0] (seq2seq, one 64-edge wireframe, 258 steps) for the record."""
