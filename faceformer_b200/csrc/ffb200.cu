@@ -21,6 +21,7 @@
 #include "attn_h.cuh"
 #include "attn_x.cuh"
 #include "enc64.cuh"
+#include "attn_l.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -80,6 +81,8 @@ struct ffb_handle {
     DevBuf x64, y64, yp64, qkv64, att64, h64;
     DevBuf projT, memW, hy32;                     // folded head: [W_project^T ; b_project] (E+1 x E), memory . projT^T [R, E+4], LN of the last position [B, E]
     bool enc_used_64 = false;
+    DevBuf d_tile_off;                            // [N + 1] prefix of ceil(vlen / 256): work items (pairs of query tiles) of attn_l.cuh
+    int opt_attn_long = 1;                        // encoder self-attention with > 256 keys per wireframe on the tcgen05 streaming kernel (0: mma.sync)
     int opt_encode_only = 0;                      // encoder-only use (BASELINE configs[4]): no decode workspaces, no cross K/V cache, no folded head
     bool encode_only = false;                     // ... of the encoded batch
     int opt_force_F = 0;                          // F of the GLOBAL batch when this handle decodes a share of it (0 = local max(num_input))
@@ -117,6 +120,8 @@ struct ffb_handle {
     int opt_gemm_variant = 2;                     // fp16x2 GEMM: 0 / 1 = single-CTA pipeline variant (gemm_tc.cuh Cfg<NS, V>), 2 = variant per launch,
                                                   // 3 = CTA-pair kernel (gemm_tc2.cuh, cta_group::2) wherever the TMA epilogue applies
     std::unordered_map<const CUtensorMap*, CUtensorMap> w_half_maps;   // W map (256-row boxes) -> its twin with 128-row boxes (CTA-pair kernel)
+    std::unordered_map<const CUtensorMap*, CUtensorMap> w_skinny_maps; // ... and with 64-row boxes (64-column tiles for small M)
+    int opt_skinny = 1;                           // fp16x2 GEMMs whose 128 x 256 tiles would leave most SMs idle run with 128 x 64 tiles
     CUtensorMap mc_x, mc_xl, mc_qkv3, mc_qkv1, mc_att;   // fp32 output maps of the decode-step activation buffers
     CUtensorMap ms_h;                             // fp16x2 split STORE map of a_h (FFN hidden)
     // "half pipeline" (fp16x2 GEMM + fp16x2 attention): q,k,v and the cross-attention query never exist in fp32
@@ -395,6 +400,22 @@ int launch_attn_x(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, c
     return FFB_OK;
 }
 
+// tcgen05 attention over many keys (attn_l.cuh): queries = keys = the rows of each group
+int launch_attn_long(ffb_handle* h, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, al::Params p, long long total_tiles,
+                     double qk_pairs, int prof_class, cudaStream_t s) {
+    const long long items = total_tiles * h->H;
+    if (items <= 0) return FFB_OK;
+    if (items > 0x7fffffffLL) return fail(h, FFB_ERR_ARG, "attention: too many work items");
+    p.n_heads = h->H; p.total_items = (int)items;
+    const int grid = (int)std::min<long long>(items, h->num_sms);
+    prof_begin(h, prof_class, 4.0 * 64 * h->H * qk_pairs, s);
+    al::attn_long_kernel<<<grid, al::NUM_THREADS, al::SMEM_BYTES, s>>>(mq, mk, mv, p);
+    prof_end(h, s);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return FFB_OK;
+}
+
 int launch_attn_tiled(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                       const AttnGroups& g_in, int G, int max_q_rows, double qk_pairs, const int* stop, cudaStream_t s,
                       uint16_t* Os = nullptr, long long os_stride = 0) {
@@ -468,9 +489,11 @@ int encode_operand_map(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, ui
 int encode_weight_maps(ffb_handle* h, CUtensorMap* m, void* base, uint64_t K, uint64_t rows, int fmt) {
     int rc = encode_operand_map(h, m, base, K, rows, tc::BN, fmt);
     if (rc != FFB_OK || fmt != 2) return rc;
-    CUtensorMap half;
+    CUtensorMap half, skinny;
     rc = encode_operand_map(h, &half, base, K, rows, tc2::BN / 2, fmt);
     if (rc == FFB_OK) h->w_half_maps[m] = half;
+    if (rc == FFB_OK) rc = encode_operand_map(h, &skinny, base, K, rows, 64, fmt);
+    if (rc == FFB_OK) h->w_skinny_maps[m] = skinny;
     return rc;
 }
 
@@ -533,6 +556,20 @@ int launch_tc(ffb_handle* h, const TcLin& l, const int* stop, cudaStream_t s) {
             const int tiles2 = ((l.M + 2 * tc2::BM - 1) / (2 * tc2::BM)) * (l.N / tc2::BN);
             const int pairs = std::max(1, std::min(tiles2, h->num_sms / 2));
             tc2::gemm2_kernel<<<2 * pairs, tc2::NUM_THREADS, tc2::SMEM_BYTES, s>>>(*l.A0, l.A1 ? *l.A1 : *l.A0, it->second, mc, p);
+            prof_end(h, s);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            return FFB_OK;
+        }
+    }
+    // small M: 128 x 64 tiles (gemm_tc.cuh Cfg<2, 1, 64>) put 4x as many CTAs on the weight stream and cut the per-tile MMA time 4x
+    if (h->tc_fmt == 2 && h->opt_skinny && 2 * tiles <= h->num_sms) {
+        auto it = h->w_skinny_maps.find(l.W);
+        if (it != h->w_skinny_maps.end()) {
+            const int tiles64 = ((l.M + tc::BM - 1) / tc::BM) * (l.N / 64);
+            p.n_switch = (l.n_switch >= (1 << 28)) ? l.n_switch : l.n_switch * (tc::BN / 64);
+            launch_k(h, tc::gemm_kernel<2, 1, 64>, dim3(std::min(tiles64, h->num_sms)), dim3(tc::NUM_THREADS), (size_t)tc::Cfg<2, 1, 64>::SMEM_BYTES, s,
+                     *l.A0, l.A1 ? *l.A1 : *l.A0, it->second, mc, p);
             prof_end(h, s);
             h->launches++;
             CU(h, cudaGetLastError());
@@ -778,6 +815,11 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     FFB_TRY(upload(h, h->d_seq_off, h->h_seq_off, s));
     FFB_TRY(upload(h, h->d_slot_seq, slot_seq, s));
     FFB_TRY(upload(h, h->d_seq_slot, seq_slot, s));
+    {
+        std::vector<int> tile_off(N + 1, 0);
+        for (int i = 0; i < N; ++i) tile_off[i + 1] = tile_off[i] + (h->h_vlen[i] + 2 * al::BQ - 1) / (2 * al::BQ);     // pairs of 128-query tiles
+        FFB_TRY(upload(h, h->d_tile_off, tile_off, s));
+    }
     // the std::vectors above are pageable: make sure the copies are done before they go out of scope
     CU(h, cudaStreamSynchronize(s));
 
@@ -960,11 +1002,18 @@ int run_encoder64(ffb_handle* h, const float* coords_dev, cudaStream_t s) {
     }
     // encoder.norm (transformer.py:80-81): memory in float64 (y), memory + pos (yp) and its fp32 rounding (what the decode gathers and scores)
     FFB_TRY(launch_ln64(h, x, nullptr, 1, 0, w.enc_nw, w.enc_nb, y, yp, h->mem.as<float>(), w.pos, pos_idx, 1, R, nullptr, s));
-    // cross-attention K / V of every decoder layer from the float64 memory, rounded to fp32 once
-    { e64::GemmArgs a{}; a.A = yp; a.lda = E; a.W = w.ckw; a.ldw = E; a.bias = w.ckb; a.C32 = h->Kc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
-      FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
-    { e64::GemmArgs a{}; a.A = y; a.lda = E; a.W = w.cvw; a.ldw = E; a.bias = w.cvb; a.C32 = h->Vc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
-      FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    // cross-attention K / V of every decoder layer.  Large batches: fp16x2 tcgen05 GEMMs on the fp32 rounding of the float64 memory (the
+    // products are exact to 2^-22, the class of the decoder that consumes them; 24 of the encoder's 135 GFLOP on the bench batch leave the
+    // FP64 pipe).  Otherwise from the float64 memory on the FP64 pipe, rounded to fp32 once.
+    const ffb_handle::TcSet& TS = h->tcs[0];
+    if (h->half_pipe && h->tc_fmt == 2 && TS.ready && R >= TC_MIN_ROWS && !h->encode_only) {
+        FFB_TRY(run_cross_cache(h, s, true));
+    } else if (!h->encode_only) {
+        { e64::GemmArgs a{}; a.A = yp; a.lda = E; a.W = w.ckw; a.ldw = E; a.bias = w.ckb; a.C32 = h->Kc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
+          FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+        { e64::GemmArgs a{}; a.A = y; a.lda = E; a.W = w.cvw; a.ldw = E; a.bias = w.cvb; a.C32 = h->Vc.as<float>(); a.ldc32 = LdE; a.M = R; a.N = LdE; a.K = E;
+          FFB_TRY(launch_dgemm(h, a, nullptr, s)); }
+    }
     FFB_TRY(run_head_fold(h, s, true));
     return run_cross_cache_split(h, s);
 }
@@ -1012,7 +1061,13 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
               ax::Params ap{}; ap.mode = 0; ap.seq_off = row_off; ap.q_mul = 1; ap.row_off = row_off; ap.vlen = vlen; ap.n_groups = N;
               ap.q_col = 0; ap.k_col = E; ap.v_col = 2 * E; ap.Os = aatt; ap.os_stride = ssE; ap.ldo = E;
               if ((rc = launch_attn_x(h, h->msf_q, h->msf_k, h->msf_v, ap, &h->h_row_off, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break;
-            } else {                                                      // any number of keys: fp16x2 mma.sync kernel on the same operands
+            } else if (h->opt_attn_long) {                                // > 256 keys per wireframe: K / V stream through the tcgen05 kernel
+              al::Params lp{}; lp.tile_off = h->d_tile_off.as<int>(); lp.row_off = row_off; lp.vlen = vlen; lp.n_groups = N;
+              lp.q_col = 0; lp.k_col = E; lp.v_col = 2 * E; lp.Os = aatt; lp.os_stride = ssE; lp.ldo = E;
+              long long tiles = 0;
+              for (int i = 0; i < N; ++i) tiles += (h->h_vlen[i] + 2 * al::BQ - 1) / (2 * al::BQ);
+              if ((rc = launch_attn_long(h, h->msf_q, h->msf_k, h->msf_v, lp, tiles, h->sum_vlen2, PC_ATTN_TILED, s)) != FFB_OK) break;
+            } else {                                                      // fp16x2 mma.sync kernel on the same operands
               AttnHalfIn in{aqkv, h->cap_rows * 3 * E, 3 * E, aqkv + E, h->cap_rows * 3 * E, aqkv + 2 * E, h->cap_rows * 3 * E, 3 * E};
               AttnGroups g{}; g.ragged = 1; g.q_begin = row_off; g.q_mul = 1; g.k_begin = row_off; g.k_len = vlen;
               if ((rc = launch_attn_h(h, in, aatt, ssE, g, N, h->max_vlen, h->max_vlen, h->sum_vlen2, PC_ATTN_TILED, nullptr, s)) != FFB_OK) break;
@@ -1301,6 +1356,8 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(attn_mma_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(tc::gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2, 1>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<2, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2, 1, 64>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(al::attn_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, al::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc2::gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, FFB_ERR_CUDA, "cudaFuncSetAttribute(tc::gemm_kernel): %s", cudaGetErrorString(e));
@@ -1338,7 +1395,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -1358,6 +1415,8 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (value != 0 && value != 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ENCODER_PRECISION: 0 = fp16x2 tcgen05 / fp32, 2 = float64");
             h->opt_enc_prec = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_HEAD_FP64: h->opt_head64 = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_SKINNY_GEMM: h->opt_skinny = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_ATTN_LONG: h->opt_attn_long = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ENCODE_ONLY: h->opt_encode_only = value ? 1 : 0; h->encoded = false; return FFB_OK;
         case FFB_OPT_FORCE_F:
             if (value < 0 || value > h->cfg.num_lines) return fail(h, FFB_ERR_ARG, "FFB_OPT_FORCE_F must be in [0, num_lines]");
@@ -2062,6 +2121,45 @@ int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, c
             if (cudaStreamSynchronize(s) != cudaSuccess && rc == FFB_OK) rc = fail(h, FFB_ERR_CUDA, "op_attention: %s", cudaGetErrorString(cudaGetLastError()));
         }
         qh.release(); kh.release(); vh.release();
+        return rc;
+    }
+    if (kind == 7) {
+        // tcgen05 streaming kernel (attn_l.cuh): G groups of nq == nk rows, queries = keys rows of the group (encoder self-attention)
+        if (nq != nk) return fail(h, FFB_ERR_UNSUPPORTED, "op_attention kind 7: needs nq == nk");
+        if (ldq != H * 64 || ldk % 32 || ldk < H * 64) return fail(h, FFB_ERR_ARG, "op_attention kind 7: ldq must be H*64, ldk a multiple of 32");
+        const size_t Rk = (size_t)G * nk;
+        const int tiles_g = (nk + 2 * al::BQ - 1) / (2 * al::BQ);          // pairs of 128-query tiles per group
+        std::vector<int> tile_off(G + 1), row_off(G), vlen(G);
+        for (int g = 0; g <= G; ++g) tile_off[g] = g * tiles_g;
+        for (int g = 0; g < G; ++g) { row_off[g] = g * nk; vlen[g] = nk; }
+        DevBuf qh, kh, vh, os, meta;
+        int rc = FFB_OK;
+        do {
+            if (qh.ensure(2 * Rk * ldq * 2) != cudaSuccess || kh.ensure(2 * Rk * ldk * 2) != cudaSuccess || vh.ensure(2 * Rk * ldk * 2) != cudaSuccess ||
+                os.ensure(2 * Rk * ldq * 2) != cudaSuccess || meta.ensure((3 * (size_t)G + 1) * sizeof(int)) != cudaSuccess) {
+                rc = fail(h, FFB_ERR_CUDA, "op_attention: out of device memory"); break; }
+            int* m = meta.as<int>();
+            cudaMemcpyAsync(m, tile_off.data(), (G + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(m + G + 1, row_off.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(m + 2 * G + 1, vlen.data(), G * sizeof(int), cudaMemcpyHostToDevice, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention: upload failed"); break; }
+            split_array_kernel<<<grid1d((long long)Rk * ldq / 4), 256, 0, s>>>(q, qh.as<uint16_t>(), (long long)Rk * ldq / 4, 1.0f, 2);
+            split_array_kernel<<<grid1d((long long)Rk * ldk / 4), 256, 0, s>>>(k, kh.as<uint16_t>(), (long long)Rk * ldk / 4, 1.0f, 2);
+            split_array_kernel<<<grid1d((long long)Rk * ldk / 4), 256, 0, s>>>(v, vh.as<uint16_t>(), (long long)Rk * ldk / 4, 1.0f, 2);
+            h->launches += 3;
+            CUtensorMap mq, mk, mv;
+            if ((rc = encode_rows_map(h, &mq, qh.p, ldq, Rk, 32, al::BQ, CU_TENSOR_MAP_SWIZZLE_64B)) != FFB_OK) break;
+            if ((rc = encode_rows_map(h, &mk, kh.p, ldk, Rk, 32, al::KC, CU_TENSOR_MAP_SWIZZLE_64B)) != FFB_OK) break;
+            if ((rc = encode_rows_map(h, &mv, vh.p, ldk, Rk, 64, al::KC, CU_TENSOR_MAP_SWIZZLE_128B)) != FFB_OK) break;
+            al::Params lp{};
+            lp.tile_off = m; lp.row_off = m + G + 1; lp.vlen = m + 2 * G + 1; lp.n_groups = G;
+            lp.Os = os.as<uint16_t>(); lp.os_stride = (long long)Rk * ldq; lp.ldo = ldq;
+            if ((rc = launch_attn_long(h, mq, mk, mv, lp, (long long)G * tiles_g, (double)G * nq * nk, PC_ATTN_TILED, s)) != FFB_OK) break;
+            sum_split_kernel<<<grid1d((long long)Rk * ldq), 256, 0, s>>>(os.as<uint16_t>(), (long long)Rk * ldq, out, (long long)Rk * ldq, 2);
+            h->launches++;
+            if (cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(h, FFB_ERR_CUDA, "op_attention kind 7: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        } while (0);
+        qh.release(); kh.release(); vh.release(); os.release(); meta.release();
         return rc;
     }
     if (kind == 5 || kind == 6) {

@@ -51,22 +51,31 @@ constexpr int TMEM_COLS = 512;
 
 // V: pipeline variant of the fp16x2 kernel.  0 = 4 operand stages + one 4 KB epilogue staging buffer per warp;
 //    1 = 3 operand stages + two staging buffers per warp (the next 32x32 block is formatted while TMA still reads the previous one)
-template <int NS, int V = 0> struct Cfg {
+// BNT: output-tile width.  256 (default) is the throughput shape; 64 is the "skinny" shape for small M (decode steps of one wireframe,
+//      seq2seq): a 128 x 256 tile costs the tensor pipe 128 rows of work however few rows exist, and with M <= 128 only N / 256 CTAs would
+//      run; 64-column tiles put 4x as many SMs on the weight stream and cut the per-tile MMA time 4x (fp16x2 only).
+template <int NS, int V = 0, int BNT = BN> struct Cfg {
     static_assert(NS == 2 || NS == 3, "NS: 2 = fp16x2, 3 = bf16x3");
     static_assert(V == 0 || (V == 1 && NS == 2), "variant 1 exists for fp16x2 only");
-    static constexpr int STAGES = (NS == 2) ? (V == 1 ? 3 : 4) : 3;
+    static_assert(BNT == 256 || (BNT == 64 && NS == 2), "tile width: 256, or 64 for fp16x2");
+    static constexpr int B_TILE = BNT * BK * 2;
+    static constexpr int STAGES = (BNT == 64) ? 6 : (NS == 2) ? (V == 1 ? 3 : 4) : 3;
     static constexpr int EPI_BUFS = (V == 1) ? 2 : 1;
-    static constexpr int DRAIN_KB = (NS == 2) ? 4 : 2;            // k-blocks accumulated in TMEM per drain (24 MMAs either way)
+#ifndef FFB_DRAIN_KB
+#define FFB_DRAIN_KB 4
+#endif
+    static constexpr int DRAIN_KB = (NS == 2) ? FFB_DRAIN_KB : 2;  // k-blocks accumulated in TMEM per drain (24 MMAs either way by default)
     static constexpr int NPROD = (NS == 2) ? 3 : 6;
-    static constexpr int STAGE_BYTES = NS * (A_TILE_BYTES + B_TILE_BYTES);            // 48 KB / 72 KB
+    static constexpr int STAGE_BYTES = NS * (A_TILE_BYTES + B_TILE);                  // 48 KB / 72 KB (24 KB for the 64-column tile)
     static constexpr bool STAGED_EPI = (NS == 2);
     static constexpr int EPI_BYTES = STAGED_EPI ? EPI_BUFS * EPI_WARPS * 32 * 32 * 4 : 0;        // 32 / 64 KB
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     // kind::f16 instruction descriptor: D=f32 (bit 4), A/B format (0 = f16, 1 = bf16) at bits 7/10, K-major, N=256, M=128
     static constexpr uint32_t FMT = (NS == 2) ? 0u : 1u;
-    static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
-static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<2, 1>::SMEM_BYTES <= 232448 && Cfg<3>::SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+static_assert(Cfg<2>::SMEM_BYTES <= 232448 && Cfg<2, 1>::SMEM_BYTES <= 232448 && Cfg<3>::SMEM_BYTES <= 232448 && Cfg<2, 1, 64>::SMEM_BYTES <= 232448,
+              "exceeds 227 KB of shared memory");
 
 struct Params {
     int M, N, K;                 // N % 256 == 0, K % 32 == 0
@@ -172,12 +181,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int NS, int V = 0>
+template <int NS, int V = 0, int BNT = BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapC, const Params p) {
-    using C_ = Cfg<NS, V>;
+    using C_ = Cfg<NS, V, BNT>;
     constexpr int STAGES = C_::STAGES, DRAIN_KB = C_::DRAIN_KB, STAGE_BYTES = C_::STAGE_BYTES;
+    constexpr int HALF = BNT / 2;                 // columns per epilogue warp (128 or 32)
+    constexpr int NJ = HALF / 32;                 // 32-column blocks per epilogue warp (4 or 1)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // programmatic dependent launch (see FFB_PDL_SYNC): the next kernel's CTAs
                                                                          // may be scheduled as ours retire
     // everything up to the first read of global memory (barrier init, TMEM allocation) overlaps the previous kernel's tail
@@ -197,7 +208,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BN, k_chunks = p.K / BK;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BNT, k_chunks = p.K / BK;
     const int num_tiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
@@ -235,7 +246,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
                     for (int s = 0; s < NS; ++s) tma_load_3d(sa + s * A_TILE_BYTES, mapA, full_bar(stage), kc * BK, mt * BM, s);
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) tma_load_3d(sb + s * B_TILE_BYTES, &mapW, full_bar(stage), kc * BK, nt * BN + p.n_off, s);
+                    for (int s = 0; s < NS; ++s) tma_load_3d(sb + s * C_::B_TILE, &mapW, full_bar(stage), kc * BK, nt * BNT + p.n_off, s);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -252,7 +263,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     const uint32_t sb = sa + NS * A_TILE_BYTES;
-                    const uint32_t d = tmem_base + buf * BN;
+                    const uint32_t d = tmem_base + buf * BNT;
                     // correction products first (small), dominant A0.W0 last
                     constexpr int pa3[6] = {0, 1, 1, 0, 2, 0}, pb3[6] = {1, 0, 1, 2, 0, 0};
                     constexpr int pa2[3] = {1, 0, 0}, pb2[3] = {0, 1, 0};
@@ -261,7 +272,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     for (int q = 0; q < C_::NPROD; ++q) {
                         const int ia = (NS == 2) ? pa2[q % 3] : pa3[q], ib = (NS == 2) ? pb2[q % 3] : pb3[q];
                         const uint64_t da = make_smem_desc(sa + ia * A_TILE_BYTES);
-                        const uint64_t db = make_smem_desc(sb + ib * B_TILE_BYTES);
+                        const uint64_t db = make_smem_desc(sb + ib * C_::B_TILE);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {               // +32 B per K=16 step inside the 64-byte swizzle row
                             umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), C_::IDESC, acc);
@@ -279,10 +290,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int e = warp - EPI_WARP0;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int hcol = e >> 2;                      // which 128-column half of the tile
+        const int hcol = e >> 2;                      // which half of the tile's columns
         float* stg0 = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base)) + e * 1024 * C_::EPI_BUFS;   // 32x32 floats per warp and buffer (NS = 2)
         uint32_t n_blk = 0;                           // 32x32 blocks handed to TMA so far (selects the staging buffer)
-        float acc[128];
+        float acc[HALF];
         uint32_t c = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int mt = t / n_tiles, nt = t % n_tiles;
@@ -291,33 +302,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                 const uint32_t buf = c & 1u;
                 mbar_wait(tfull_bar(buf), (c >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hcol * 128;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BNT + hcol * HALF;
+                if constexpr (NJ == 4) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {                  // two 32-column loads in flight per wait
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(taddr + j * 64, v0);
-                    tmem_ld32(taddr + j * 64 + 32, v1);
+                    for (int j = 0; j < 2; ++j) {                  // two 32-column loads in flight per wait
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(taddr + j * 64, v0);
+                        tmem_ld32(taddr + j * 64 + 32, v1);
+                        tmem_ld_wait();
+                        if (dr == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { acc[j * 64 + i] = __uint_as_float(v0[i]); acc[j * 64 + 32 + i] = __uint_as_float(v1[i]); }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { acc[j * 64 + i] += __uint_as_float(v0[i]); acc[j * 64 + 32 + i] += __uint_as_float(v1[i]); }
+                        }
+                    }
+                } else {
+                    uint32_t v0[32];
+                    tmem_ld32(taddr, v0);
                     tmem_ld_wait();
                     if (dr == 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { acc[j * 64 + i] = __uint_as_float(v0[i]); acc[j * 64 + 32 + i] = __uint_as_float(v1[i]); }
+                        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v0[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { acc[j * 64 + i] += __uint_as_float(v0[i]); acc[j * 64 + 32 + i] += __uint_as_float(v1[i]); }
+                        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v0[i]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
             }
-            const int col0 = nt * BN + hcol * 128 + p.n_off;
+            const int col0 = nt * BNT + hcol * HALF + p.n_off;
             const int row0 = mt * BM + q * 32;
             if constexpr (C_::STAGED_EPI) {
                 // ---- coalesced epilogue: 32x32 blocks through a swizzled per-warp smem buffer; in the read phase a lane owns one column ----
                 const bool tma_out = p.tma_out && (p.C != nullptr);
                 const bool tma_cs = p.tma_out && (p.C == nullptr) && (p.Cs != nullptr);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {                 // (fully unrolled: acc[] must stay in registers)
+                for (int j = 0; j < NJ; ++j) {                // (fully unrolled: acc[] must stay in registers)
                     const uint32_t sbuf = (C_::EPI_BUFS == 2) ? (n_blk & 1u) : 0u;
                     float* stg = stg0 + sbuf * 1024;
                     const uint32_t stg_s = epi_base + ((uint32_t)e * C_::EPI_BUFS + sbuf) * 4096u;
@@ -454,7 +478,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         float* crow = p.C + (size_t)row * p.ldc + col0;
                         const float* rrow = p.R ? p.R + (size_t)row * p.ldr + col0 : nullptr;
 #pragma unroll
-                        for (int i = 0; i < 128; i += 4) {
+                        for (int i = 0; i < HALF; i += 4) {
                             float4 v = make_float4(acc[i] * p.out_scale, acc[i + 1] * p.out_scale, acc[i + 2] * p.out_scale, acc[i + 3] * p.out_scale);
                             if (p.bias) {
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
@@ -471,7 +495,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                     if (p.Cs != nullptr) {
                         __nv_bfloat16* s0 = reinterpret_cast<__nv_bfloat16*>(p.Cs) + (size_t)row * p.ldcs + col0;
 #pragma unroll
-                        for (int i = 0; i < 128; i += 8) {
+                        for (int i = 0; i < HALF; i += 8) {
                             __align__(16) __nv_bfloat16 o0[8], o1[8], o2[8];
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {

@@ -20,7 +20,7 @@ HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
-FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL, FFB_OPT_POINTER_BATCHED, FFB_OPT_BEAM, FFB_OPT_ENCODER_PRECISION, FFB_OPT_HEAD_FP64, FFB_OPT_FORCE_F, FFB_OPT_ENCODE_ONLY = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
+FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL, FFB_OPT_POINTER_BATCHED, FFB_OPT_BEAM, FFB_OPT_ENCODER_PRECISION, FFB_OPT_HEAD_FP64, FFB_OPT_FORCE_F, FFB_OPT_ENCODE_ONLY, FFB_OPT_ATTN_LONG, FFB_OPT_SKINNY_GEMM = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
 PROFILE_CLASSES = ("linear", "layernorm", "attn_rows", "attn_tiled", "pointer", "other", "linear_tc")
 
 
@@ -90,7 +90,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise FFBError("nvcc not found: cannot build libffb200.so (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("FFB_NVCC_EXTRA", "").split()          # tuning experiments only (e.g. -DFFB_DRAIN_KB=8)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise FFBError("nvcc failed:\n" + res.stdout + res.stderr)

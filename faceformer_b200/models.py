@@ -108,6 +108,7 @@ class _SurfaceFormerB200Base(nn.Module):
         self._engines = {}
         self._weights_version = 0
         self.last_steps = None
+        self.beam_width = 1           # > 1: beam search (parallel model; oracle/beam_oracle.py) -- 1 is the reference's greedy loop
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
 
     # -- weights -----------------------------------------------------------------------------
@@ -143,6 +144,9 @@ class _SurfaceFormerB200Base(nn.Module):
         eng = self.engine(coords.device.index if coords.device.index is not None else torch.cuda.current_device())
         num_input = inputs.get("num_input") if self.MODE == MODE_PARALLEL else None
         with torch.cuda.device(coords.device):
+            if self.MODE == MODE_PARALLEL:
+                from .lib import FFB_OPT_BEAM
+                eng.set_option(FFB_OPT_BEAM, int(self.beam_width))
             predict, steps = eng.forward_eval(coords.flatten(2), inputs["input_mask"], num_input, want_steps=True)
             self.last_steps = steps
             if self.MODE == MODE_SEQ2SEQ:                   # model.py:216-217
@@ -172,6 +176,12 @@ class _SurfaceFormerB200Base(nn.Module):
         """inputs['predict'] + raw `edges` lists -> per wireframe the list of (face_type, loops) that parse_parallel_faces
         (trainer.py:196-206) followed by filter_faces_by_encloseness (post_processing.py:8-20) return for the predictions."""
         return self._current_engine().parse_faces(predict, wireframes, tol=tol, check_enclosed=check_enclosed)
+
+
+    def face_accuracy(self, outputs, raw_datas, is_coedge: bool = True, tol: float = 2e-4):
+        """Trainer.face_accuracy (trainer.py:210-300) on the dict forward() returned: per-sequence parsing on the GPU, set logic on the host."""
+        from . import metrics
+        return metrics.face_accuracy(self._current_engine(), outputs, raw_datas, is_coedge=is_coedge, tol=tol)
 
 
 class SurfaceFormer_Parallel_B200(_SurfaceFormerB200Base):

@@ -105,6 +105,14 @@ int ffb_stop_exchange_export(ffb_handle* h, void* ipc_handle_out /* 64 bytes */)
 int ffb_stop_exchange_connect(ffb_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
 int ffb_stop_exchange_disconnect(ffb_handle* h);
 
+/* 1 (default): in the tensor-core encoder, self-attention over more than 256 keys per wireframe (or more than 255 wireframes) runs on
+ * the tcgen05 key-streaming kernel (attn_l.cuh: 64-key blocks, exact two-pass softmax); 0 = the mma.sync kernel (attn_h.cuh). */
+enum { FFB_OPT_ATTN_LONG = 20 };
+
+/* 1 (default): fp16x2 GEMMs with at most num_SMs / 2 output tiles of 128 x 256 (small M: one wireframe per batch, seq2seq) use
+ * 128 x 64 tiles instead: 4x as many CTAs stream the weights and the per-tile tensor time drops 4x.  0 = always 128 x 256. */
+enum { FFB_OPT_SKINNY_GEMM = 21 };
+
 /* 1: ffb_encode computes the encoder memory only (embedding, encoder layers, final norm; ffb_get_memory reads it) -- no decode
  * workspaces are sized, the cross-attention K / V cache and the folded pointer head are skipped and ffb_decode_greedy is refused.
  * The encoder-only throughput workload of BASELINE.json configs[4] (2048-edge wireframes, batch 256). */
@@ -295,7 +303,8 @@ int ffb_op_layernorm(ffb_handle* h, const float* x, const float* gamma, const fl
 /* Multi-head attention core (softmax(q k^T / 8) v) for G equal-sized groups:
  * q [G*nq, ldq], k/v [G*nk, ldk] with head h in columns [64h, 64h+64); out [G*nq, H*64].
  * kind 0 = SIMT warp-per-row kernel, 1 = SIMT tiled kernel, 2 = 3xTF32 mma.sync kernel, 3 = fp16x2 mma.sync kernel, 4 = fp16x2 kernel
- * with pre-split inputs (attn_h.cuh; the hook splits q/k/v first; q/k/v must be contiguous [rows, ld] arrays).  */
+ * with pre-split inputs (attn_h.cuh; the hook splits q/k/v first; q/k/v must be contiguous [rows, ld] arrays), 5 / 6 = tcgen05 kernel
+ * (attn_x.cuh) in CROSS / SELF mode, 7 = tcgen05 key-streaming kernel (attn_l.cuh; nq == nk, any number of keys).  */
 int ffb_op_attention(ffb_handle* h, int32_t kind, const float* q, int32_t ldq, const float* k,
                      const float* v, int32_t ldk, float* out, int32_t G, int32_t nq, int32_t nk,
                      int32_t H, void* stream);

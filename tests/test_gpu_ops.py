@@ -138,3 +138,18 @@ def test_attention_tcgen05_self(eng, G, P):
     got = eng.op_attention(6, _t(q), _t(k), _t(v), G, P, P).cpu().numpy()
     want = _attn_ref(q, k, v, G, P, P, H)
     assert np.max(np.abs(got - want)) <= 2e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("G,n", [(1, 1), (3, 7), (2, 63), (3, 64), (2, 65), (5, 129), (2, 300), (3, 516), (1, 2052), (40, 220), (2, 1000)])
+def test_attention_tcgen05_long(eng, G, n):
+    """attn_long_kernel (attn_l.cuh): encoder self-attention with any number of keys -- K / V stream through shared memory in 64-key
+    blocks, exact two-pass softmax, O drained every 8 blocks.  2052 keys = the 2048-edge wireframes of BASELINE.json configs[4]."""
+    H = OURS.num_head
+    rng = np.random.default_rng(G * 100 + n + 4)
+    q = (rng.normal(size=(G * n, H * 64)) * 1.5).astype(np.float32)
+    k = (rng.normal(size=(G * n, H * 64)) * 1.5).astype(np.float32)
+    v = (rng.normal(size=(G * n, H * 64)) * 1.5).astype(np.float32)
+    got = eng.op_attention(7, _t(q), _t(k), _t(v), G, n, n).cpu().numpy()
+    want = _attn_ref(q, k, v, G, n, n, H)
+    assert np.max(np.abs(got - want)) <= 2e-5

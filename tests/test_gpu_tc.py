@@ -200,7 +200,10 @@ def test_encoder_modes_match_the_oracle_encoder():
         info = e.encode(coords, mask, ni)
         prof = e.profile_read()
         assert info["R"] >= 2048
-        assert (prof["linear_tc"]["launches"] > 0) == bool(enc_tc and prec == 0)
+        if prec == 0:
+            assert (prof["linear_tc"]["launches"] > 0) == bool(enc_tc)
+        else:       # float64 encoder; on a batch this large only the two cross-attention K / V projections run on the tensor cores
+            assert prof["linear_tc"]["launches"] == 2
         mems.append(e.get_memory().cpu().numpy())
         assert e.fp16_fallbacks() == 0
         e.close()
