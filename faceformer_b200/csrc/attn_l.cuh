@@ -21,7 +21,9 @@
 // One persistent CTA per SM walks a contiguous range of work items.  Roles (384 threads):
 //   warp 0      TMA producer: both Q tiles once per item; K blocks twice (pass 1: hi halves only) through a 3-slot ring; V blocks
 //               through a 2-slot ring
-//   warp 1      TMEM allocator + the MMA issuer (one thread): per block S for both tiles, then O += P V of the previous block
+//   warp 1      TMEM allocator + the S issuer (one thread): per block S for both tiles, up to two blocks ahead of the softmax
+//   warp 2      the P V issuer (one thread): O += P V as the softmax publishes P; its waits never hold back the S issuer
+//               (with ONE issuer thread the softmax warps spent 40 % of their time waiting for S: profiles/ncu_attn_long_r2_summary.md)
 //   warps 4-7   softmax + epilogue of tile 0, warps 8-11 of tile 1: one query row per thread (TMEM lane = row)
 // TMEM: per tile two S buffers of 64 columns and one O of 64 columns.
 #pragma once
@@ -152,10 +154,10 @@ attn_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===== MMA issuer =====
+            // ===== S issuer: runs ahead of the softmax by up to two blocks (two S buffers per tile) =====
             constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};            // (lo,hi), (hi,lo), (hi,hi): small products first
-            const uint32_t idesc_s = idesc_f16(KB, 0), idesc_o = idesc_f16(64, 1);
-            uint32_t nk_use = 0, nv_use = 0, ns = 0, npv = 0, n_og = 0;    // K blocks, V blocks, S uses (per tile), P uses (per tile), O drain groups
+            const uint32_t idesc_s = idesc_f16(KB, 0);
+            uint32_t nk_use = 0, ns = 0;                                   // K blocks and S buffers (per tile) consumed
             // S of BOTH tiles against one K block; hi_only: the single product of pass 1
             auto issue_s = [&](bool hi_only) {
                 const uint32_t ks = nk_use % NKS, sb = ns & 1u;
@@ -189,40 +191,48 @@ attn_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const int nb = (it.nk + KB - 1) / KB;
                 mbar_wait(q_full, (uint32_t)j & 1u);
                 for (int b = 0; b < nb; ++b) issue_s(true);                // pass 1
-                for (int b = 0; b <= nb; ++b) {                            // pass 2: S(b) of both tiles, then O += P(b-1) V(b-1) of both
-                    if (b < nb) issue_s(false);
-                    if (b == nb) umma_commit(q_empty);                     // every S product of this item has been issued
-                    if (b > 0) {
-                        const int bb = b - 1;
-                        const uint32_t vs = nv_use % NVS;
-                        const bool first = (bb % DRAIN) == 0;              // first block of a drain group: O restarts from zero
-                        const bool last = (bb % DRAIN) == DRAIN - 1 || bb == nb - 1;
-                        mbar_wait(v_full(vs), (nv_use / NVS) & 1u);
+                for (int b = 0; b < nb; ++b) issue_s(false);               // pass 2
+                umma_commit(q_empty);                                      // every S product of this item has been issued
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ===== P V issuer: O += P(b) V(b) as the softmax warpgroups publish P (its waits never hold back the S issuer) =====
+            constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+            const uint32_t idesc_o = idesc_f16(64, 1);
+            uint32_t nv_use = 0, npv = 0, n_og = 0;                        // V blocks, P uses (per tile), O drain groups consumed
+            for (int j = 0; j < n_items; ++j) {
+                Item it; get_item(p, item0 + j, it);
+                const int nb = (it.nk + KB - 1) / KB;
+                for (int bb = 0; bb < nb; ++bb) {
+                    const uint32_t vs = nv_use % NVS;
+                    const bool first = (bb % DRAIN) == 0;                  // first block of a drain group: O restarts from zero
+                    const bool last = (bb % DRAIN) == DRAIN - 1 || bb == nb - 1;
+                    mbar_wait(v_full(vs), (nv_use / NVS) & 1u);
 #pragma unroll
-                        for (uint32_t w = 0; w < 2; ++w) {
-                            mbar_wait(p_full(w), npv & 1u);
-                            if (first) mbar_wait(o_empty(w), (n_og & 1u) ^ 1u);   // the softmax threads have read the previous group's O
-                            tc_fence_after();
-                            const uint32_t d_o = tmem_base + w * 256u + 128u;
-                            uint32_t acc = first ? 0u : 1u;
+                    for (uint32_t w = 0; w < 2; ++w) {
+                        mbar_wait(p_full(w), npv & 1u);
+                        if (first) mbar_wait(o_empty(w), (n_og & 1u) ^ 1u);       // the softmax threads have read the previous group's O
+                        tc_fence_after();
+                        const uint32_t d_o = tmem_base + w * 256u + 128u;
+                        uint32_t acc = first ? 0u : 1u;
 #pragma unroll
-                            for (int c = 0; c < 2; ++c)
+                        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                                for (int s2 = 0; s2 < 2; ++s2)
+                            for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-                                    for (int q = 0; q < 3; ++q) {
-                                        const uint64_t da = make_smem_desc(p_s + w * P_BUF + (pa[q] * 2 + c) * P_TILE) + (uint64_t)(2 * s2);
-                                        const uint64_t db = make_smem_desc_mn128(v_s + vs * V_SLOT + (pb[q] * 2 + c) * V_TILE + s2 * 2048u);
-                                        umma_bf16(d_o, da, db, idesc_o, acc);
-                                        acc = 1;
-                                    }
-                            umma_commit(p_empty(w));
-                            if (w == 1) umma_commit(v_empty(vs));
-                            if (last) umma_commit(o_full(w));
-                        }
-                        ++npv; ++nv_use;
-                        if (last) ++n_og;
+                                for (int q = 0; q < 3; ++q) {
+                                    const uint64_t da = make_smem_desc(p_s + w * P_BUF + (pa[q] * 2 + c) * P_TILE) + (uint64_t)(2 * s2);
+                                    const uint64_t db = make_smem_desc_mn128(v_s + vs * V_SLOT + (pb[q] * 2 + c) * V_TILE + s2 * 2048u);
+                                    umma_bf16(d_o, da, db, idesc_o, acc);
+                                    acc = 1;
+                                }
+                        umma_commit(p_empty(w));
+                        if (w == 1) umma_commit(v_empty(vs));
+                        if (last) umma_commit(o_full(w));
                     }
+                    ++npv; ++nv_use;
+                    if (last) ++n_og;
                 }
             }
         }
