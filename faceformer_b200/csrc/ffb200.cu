@@ -157,6 +157,7 @@ struct ffb_handle {
         std::vector<EncTcW> enc;                  // encoder layers
         CUtensorMap ck, cv; float s_ck = 1.f, s_cv = 1.f;   // packed cross-attention K / V projections of all decoder layers [Ld*E, E]
         CUtensorMap proj; float s_proj = 1.f;
+        CUtensorMap emb2; float s_emb2 = 1.f;     // second linear of the value embedding (embedding.py:17), E x E
         CUtensorMap m_x2, m_x2p, m_att, m_h;      // activation-operand maps (re-encoded per batch)
     };
     TcSet tcs[2];                                 // [fmt - 2]
@@ -644,7 +645,7 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
     if (!T.ready) {
         const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
         const size_t Le = h->Le, per_enc = 3 * E * E + E * E + FF * E + E * FF;
-        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E + Le * per_enc + 2 * Ld * E * E) * 2));
+        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E + Le * per_enc + 2 * Ld * E * E + E * E) * 2));
         uint16_t* wp = T.wsplit.as<uint16_t>();
         T.layers.resize(Ld);
         for (size_t l = 0; l < Ld; ++l) {
@@ -668,7 +669,8 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
             FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
         }
         FFB_TRY(split_weight(h, h->w.ckw, wp, Ld * E, E, &T.ck, fmt, &T.s_ck, s)); wp += fmt * Ld * E * E;
-        FFB_TRY(split_weight(h, h->w.cvw, wp, Ld * E, E, &T.cv, fmt, &T.s_cv, s));
+        FFB_TRY(split_weight(h, h->w.cvw, wp, Ld * E, E, &T.cv, fmt, &T.s_cv, s)); wp += fmt * Ld * E * E;
+        FFB_TRY(split_weight(h, h->w.e2w, wp, E, E, &T.emb2, fmt, &T.s_emb2, s));
         T.ready = true;
     }
     if (h->cap_rows > 0) {
@@ -1026,19 +1028,35 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
     const int* row_off = h->d_row_off.as<int>(); const int* vlen = h->d_vlen.as<int>();
     const int* pos_idx = h->d_pos_idx.as<int>();
 
-    // value embedding (embedding.py:34): relu(coords W0^T + b0) W2^T + b2 on the valid edges only
-    { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
-      l.C = hb; l.ldc = E; l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
-    { Lin l; l.A = hb; l.lda = E; l.W = w.e2w; l.ldw = E; l.bias = w.e2b; l.C = x; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>();
-      l.M = Re; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
-    token_rows_kernel<<<grid1d((long long)N * h->cfg.num_token * (E / 4)), 256, 0, s>>>(w.tok_table, row_off, x, N, h->cfg.num_token, E);
-    h->launches++; CU(h, cudaGetLastError());
-
     // Encoder layers + cross K / V projections on the tcgen05 pipeline (fp16x2 GEMMs, tcgen05 attention) when the batch is large
-    // enough and every wireframe has <= 256 memory rows; otherwise fp32 SIMT GEMMs + the 3xTF32 mma.sync attention kernel.
+    // enough; otherwise fp32 SIMT GEMMs + the 3xTF32 mma.sync attention kernel.
     const ffb_handle::TcSet& TS = h->tcs[0];
     const bool enc_tc = allow_tc && h->opt_enc_tc && h->half_pipe && h->tc_fmt == 2 && TS.ready &&
                         (int)TS.enc.size() == h->Le && (h->opt_tc == 2 || R >= TC_MIN_ROWS);
+    // value embedding (embedding.py:34): relu(coords W0^T + b0) W2^T + b2 on the valid edges only
+    if (enc_tc) {
+        // first linear (K = in_dim, 100: off the tensor-core grid) on the FFMA kernel, written at the edges' memory rows; the E x E second
+        // linear on the tcgen05 GEMM over ALL memory rows (the 4 token rows per wireframe compute don't-care values that token_rows_kernel
+        // overwrites): 83 % of the embedding's FLOPs leave the FFMA pipe
+        CU(h, cudaMemsetAsync(hb, 0, (size_t)R * E * sizeof(float), s));
+        { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
+          l.C = hb; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>(); l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        h->ovf_slot = 6;
+        CU(h, cudaMemsetAsync(h->state.as<int>() + 6, 0, sizeof(int), s));
+        split_rows_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(hb, h->a_x2.as<uint16_t>(), h->cap_rows * E, R, E, 2, ovf_ptr(h));
+        h->launches++; CU(h, cudaGetLastError());
+        { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.emb2; l.w_scale = TS.s_emb2; l.bias = w.e2b; l.C = x; l.ldc = E; l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = E;
+          FFB_TRY(launch_tc(h, l, nullptr, s)); }
+        h->ovf_slot = 4;
+    } else {
+        { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
+          l.C = hb; l.ldc = E; l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        { Lin l; l.A = hb; l.lda = E; l.W = w.e2w; l.ldw = E; l.bias = w.e2b; l.C = x; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>();
+          l.M = Re; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    }
+    token_rows_kernel<<<grid1d((long long)N * h->cfg.num_token * (E / 4)), 256, 0, s>>>(w.tok_table, row_off, x, N, h->cfg.num_token, E);
+    h->launches++; CU(h, cudaGetLastError());
+
     const bool enc_ax = h->attn_x_ok && (h->opt_attn_x & 1);             // tcgen05 attention needs <= 256 rows per wireframe
     h->enc_used_tc = enc_tc;
     const int LdE = h->Ld * E;
@@ -1047,8 +1065,7 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
         uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>(); uint16_t* aqkv = h->a_qkv.as<uint16_t>();
         const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;
         h->ovf_slot = 6;                                                  // an fp16-range overflow here makes ffb_encode redo the encoder in fp32
-        CU(h, cudaMemsetAsync(h->state.as<int>() + 6, 0, sizeof(int), s));
-        int rc = FFB_OK;
+        int rc = FFB_OK;                                                  // (state[6] was cleared before the embedding above)
         for (int li = 0; li < h->Le && rc == FFB_OK; ++li) {              // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
             const EncLayerW& L = w.enc[li];
             const ffb_handle::EncTcW& Tw = TS.enc[li];

@@ -394,6 +394,16 @@ __global__ void __launch_bounds__(256) split_pos_kernel(const float* __restrict_
     }
 }
 
+// operand formatting of a plain fp32 [M, E] array: out <- split(x) with the splits `split_stride` elements apart
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, long long split_stride,
+                                                         int M, int E, int fmt, int* ovf) {
+    const long long n4 = (long long)M * (E / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+        store_split4(out + i * 4, split_stride, v, fmt, ovf);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // featurize: edge polylines -> [N, num_lines, P, 2] float32 + padding mask (datasets/data_para.py:8-25,59-68).
 //   2-point edge: P points on the segment, x = x1 + (x2 - x1) * t with t = linspace(0, 1, P), evaluated in float64 exactly as
