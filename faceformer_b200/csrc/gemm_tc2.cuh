@@ -35,9 +35,15 @@ using tc::BK;
 constexpr int BM = 128, BN = 256;                    // per CTA: 128 rows x 256 columns of the 256 x 256 pair tile
 constexpr int A_TILE_BYTES = BM * BK * 2;            // 8 KB per split
 constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;      // 8 KB per split: this CTA's 128 of the 256 W rows
-constexpr int STAGES = 4, DRAIN_KB = 4;
+#ifndef FFB_TC2_STAGES
+#define FFB_TC2_STAGES 4
+#endif
+#ifndef FFB_TC2_EPI_BUFS
+#define FFB_TC2_EPI_BUFS 2
+#endif
+constexpr int STAGES = FFB_TC2_STAGES, DRAIN_KB = 4;
 constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + B_HALF_BYTES);        // 32 KB
-constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_BUFS = 2, NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_BUFS = FFB_TC2_EPI_BUFS, NUM_THREADS = 384;
 constexpr int EPI_BYTES = EPI_BUFS * EPI_WARPS * 4096;                // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
@@ -219,7 +225,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             const int row0 = mt * 2 * BM + (int)rank * BM + q * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t sbuf = n_blk & 1u;
+                const uint32_t sbuf = (EPI_BUFS == 2) ? (n_blk & 1u) : 0u;
                 float* stg = stg0 + sbuf * 1024;
                 const uint32_t stg_s = epi_base + ((uint32_t)e * EPI_BUFS + sbuf) * 4096u;
                 if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();
