@@ -255,12 +255,13 @@ int ffb_phase_times(ffb_handle* h, float* out_ms, int32_t n);
 enum { FFB_OPT_PROFILE = 4, FFB_PROFILE_CLASSES = 7 };
 int ffb_profile_read(ffb_handle* h, int32_t n_classes, float* ms, double* flops, int64_t* launches);
 
-/* Tensor-core path selection for the decode-step linear layers (gemm_tc.cuh: bf16x3 split-precision tcgen05 GEMM):
- * 0 = off (fp32 SIMT everywhere), 1 = auto (default: steps with >= 2048 token rows), 2 = force (every step). */
+/* Tensor-core path selection for the decode-step linear layers (gemm_tc.cuh: split-precision tcgen05 GEMM, operand format per
+ * FFB_OPT_TC_FORMAT): 0 = off (fp32 SIMT everywhere), 1 = auto (default; since round 2 every step of a geometry on the 256 grid, the
+ * tcgen05 GEMM being faster than the SIMT kernel at every M), 2 = force (same as auto today; kept for tests). */
 enum { FFB_OPT_TENSOR_CORE = 5 };
-/* Attention core of the decode loop: 2 (default) = mma.sync m16n8k16 fp16x2 split (attn_f16.cuh; used while the GEMM operand
- * format is fp16x2, same overflow fallback), 1 = mma.sync m16n8k8 3xTF32 split (attn_mma.cuh; also what the encoder uses),
- * 0 = fp32 SIMT kernels. */
+/* Attention core of the decode loop where the tcgen05 kernels (FFB_OPT_ATTN_X) do not apply: 2 (default) = fp16x2 operands (the half
+ * pipeline: attn_h.cuh / attn_f16.cuh on mma.sync m16n8k16; same overflow fallback as the GEMM format), 1 = mma.sync m16n8k8 3xTF32
+ * split (attn_mma.cuh; also the fp32 encoder's), 0 = fp32 SIMT kernels.  Values other than 2 switch the half pipeline off. */
 enum { FFB_OPT_ATTN_MMA = 6 };
 /* Operand format of the tensor-core GEMM: 2 (default) = fp16x2 (3 MMA passes; weights pre-scaled by a power of two;
  * if an activation exceeds the fp16 range the decode is transparently re-run in format 3 and the handle stays there),
