@@ -128,6 +128,60 @@ def test_one_batch_split_over_two_ranks_equals_the_single_gpu_tensor(case):
         assert np.array_equal(merged, g["predict"])
 
 
+def _split_worker_big(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from faceformer_b200.engine import Engine
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        cfg = OURS
+        eng = Engine(cfg, MODE_PARALLEL, dev)
+        eng.load_state_dict(synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse"))
+        batch = synth.synth_batch(cfg, MODE_PARALLEL, 12, seed=21, lo=24, hi=64)
+        sd = sharding.SplitDecoder(eng)
+        sd.connect()
+        coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+        mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+        pred, steps = sd.forward_eval(coords, mask, ni, gather=False)
+        q.put((rank, pred.cpu().numpy(), steps, sharding.split_batch(batch["num_input"], world)[rank]))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_split_batch_full_size_equals_single_gpu_tensor():
+    """ours.yml geometry, 12 wireframes of 24-64 edges: the [12, F, 37] tensor of two ranks sharing the batch (F fixed globally, stop
+    predicate exchanged per step) equals the single-GPU tensor of the whole batch."""
+    from faceformer_b200.engine import Engine
+    cfg = OURS
+    eng = Engine(cfg, MODE_PARALLEL, 0)
+    eng.load_state_dict(synth.synth_state_dict(cfg, MODE_PARALLEL, 0, "diverse"))
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 12, seed=21, lo=24, hi=64)
+    want, s_want = eng.forward_eval(torch.from_numpy(batch["input"]).cuda().flatten(2), torch.from_numpy(batch["input_mask"]).cuda(),
+                                    torch.from_numpy(batch["num_input"]).cuda())
+    want = want.cpu().numpy()
+    eng.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=_split_worker_big, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    merged = np.zeros_like(want)
+    for rank, pred, steps, idx in got:
+        assert steps == s_want and pred.shape == want.shape
+        merged[idx] = pred[idx]
+    assert np.array_equal(merged, want)
+
+
 def test_full_size_properties():
     """configs/ours.yml geometry, 6 wireframes (too slow for the oracle): properties that must hold at any size."""
     from faceformer_b200.engine import Engine
