@@ -32,7 +32,10 @@
 namespace ffb {
 namespace al {
 
-constexpr int BQ = 128, KB = 64, KC = 32, NUM_THREADS = 384, NKS = 3, NVS = 2, DRAIN = 8;
+#ifndef FFB_AL_DRAIN
+#define FFB_AL_DRAIN 8
+#endif
+constexpr int BQ = 128, KB = 64, KC = 32, NUM_THREADS = 384, NKS = 3, NVS = 2, DRAIN = FFB_AL_DRAIN;
 constexpr int Q_TILE = BQ * 64;                    // one (part, head-dim chunk) Q tile: 128 rows x 64 B
 constexpr int K_TILE = KB * 64;                    // one (part, head-dim chunk) K tile of a block: 64 rows x 64 B
 constexpr int V_TILE = KC * 128;                   // 32 keys x 128 B

@@ -79,6 +79,9 @@ struct ffb_handle {
     int opt_enc_prec = 2;                         // encoder + cross K/V projections: 2 = float64 (default, enc64.cuh), 0 = fp16x2 tcgen05 / fp32 SIMT
     int opt_head64 = 1;                           // decoder.norm + project + pointer dot of the last position in float64
     DevBuf x64, y64, yp64, qkv64, att64, h64;
+    int opt_l0cache = 1;                          // decoder layer 0: q / k / v of earlier prefix positions are cached (exact), only the new position is projected
+    DevBuf qkv0_cache, a_qkv0; CUtensorMap ms_qkv0; bool l0_ok = false;
+    DevBuf e0pad, a_c; CUtensorMap ms_x2;         // W0 zero-padded to [E, 128]; coordinates as fp16x2 operand [2][cap][128]; split-store map of a_x2
     DevBuf projT, memW, hy32;                     // folded head: [W_project^T ; b_project] (E+1 x E), memory . projT^T [R, E+4], LN of the last position [B, E]
     bool enc_used_64 = false;
     DevBuf d_tile_off;                            // [N + 1] prefix of ceil(vlen / 256): work items (pairs of query tiles) of attn_l.cuh
@@ -158,6 +161,8 @@ struct ffb_handle {
         CUtensorMap ck, cv; float s_ck = 1.f, s_cv = 1.f;   // packed cross-attention K / V projections of all decoder layers [Ld*E, E]
         CUtensorMap proj; float s_proj = 1.f;
         CUtensorMap emb2; float s_emb2 = 1.f;     // second linear of the value embedding (embedding.py:17), E x E
+        CUtensorMap emb0; float s_emb0 = 1.f; bool has_emb0 = false;   // first linear (embedding.py:15), K = in_dim zero-padded to 128
+        CUtensorMap m_c;                          // activation-operand map of a_c (padded coordinates)
         CUtensorMap m_x2, m_x2p, m_att, m_h;      // activation-operand maps (re-encoded per batch)
     };
     TcSet tcs[2];                                 // [fmt - 2]
@@ -645,7 +650,7 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
     if (!T.ready) {
         const size_t per_layer = 3 * E * E + E * E + E * E + E * E + FF * E + E * FF;
         const size_t Le = h->Le, per_enc = 3 * E * E + E * E + FF * E + E * FF;
-        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E + Le * per_enc + 2 * Ld * E * E + E * E) * 2));
+        CU(h, T.wsplit.ensure((size_t)fmt * (Ld * per_layer + E * E + Le * per_enc + 2 * Ld * E * E + E * E + E * 128) * 2));
         uint16_t* wp = T.wsplit.as<uint16_t>();
         T.layers.resize(Ld);
         for (size_t l = 0; l < Ld; ++l) {
@@ -670,7 +675,9 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
         }
         FFB_TRY(split_weight(h, h->w.ckw, wp, Ld * E, E, &T.ck, fmt, &T.s_ck, s)); wp += fmt * Ld * E * E;
         FFB_TRY(split_weight(h, h->w.cvw, wp, Ld * E, E, &T.cv, fmt, &T.s_cv, s)); wp += fmt * Ld * E * E;
-        FFB_TRY(split_weight(h, h->w.e2w, wp, E, E, &T.emb2, fmt, &T.s_emb2, s));
+        FFB_TRY(split_weight(h, h->w.e2w, wp, E, E, &T.emb2, fmt, &T.s_emb2, s)); wp += fmt * E * E;
+        T.has_emb0 = (h->cfg.in_dim <= 128 && h->e0pad.p != nullptr);
+        if (T.has_emb0) FFB_TRY(split_weight(h, h->e0pad.as<float>(), wp, E, 128, &T.emb0, fmt, &T.s_emb0, s));
         T.ready = true;
     }
     if (h->cap_rows > 0) {
@@ -679,6 +686,7 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
         FFB_TRY(encode_operand_map(h, &T.m_x2p, h->a_x2p.p, E, cr, tc::BM, fmt));
         FFB_TRY(encode_operand_map(h, &T.m_att, h->a_att.p, E, cr, tc::BM, fmt));
         FFB_TRY(encode_operand_map(h, &T.m_h, h->a_h.p, FF, cr, tc::BM, fmt));
+        if (h->a_c.p) FFB_TRY(encode_operand_map(h, &T.m_c, h->a_c.p, 128, cr, tc::BM, fmt));
     }
     return FFB_OK;
 }
@@ -700,7 +708,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     const int nl = h->cfg.num_lines, nt = h->cfg.num_token;
     h->N = N;
     h->h_row_off.assign(N + 1, 0); h->h_vlen.assign(N, 0);
-    std::vector<int> nvalid(N), pos_idx, edge_src, edge_dst;
+    std::vector<int> nvalid(N);
     long long R = 0, Re = 0; int max_vlen = 0;
     for (int i = 0; i < N; ++i) {
         const uint8_t* m = mask + (size_t)i * nl;
@@ -719,12 +727,7 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
     if (R > 0x7fffffffLL / std::max(h->E * 3, h->Ld * h->E)) return fail(h, FFB_ERR_ARG, "batch too large (memory rows)");
     h->h_row_off[N] = (int)R;
     h->R = R; h->Re = Re; h->max_vlen = max_vlen;
-    pos_idx.resize(R); edge_src.resize(Re); edge_dst.resize(Re);
-    long long e = 0;
-    for (int i = 0; i < N; ++i) {
-        for (int j = 0; j < h->h_vlen[i]; ++j) pos_idx[h->h_row_off[i] + j] = j;
-        for (int j = 0; j < nvalid[i]; ++j, ++e) { edge_src[e] = i * nl + j; edge_dst[e] = h->h_row_off[i] + nt + j; }
-    }
+    // pos_idx / edge_src / edge_dst (one entry per memory row / edge) are expanded on the device from row_off and vlen (plan_rows_kernel below)
 
     std::vector<int> seq_wf, seq_first, slot_seq, seq_slot;
     h->h_seq_off.assign(N + 1, 0);
@@ -745,8 +748,9 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             F = h->opt_force_F;                                     // F = max(num_input) over the whole (split) batch, model_para.py:187
         }
         h->F = (int)F;
-        slot_seq.assign((size_t)N * F, 0);
-        for (int i = 0; i < N; ++i) {
+        const bool skip_seqs = h->opt_encode_only != 0;           // encoder-only use: no sequence will be decoded, no per-sequence plan is needed
+        if (!skip_seqs) slot_seq.assign((size_t)N * F, 0);
+        for (int i = 0; i < N && !skip_seqs; ++i) {
             const int ni = (int)num_input[i];
             h->h_seq_off[i] = (int)seq_wf.size();
             for (int a = 0; a < ni; ++a) {                         // anchors = arange(F): rows 0..n_i-1, NOT +4 (model_para.py:201)
@@ -809,9 +813,11 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
 
     FFB_TRY(upload(h, h->d_row_off, h->h_row_off, s));
     FFB_TRY(upload(h, h->d_vlen, h->h_vlen, s));
-    FFB_TRY(upload(h, h->d_pos_idx, pos_idx, s));
-    FFB_TRY(upload(h, h->d_edge_src, edge_src, s));
-    FFB_TRY(upload(h, h->d_edge_dst, edge_dst, s));
+    CU(h, h->d_pos_idx.ensure(std::max<size_t>((size_t)R, 1) * sizeof(int)));
+    CU(h, h->d_edge_src.ensure(std::max<size_t>((size_t)Re, 1) * sizeof(int)));
+    CU(h, h->d_edge_dst.ensure(std::max<size_t>((size_t)Re, 1) * sizeof(int)));
+    plan_rows_kernel<<<grid1d(R), 256, 0, s>>>(h->d_row_off.as<int>(), N, (int)R, nl, nt, h->d_pos_idx.as<int>(), h->d_edge_src.as<int>(), h->d_edge_dst.as<int>());
+    h->launches++; CU(h, cudaGetLastError());
     FFB_TRY(upload(h, h->d_seq_wf, seq_wf, s));
     FFB_TRY(upload(h, h->d_seq_first, seq_first, s));
     FFB_TRY(upload(h, h->d_seq_off, h->h_seq_off, s));
@@ -852,7 +858,9 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
         const size_t cr = (size_t)h->cap_rows;
         CU(h, h->a_x2.ensure(3 * cr * E * 2)); CU(h, h->a_x2p.ensure(3 * cr * E * 2));
         CU(h, h->a_att.ensure(3 * cr * E * 2)); CU(h, h->a_h.ensure(3 * cr * FF * 2));
+        if (h->cfg.in_dim <= 128 && h->opt_enc_prec == 0) CU(h, h->a_c.ensure(2 * cr * 128 * 2));
         FFB_TRY(prepare_tc(h, h->tc_fmt, s));
+        FFB_TRY(encode_split_store_map(h, &h->ms_x2, h->a_x2.p, E, cr));
         FFB_TRY(encode_output_map(h, &h->mc_x, h->x.p, E, rows));
         FFB_TRY(encode_output_map(h, &h->mc_xl, h->xl.p, E, rows_b));
         FFB_TRY(encode_output_map(h, &h->mc_qkv3, h->qkv.p, 3 * E, rows));
@@ -868,6 +876,13 @@ int plan_batch(ffb_handle* h, const uint8_t* mask, const int64_t* num_input, int
             h->cap_b = (long long)rows_b;
             CU(h, h->a_ql.ensure(2 * rows_b * E * 2));
             FFB_TRY(encode_split_store_map(h, &h->ms_ql, h->a_ql.p, E, rows_b));
+            h->l0_ok = false;
+            if (h->opt_l0cache && !h->encode_only && h->W == 1 && h->Ld > 1) {
+                CU(h, h->qkv0_cache.ensure(2 * (size_t)h->B * h->T * 3 * E * 2));
+                CU(h, h->a_qkv0.ensure(2 * rows_b * 3 * E * 2));
+                FFB_TRY(encode_split_store_map(h, &h->ms_qkv0, h->a_qkv0.p, 3 * E, rows_b));
+                h->l0_ok = true;
+            }
             h->m_last.resize(h->T);
             for (int P = 1; P < h->T && !h->encode_only; ++P)
                 FFB_TRY(encode_operand_map_strided(h, &h->m_last[P], h->a_x2p.as<uint16_t>(), E, (uint64_t)h->B, (uint64_t)P, (uint64_t)(P - 1),
@@ -1035,16 +1050,24 @@ int run_encoder(ffb_handle* h, const float* coords_dev, cudaStream_t s, bool all
                         (int)TS.enc.size() == h->Le && (h->opt_tc == 2 || R >= TC_MIN_ROWS);
     // value embedding (embedding.py:34): relu(coords W0^T + b0) W2^T + b2 on the valid edges only
     if (enc_tc) {
-        // first linear (K = in_dim, 100: off the tensor-core grid) on the FFMA kernel, written at the edges' memory rows; the E x E second
-        // linear on the tcgen05 GEMM over ALL memory rows (the 4 token rows per wireframe compute don't-care values that token_rows_kernel
-        // overwrites): 83 % of the embedding's FLOPs leave the FFMA pipe
-        CU(h, cudaMemsetAsync(hb, 0, (size_t)R * E * sizeof(float), s));
-        { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
-          l.C = hb; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>(); l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        // both linears run over ALL memory rows on the tcgen05 GEMM (the 4 token rows per wireframe compute don't-care values that
+        // token_rows_kernel overwrites); the first one needs K = in_dim (100) zero-padded to 128, else it stays on the FFMA kernel
         h->ovf_slot = 6;
         CU(h, cudaMemsetAsync(h->state.as<int>() + 6, 0, sizeof(int), s));
-        split_rows_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(hb, h->a_x2.as<uint16_t>(), h->cap_rows * E, R, E, 2, ovf_ptr(h));
-        h->launches++; CU(h, cudaGetLastError());
+        if (TS.has_emb0 && h->a_c.p) {
+            // both linears on tcgen05: the coordinates become an fp16x2 operand with K zero-padded to 128, written at the edges' memory rows
+            split_coords_kernel<<<grid1d((long long)Re * 32), 256, 0, s>>>(coords_dev, h->d_edge_src.as<int>(), h->d_edge_dst.as<int>(), h->a_c.as<uint16_t>(),
+                                                                        h->cap_rows * 128, Re, h->cfg.in_dim, ovf_ptr(h));
+            h->launches++; CU(h, cudaGetLastError());
+            { TcLin l; l.A0 = &TS.m_c; l.W = &TS.emb0; l.w_scale = TS.s_emb0; l.bias = w.e0b; l.relu = 1; l.Cs = h->a_x2.as<uint16_t>();
+              l.cs_stride = h->cap_rows * E; l.ldcs = E; l.Cmap = &h->ms_x2; l.M = R; l.N = E; l.K = 128; FFB_TRY(launch_tc(h, l, nullptr, s)); }
+        } else {
+            CU(h, cudaMemsetAsync(hb, 0, (size_t)R * E * sizeof(float), s));
+            { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.a_rows = h->d_edge_src.as<int>(); l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b;
+              l.C = hb; l.ldc = E; l.c_rows = h->d_edge_dst.as<int>(); l.M = Re; l.N = E; l.K = h->cfg.in_dim; l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+            split_rows_kernel<<<grid1d((long long)R * (E / 4)), 256, 0, s>>>(hb, h->a_x2.as<uint16_t>(), h->cap_rows * E, R, E, 2, ovf_ptr(h));
+            h->launches++; CU(h, cudaGetLastError());
+        }
         { TcLin l; l.A0 = &TS.m_x2; l.W = &TS.emb2; l.w_scale = TS.s_emb2; l.bias = w.e2b; l.C = x; l.ldc = E; l.Cmap = &h->mc_x; l.M = R; l.N = E; l.K = E;
           FFB_TRY(launch_tc(h, l, nullptr, s)); }
         h->ovf_slot = 4;
@@ -1198,9 +1221,26 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
         } else {
             // ---- tensor-core path: every GEMM operand is produced directly in the split operand format (fp16x2 / bf16x3) ----
             const ffb_handle::DecTcW& Tw = TS.layers[li];
+            // layer 0 inside the greedy loop: q / k / v of the positions that existed in the previous step are unchanged (exact): project the
+            // NEW position only (B rows instead of B * P) and assemble the (sequence, position)-ordered operand from the cache
+            const bool l0 = (li == 0) && append && hp && h->l0_ok && !last;
+            if (l0) {
+                launch_k(h, copy_rows_kernel, dim3(grid1d((long long)B * (E / 4))), dim3(256), 0, s, (const float*)x, xl, B, P, P - 1, E, stop);
+                h->launches++; CU(h, cudaGetLastError());
+                FFB_TRY(launch_ln_split(h, xl, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos + (size_t)(P - 1) * E, 1, B, E, stop, s));
+                { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = 2 * E / tc::BN; l.W = &Tw.sa_in; l.w_scale = Tw.s_sa_in; l.bias = Lw.sa.in_b;
+                  l.M = B; l.N = 3 * E; l.K = E; l.Cs = h->a_qkv0.as<uint16_t>(); l.cs_stride = h->cap_b * 3 * E; l.ldcs = 3 * E; l.Cmap = &h->ms_qkv0;
+                  FFB_TRY(launch_tc(h, l, stop, s)); }
+                prof_begin(h, PC_OTHER, 0.0, s);
+                launch_k(h, assemble_qkv0_kernel, dim3(grid1d(2ll * M * (3 * E / 8))), dim3(256), 0, s, (const uint16_t*)h->a_qkv0.as<uint16_t>(), h->cap_b * 3 * E,
+                         h->qkv0_cache.as<uint16_t>(), (long long)h->B * h->T * 3 * E, aqkv, h->cap_rows * 3 * E, B, P, h->T, 3 * E, stop);
+                prof_end(h, s);
+                h->launches++; CU(h, cudaGetLastError());
+            } else
             FFB_TRY(launch_ln_split(h, x, Lw.n1w, Lw.n1b, ax2, ax2p, ssE, w.qpos, P, M, E, stop, s));
             const bool q_last_only = last && hp && h->H <= 8;        // pruned last layer: q is needed for the last prefix position only
-            if (q_last_only) {
+            if (l0) {
+            } else if (q_last_only) {
                 // k, v for every position: the column window [E, 3E) of the in-projection; q for the rows b*P + P-1 only, through a
                 // strided view of the LayerNorm output, into the compact buffer a_ql
                 { TcLin l; l.A0 = &TS.m_x2p; l.A1 = &TS.m_x2; l.n_switch = E / tc::BN; l.n_off = E;
@@ -1412,7 +1452,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -1432,6 +1472,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             if (value != 0 && value != 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_ENCODER_PRECISION: 0 = fp16x2 tcgen05 / fp32, 2 = float64");
             h->opt_enc_prec = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_HEAD_FP64: h->opt_head64 = value ? 1 : 0; return FFB_OK;
+        case FFB_OPT_L0_CACHE: h->opt_l0cache = value ? 1 : 0; h->encoded = false; return FFB_OK;
         case FFB_OPT_SKINNY_GEMM: h->opt_skinny = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ATTN_LONG: h->opt_attn_long = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ENCODE_ONLY: h->opt_encode_only = value ? 1 : 0; h->encoded = false; return FFB_OK;
@@ -1495,6 +1536,11 @@ int ffb_load_weights(ffb_handle* h, const float* blob, size_t count, int loc, vo
     transpose_kernel<<<grid1d((long long)(E * E)), 256, 0, s>>>(h->w.proj_w, h->projT.as<float>(), (int)E, (int)E);
     h->launches++; CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(h->projT.as<float>() + E * E, h->w.proj_b, E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (h->cfg.in_dim <= 128) {                             // first embedding linear with K zero-padded to 128 (tensor-core encoder)
+        CU(h, h->e0pad.ensure(E * 128 * sizeof(float)));
+        pad_cols_kernel<<<grid1d((long long)(E * 128)), 256, 0, s>>>(h->w.e0w, h->e0pad.as<float>(), (int)E, h->cfg.in_dim, 128);
+        h->launches++; CU(h, cudaGetLastError());
+    }
     for (auto& T : h->tcs) T.ready = false;                 // split weights are rebuilt lazily per operand format
     if (h->tc_ok && h->opt_tc) FFB_TRY(prepare_tc(h, h->tc_fmt, s));
     CU(h, cudaStreamSynchronize(s));

@@ -1207,6 +1207,77 @@ __global__ void unpack_memory_kernel(const float* __restrict__ mem, const int* _
     }
 }
 
+// Per-row plan of the packed memory, expanded on the device from the wireframes' row offsets (the host only scans the masks):
+//   pos_idx[r]  = row index within its wireframe (position-table row, embedding.py:106-108)
+//   edge e (valid edges in wireframe order) : edge_src[e] = its slot in the [N, num_lines] input, edge_dst[e] = its memory row
+__global__ void plan_rows_kernel(const int* __restrict__ row_off, int n_wf, int R, int num_lines, int num_token,
+                                 int* __restrict__ pos_idx, int* __restrict__ edge_src, int* __restrict__ edge_dst) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_wf - 1;                       // largest w with row_off[w] <= r
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_off[mid] <= r) lo = mid; else hi = mid - 1; }
+        const int j = r - row_off[lo];
+        pos_idx[r] = j;
+        if (j >= num_token) {
+            const int e = r - num_token * (lo + 1);      // every wireframe before (and this one) contributes num_token non-edge rows
+            edge_src[e] = lo * num_lines + (j - num_token);
+            edge_dst[e] = r;
+        }
+    }
+}
+
+// Layer-0 q/k/v of the decoder do not depend on the step for positions that already exist (the layer-0 input of position p is
+// memory[token_p] and its LayerNorm + in-projection involve that row alone; tokens never change once appended): they are computed
+// for the NEW position only and kept in a position-stable cache [2][B][T][ld].  This kernel builds the (sequence, position)-ordered
+// operand rows a_qkv[(b*P + p)] the attention kernel reads: old positions from the cache, the new one from `fresh` [2][capb][ld]
+// (which it also appends to the cache).  16-byte chunks; `parts` are the fp16x2 halves.
+__global__ void assemble_qkv0_kernel(const uint16_t* __restrict__ fresh, long long fresh_stride, uint16_t* __restrict__ cache, long long cache_stride,
+                                     uint16_t* __restrict__ out, long long out_stride, int B, int P, int T, int ld, const int* stop) {
+    FFB_PDL_SYNC();
+    FFB_STOP_CHECK(stop);
+    const int c8n = ld >> 3;
+    const long long total = 2ll * B * P * c8n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c8n);
+        long long r = i / c8n;
+        const int p = (int)(r % P); r /= P;
+        const int b = (int)(r % B); const int part = (int)(r / B);
+        uint4 v;
+        uint16_t* cslot = cache + (size_t)part * cache_stride + ((size_t)b * T + p) * ld + c * 8;
+        if (p == P - 1) {
+            v = *reinterpret_cast<const uint4*>(fresh + (size_t)part * fresh_stride + (size_t)b * ld + c * 8);
+            *reinterpret_cast<uint4*>(cslot) = v;
+        } else {
+            v = *reinterpret_cast<const uint4*>(cslot);
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)part * out_stride + ((size_t)b * P + p) * ld + c * 8) = v;
+    }
+}
+
+// dst [rows, cols_out] = src [rows, cols_in] zero-padded on the right
+__global__ void pad_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols_in, int cols_out) {
+    const long long total = (long long)rows * cols_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols_out); const long long r = i / cols_out;
+        dst[i] = c < cols_in ? src[r * cols_in + c] : 0.f;
+    }
+}
+
+// coordinates of the valid edges -> fp16x2 operand rows of 128 columns (zero-padded beyond in_dim) at the edges' memory rows
+__global__ void split_coords_kernel(const float* __restrict__ coords, const int* __restrict__ edge_src, const int* __restrict__ edge_dst,
+                                    uint16_t* __restrict__ out, long long split_stride, int Re, int in_dim, int* ovf) {
+    const long long total = (long long)Re * 32;          // 32 float4 chunks per row
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 31) * 4; const long long e = i >> 5;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < in_dim) v = *reinterpret_cast<const float4*>(coords + (size_t)edge_src[e] * in_dim + c);
+        else if (c < in_dim) {
+            const float* p = coords + (size_t)edge_src[e] * in_dim + c;
+            v.x = p[0]; if (c + 1 < in_dim) v.y = p[1]; if (c + 2 < in_dim) v.z = p[2];
+        }
+        store_split4(out + (size_t)edge_dst[e] * 128 + c, split_stride, v, 2, ovf);
+    }
+}
+
 // dst[c][r] = src[r][c]  (src [rows, cols])
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
     const long long total = (long long)rows * cols;

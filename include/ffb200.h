@@ -113,6 +113,11 @@ enum { FFB_OPT_ATTN_LONG = 20 };
  * 128 x 64 tiles instead: 4x as many CTAs stream the weights and the per-tile tensor time drops 4x.  0 = always 128 x 256. */
 enum { FFB_OPT_SKINNY_GEMM = 21 };
 
+/* 1 (default): in decoder layer 0 the q / k / v rows of prefix positions that already existed in the previous greedy step are taken from a
+ * position-stable cache (their inputs -- memory[token], query_pos -- cannot change: exact, not the causal KV cache DESIGN.md rules out);
+ * only the new position is normalised and projected.  Greedy loop on the half pipeline only (not with beams, not for forced prefixes). */
+enum { FFB_OPT_L0_CACHE = 22 };
+
 /* 1: ffb_encode computes the encoder memory only (embedding, encoder layers, final norm; ffb_get_memory reads it) -- no decode
  * workspaces are sized, the cross-attention K / V cache and the folded pointer head are skipped and ffb_decode_greedy is refused.
  * The encoder-only throughput workload of BASELINE.json configs[4] (2048-edge wireframes, batch 256). */
