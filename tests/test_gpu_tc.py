@@ -353,3 +353,26 @@ def test_trained_e512_checkpoint_through_forced_tcgen05(name, fmt):
     vm = valid_rows_mask(b, g["cfg"])
     assert np.max(np.abs(e.get_memory().cpu().numpy()[vm] - g["memory"][vm])) <= LOGIT_TOL
     e.close()
+
+
+@pytest.mark.parametrize("name", ["ours_parallel_small", "mid_parallel_trained", "perspective_small"])
+def test_layer0_cache_is_exact(name):
+    """FFB_OPT_L0_CACHE: decoder layer 0 projects only the NEW prefix position and takes q / k / v of the earlier ones from a cache.  Their
+    inputs cannot change between steps, every row goes through the same LayerNorm and the same K-loop, so tokens AND logits must be
+    bit-identical to the run that recomputes them (and equal to the reference golden)."""
+    from faceformer_b200.lib import FFB_OPT_L0_CACHE
+    g = load_case(name)
+    b = g["batch"]
+    coords = torch.from_numpy(b["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(b["input_mask"]).cuda(), torch.from_numpy(b["num_input"]).cuda()
+    res = []
+    for cache in (0, 1):
+        e = Engine(g["cfg"], g["mode"], 0)
+        e.load_state_dict(g["sd"])
+        e.set_option(FFB_OPT_L0_CACHE, cache)
+        pred, steps = e.forward_eval(coords, mask, ni)
+        res.append((pred.cpu().numpy(), steps, e.get_last_logits().cpu().numpy(), e.kernel_launches()))
+        e.close()
+    assert res[0][1] == res[1][1] == g["steps"]
+    assert np.array_equal(res[0][0], g["predict"]) and np.array_equal(res[1][0], g["predict"])
+    assert np.array_equal(res[0][2], res[1][2])
