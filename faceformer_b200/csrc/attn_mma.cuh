@@ -41,36 +41,36 @@ __device__ __forceinline__ uint32_t tf32_lo(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restrict__ Q, int ldq,
-                                                          const float* __restrict__ K, const float* __restrict__ V, int ldk,
-                                                          float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
-                                                          long long os_stride, const AttnGroups g, const int* stop) {
-    FFB_STOP_CHECK(stop);
-    extern __shared__ __align__(16) float smem[];
+// One work item = (group, head, tile of <= 64 query rows) on 128 threads; `smem` = AM_SMEM_BYTES of shared memory.  Callable from a
+// persistent kernel (persist.cuh): global reads go through L2 (__ldcg: q / k / v may have been written by other CTAs of the SAME launch),
+// and with q_staged the caller has already placed the pre-scaled Q tile in smem[0, 64 * 80) and synchronised the CTA.
+__device__ __forceinline__ void attn_mma_tile(float* smem, bool q_staged, const float* __restrict__ Q, int ldq,
+                                              const float* __restrict__ K, const float* __restrict__ V, int ldk,
+                                              float* __restrict__ O, int ldo, uint16_t* __restrict__ Os, long long os_stride,
+                                              int split_fmt, int* overflow, long long q0, int nqt, long long k0, int nk, long long o0, int head,
+                                              int tid, int bar_id) {
+    // the 128 threads of this work item meet at named barrier `bar_id` (0 with a 128-thread CTA = __syncthreads)
+    auto sync128 = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     float* Qs = smem;                              // [64][80]
     float* Ks = smem + AM_BQ * AM_SQ;              // [64][80]
     float* Vs = smem + 2 * AM_BQ * AM_SQ;          // [64][68]
-
-    long long q0, k0, o0; int nq, nk;
-    attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
-    const int head = blockIdx.y;
-    const int qt0 = blockIdx.z * AM_BQ;
-    if (qt0 >= nq) return;
-    const int nqt = min(AM_BQ, nq - qt0);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lane = tid & 31, w = tid >> 5;
     const int gq = lane >> 2, t = lane & 3;        // MMA fragment coordinates
 
-    // stage the Q tile, pre-scaled by sqrt(1/64) = 0.125 (exact)
-    for (int idx = tid; idx < AM_BQ * 16; idx += 128) {
-        const int r = idx >> 4, d4 = idx & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nqt) {
-            v = *reinterpret_cast<const float4*>(Q + (size_t)(q0 + qt0 + r) * ldq + head * 64 + d4 * 4);
-            v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+    if (!q_staged) {
+        sync128();                                 // a previous work item of this CTA may still be reading the tile buffers
+        // stage the Q tile, pre-scaled by sqrt(1/64) = 0.125 (exact)
+        for (int idx = tid; idx < AM_BQ * 16; idx += 128) {
+            const int r = idx >> 4, d4 = idx & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nqt) {
+                v = __ldcg(reinterpret_cast<const float4*>(Q + (size_t)(q0 + r) * ldq + head * 64 + d4 * 4));
+                v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+            }
+            *reinterpret_cast<float4*>(Qs + r * AM_SQ + d4 * 4) = v;
         }
-        *reinterpret_cast<float4*>(Qs + r * AM_SQ + d4 * 4) = v;
     }
-    __syncthreads();
+    sync128();
 
     const bool warp_active = (w * 16) < nqt;       // warps whose 16 rows are all padding skip the math
     // A fragments of this warp's 16 query rows for all 8 k-steps: chunk c (LDS.128) holds k-steps 2c, 2c+1
@@ -97,19 +97,20 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
     for (int u = 0; u < 8; ++u) { o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0.f; }
 
     for (int kt = 0; kt < nk; kt += AM_BK) {
-        __syncthreads();                                          // previous K/V tile fully consumed
+        const int nkb = min(8, (nk - kt + 7) >> 3);               // 8-key blocks of this tile that hold keys: the others are skipped
+        sync128();                                                // previous K/V tile fully consumed
         for (int idx = tid; idx < AM_BK * 16; idx += 128) {
             const int r = idx >> 4, d4 = idx & 15;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
             if (kt + r < nk) {
                 const size_t off = (size_t)(k0 + kt + r) * ldk + head * 64 + d4 * 4;
-                kv = *reinterpret_cast<const float4*>(K + off);
-                vv = *reinterpret_cast<const float4*>(V + off);
+                kv = __ldcg(reinterpret_cast<const float4*>(K + off));
+                vv = __ldcg(reinterpret_cast<const float4*>(V + off));
             }
             *reinterpret_cast<float4*>(Ks + r * AM_SQ + d4 * 4) = kv;
             *reinterpret_cast<float4*>(Vs + r * AM_SV + d4 * 4) = vv;
         }
-        __syncthreads();
+        sync128();
         if (!warp_active) continue;
 
         // ---- S = Q K^T for this warp's 16 rows x 64 keys: s[j] = key tile j (keys 8j..8j+7), C layout ----
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float sm[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (j < nkb) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float4 kb = *reinterpret_cast<const float4*>(Ks + (8 * j + gq) * AM_SQ + 16 * c + 4 * t);
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
                 mma_tf32(sc, ql[2 * c + 1], __float_as_uint(kb.z), __float_as_uint(kb.w));
                 mma_tf32(sc, qa[2 * c + 1], tf32_lo(kb.z), tf32_lo(kb.w));
                 mma_tf32(sm, qa[2 * c + 1], __float_as_uint(kb.z), __float_as_uint(kb.w));
+            }
             }
             // C layout: [0]=(gq, 2t) [1]=(gq, 2t+1) [2]=(gq+8, 2t) [3]=(gq+8, 2t+1); mask keys beyond nk
             const int key = kt + 8 * j + 2 * t;
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
         for (int u = 0; u < 8; ++u) { om[u][0] = om[u][1] = om[u][2] = om[u][3] = 0.f; oc[u][0] = oc[u][1] = oc[u][2] = oc[u][3] = 0.f; }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            if (j >= nkb) continue;                               // all probabilities of the block are exactly 0
             uint32_t pa[4], pl[4];
             pa[0] = __float_as_uint(s[j][0]); pa[1] = __float_as_uint(s[j][2]); pa[2] = __float_as_uint(s[j][1]); pa[3] = __float_as_uint(s[j][3]);
             pl[0] = tf32_lo(s[j][0]); pl[1] = tf32_lo(s[j][2]); pl[2] = tf32_lo(s[j][1]); pl[3] = tf32_lo(s[j][3]);
@@ -202,16 +206,30 @@ __global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restric
         for (int hi = 0; hi < 2; ++hi) {                           // u = 4*hi .. 4*hi+3  -> head dims 32*hi + 8t + ...
             const float4 c0 = make_float4(o[4 * hi][e] * inv, o[4 * hi + 1][e] * inv, o[4 * hi + 2][e] * inv, o[4 * hi + 3][e] * inv);
             const float4 c1 = make_float4(o[4 * hi][e + 1] * inv, o[4 * hi + 1][e + 1] * inv, o[4 * hi + 2][e + 1] * inv, o[4 * hi + 3][e + 1] * inv);
-            const size_t off = (size_t)(o0 + qt0 + r) * ldo + head * 64 + 32 * hi + 8 * t;
+            const size_t off = (size_t)(o0 + r) * ldo + head * 64 + 32 * hi + 8 * t;
             if (Os == nullptr) {
                 *reinterpret_cast<float4*>(O + off) = c0;
                 *reinterpret_cast<float4*>(O + off + 4) = c1;
             } else {
-                store_split4(Os + off, os_stride, c0, g.split_fmt, g.overflow);
-                store_split4(Os + off + 4, os_stride, c1, g.split_fmt, g.overflow);
+                store_split4(Os + off, os_stride, c0, split_fmt, overflow);
+                store_split4(Os + off + 4, os_stride, c1, split_fmt, overflow);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(128, 2) attn_mma_kernel(const float* __restrict__ Q, int ldq,
+                                                          const float* __restrict__ K, const float* __restrict__ V, int ldk,
+                                                          float* __restrict__ O, int ldo, uint16_t* __restrict__ Os,
+                                                          long long os_stride, const AttnGroups g, const int* stop) {
+    FFB_STOP_CHECK(stop);
+    extern __shared__ __align__(16) float smem[];
+    long long q0, k0, o0; int nq, nk;
+    attn_group(g, blockIdx.x, q0, nq, k0, nk, o0);
+    const int qt0 = blockIdx.z * AM_BQ;
+    if (qt0 >= nq) return;
+    attn_mma_tile(smem, false, Q, ldq, K, V, ldk, O, ldo, Os, os_stride, g.split_fmt, g.overflow, q0 + qt0, min(AM_BQ, nq - qt0), k0, nk, o0 + qt0,
+                  (int)blockIdx.y, (int)threadIdx.x, 0);
 }
 
 }  // namespace ffb

@@ -22,6 +22,7 @@
 #include "attn_x.cuh"
 #include "enc64.cuh"
 #include "attn_l.cuh"
+#include "persist.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -79,6 +80,10 @@ struct ffb_handle {
     int opt_enc_prec = 2;                         // encoder + cross K/V projections: 2 = float64 (default, enc64.cuh), 0 = fp16x2 tcgen05 / fp32 SIMT
     int opt_head64 = 1;                           // decoder.norm + project + pointer dot of the last position in float64
     DevBuf x64, y64, yp64, qkv64, att64, h64;
+    int opt_persist = 1;                          // whole greedy loop as one persistent cooperative kernel (persist.cuh): 0 off, 1 auto (small batches), 2 wherever supported
+    int pd_grid = 0;                              // co-resident CTAs of decode_persistent_kernel on this device (0: cooperative launch unavailable)
+    DevBuf pd_sync, pd_prof;                      // unsigned barrier counter + int[T] per-step counters; FFB_PD_PROF clock sums
+    bool used_persist = false;                    // the last decode ran in the persistent kernel
     int opt_l0cache = 1;                          // decoder layer 0: q / k / v of earlier prefix positions are cached (exact), only the new position is projected
     DevBuf qkv0_cache, a_qkv0; CUtensorMap ms_qkv0; bool l0_ok = false;
     DevBuf e0pad, a_c; CUtensorMap ms_x2;         // W0 zero-padded to [E, 128]; coordinates as fp16x2 operand [2][cap][128]; split-store map of a_x2
@@ -151,7 +156,8 @@ struct ffb_handle {
     int num_sms = 148;
     int tc_fmt = 2;                               // operand format: 2 = fp16x2 (3 MMA passes), 3 = bf16x3 (6 passes)
     int fp16_fallbacks = 0;                       // decodes re-run in bf16x3 because an activation exceeded the fp16 range
-    struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; float s_sa_in, s_sa_out, s_ca_q, s_ca_out, s_l1, s_l2; };
+    struct DecTcW { CUtensorMap sa_in, sa_out, ca_q, ca_out, l1, l2; float s_sa_in, s_sa_out, s_ca_q, s_ca_out, s_l1, s_l2;
+                    const uint16_t *p_sa_in, *p_sa_out, *p_ca_q, *p_ca_out, *p_l1, *p_l2; };     // the split arrays themselves (persist.cuh)
     struct EncTcW { CUtensorMap sa_in, sa_out, l1, l2; float s_sa_in, s_sa_out, s_l1, s_l2; };
     struct TcSet {                                // everything that depends on the operand format
         bool ready = false;
@@ -656,12 +662,12 @@ int prepare_tc(ffb_handle* h, int fmt, cudaStream_t s) {
         for (size_t l = 0; l < Ld; ++l) {
             const DecLayerW& L = h->w.dec[l];
             ffb_handle::DecTcW& D = T.layers[l];
-            FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &D.sa_in, fmt, &D.s_sa_in, s)); wp += fmt * 3 * E * E;
-            FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &D.sa_out, fmt, &D.s_sa_out, s)); wp += fmt * E * E;
-            FFB_TRY(split_weight(h, L.ca.in_w, wp, E, E, &D.ca_q, fmt, &D.s_ca_q, s)); wp += fmt * E * E;      // q rows of the cross in_proj
-            FFB_TRY(split_weight(h, L.ca.out_w, wp, E, E, &D.ca_out, fmt, &D.s_ca_out, s)); wp += fmt * E * E;
-            FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &D.l1, fmt, &D.s_l1, s)); wp += fmt * FF * E;
-            FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
+            D.p_sa_in = wp; FFB_TRY(split_weight(h, L.sa.in_w, wp, 3 * E, E, &D.sa_in, fmt, &D.s_sa_in, s)); wp += fmt * 3 * E * E;
+            D.p_sa_out = wp; FFB_TRY(split_weight(h, L.sa.out_w, wp, E, E, &D.sa_out, fmt, &D.s_sa_out, s)); wp += fmt * E * E;
+            D.p_ca_q = wp; FFB_TRY(split_weight(h, L.ca.in_w, wp, E, E, &D.ca_q, fmt, &D.s_ca_q, s)); wp += fmt * E * E;      // q rows of the cross in_proj
+            D.p_ca_out = wp; FFB_TRY(split_weight(h, L.ca.out_w, wp, E, E, &D.ca_out, fmt, &D.s_ca_out, s)); wp += fmt * E * E;
+            D.p_l1 = wp; FFB_TRY(split_weight(h, L.l1w, wp, FF, E, &D.l1, fmt, &D.s_l1, s)); wp += fmt * FF * E;
+            D.p_l2 = wp; FFB_TRY(split_weight(h, L.l2w, wp, E, FF, &D.l2, fmt, &D.s_l2, s)); wp += fmt * E * FF;
         }
         FFB_TRY(split_weight(h, h->w.proj_w, wp, E, E, &T.proj, fmt, &T.s_proj, s)); wp += fmt * E * E;
         T.enc.resize(Le);
@@ -1372,6 +1378,79 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     return FFB_OK;
 }
 
+
+// ---- the whole greedy loop in one persistent cooperative kernel (persist.cuh) ------------------------------------------------------
+constexpr long long PD_AUTO_ROWS = 1024;     // auto mode: batches with at most this many decoder rows (sequences x (T - 1)) in the last step
+
+bool persist_applicable(const ffb_handle* h) {
+    if (!h->opt_persist || h->pd_grid <= 0) return false;
+    if (h->tc_fmt != 2 || !h->tc_ok || !h->opt_tc) return false;
+    const ffb_handle::TcSet& TS = h->tcs[0];
+    if (!TS.ready || (int)TS.layers.size() != h->Ld) return false;
+    if (!h->opt_head64 || h->W != 1 || h->xchg_on || h->encode_only) return false;
+    if (h->N > pd::MAX_WF || h->Ld > pd::MAX_LAYERS || h->E % 128 != 0 || h->E > 1024 || h->FF % pd::TK != 0 || h->H * 64 != h->E) return false;
+    if (h->opt_persist == 2) return true;
+    // auto: the launch-bound regime only, and never when a test forces one of the multi-kernel pipelines
+    return h->opt_tc == 1 && h->B * (long long)(h->T - 1) <= PD_AUTO_ROWS;
+}
+
+int run_persistent(ffb_handle* h, cudaStream_t s) {
+    const ffb_handle::TcSet& TS = h->tcs[0];
+    pd::Params p{};
+    for (int li = 0; li < h->Ld; ++li) {
+        const DecLayerW& Lw = h->w.dec[li];
+        const ffb_handle::DecTcW& Tw = TS.layers[li];
+        pd::LayerP& L = p.L[li];
+        L.w_sa_in = Tw.p_sa_in; L.w_sa_out = Tw.p_sa_out; L.w_ca_q = Tw.p_ca_q; L.w_ca_out = Tw.p_ca_out; L.w_l1 = Tw.p_l1; L.w_l2 = Tw.p_l2;
+        L.s_sa_in = 1.0f / Tw.s_sa_in; L.s_sa_out = 1.0f / Tw.s_sa_out; L.s_ca_q = 1.0f / Tw.s_ca_q; L.s_ca_out = 1.0f / Tw.s_ca_out;
+        L.s_l1 = 1.0f / Tw.s_l1; L.s_l2 = 1.0f / Tw.s_l2;
+        L.b_sa_in = Lw.sa.in_b; L.b_sa_out = Lw.sa.out_b; L.b_ca_q = Lw.ca.in_b; L.b_ca_out = Lw.ca.out_b; L.b_l1 = Lw.l1b; L.b_l2 = Lw.l2b;
+        L.n1w = Lw.n1w; L.n1b = Lw.n1b; L.n2w = Lw.n2w; L.n2b = Lw.n2b; L.n3w = Lw.n3w; L.n3b = Lw.n3b;
+    }
+    p.Ld = h->Ld; p.E = h->E; p.FF = h->FF; p.H = h->H; p.B = (int)h->B; p.T = h->T; p.N = h->N; p.Lrows = h->L; p.mode = h->cfg.mode;
+    p.num_token = h->cfg.num_token;
+    p.x = h->x.as<float>(); p.qkv = h->qkv.as<float>();
+    p.xs = h->a_x2.as<uint16_t>(); p.xps = h->a_x2p.as<uint16_t>(); p.atts = h->a_att.as<uint16_t>(); p.hs = h->a_h.as<uint16_t>();
+    p.ssE = h->cap_rows * h->E; p.ssF = h->cap_rows * h->FF;
+    p.mem = h->mem.as<float>(); p.memW = h->memW.as<float>(); p.Kc = h->Kc.as<float>(); p.Vc = h->Vc.as<float>();
+    p.qpos = h->w.qpos; p.dec_nw = h->w.dec_nw; p.dec_nb = h->w.dec_nb;
+    p.row_off = h->d_row_off.as<int>(); p.vlen = h->d_vlen.as<int>(); p.seq_wf = h->d_seq_wf.as<int>(); p.seq_off = h->d_seq_off.as<int>();
+    p.tok = tok_cur(h); p.logits = h->logits.as<float>(); p.state = h->state.as<int>();
+    const size_t sync_bytes = (size_t)(h->T + 1) * sizeof(int);
+    CU(h, h->pd_sync.ensure(sync_bytes));
+    CU(h, cudaMemsetAsync(h->pd_sync.p, 0, sync_bytes, s));
+    p.bar = h->pd_sync.as<unsigned>(); p.counts = h->pd_sync.as<int>() + 1;
+    const bool prof = getenv("FFB_PD_PROF") != nullptr;          // debugging aid: per-phase clock sums of CTA 0 on stderr
+    if (prof) {
+        CU(h, h->pd_prof.ensure(32 * sizeof(long long)));
+        CU(h, cudaMemsetAsync(h->pd_prof.p, 0, 32 * sizeof(long long), s));
+        p.prof = h->pd_prof.as<long long>();
+    }
+    void* args[] = {(void*)&p};
+    CU(h, cudaLaunchCooperativeKernel((const void*)pd::decode_persistent_kernel, dim3(h->pd_grid), dim3(pd::THREADS), args, (size_t)pd::SMEM_BYTES, s));
+    h->launches++;
+    h->last_P = 0;
+    if (prof) {
+        long long v[32];
+        CU(h, cudaMemcpyAsync(v, h->pd_prof.p, sizeof v, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        static const char* names[11] = {"ln1", "qkv", "self_attn", "sa_out", "ln2", "cross", "ca_out", "ln3", "ffn1", "ffn2", "head"};
+        for (int i = 0; i < 11; ++i) fprintf(stderr, "[pd] %-9s work %10lld clk   barrier %10lld clk\n", names[i], v[i], v[16 + i]);
+    }
+    return FFB_OK;
+}
+
+// seq2seq 'pointer' output after a persistent decode: att <- project(decoder.norm(x)) for every row the loop can have produced (row-wise
+// operations: rows beyond the executed steps hold stale but finite values and are never read back)
+int run_project_rows(ffb_handle* h, cudaStream_t s) {
+    const int E = h->E, rows = (int)(h->B * (long long)(h->T - 1));
+    const ffb_handle::TcSet& TS = h->tcs[h->tc_fmt - 2];
+    FFB_TRY(launch_ln_split(h, h->x.as<float>(), h->w.dec_nw, h->w.dec_nb, h->a_x2.as<uint16_t>(), nullptr, h->cap_rows * E, nullptr, 1, rows, E, nullptr, s));
+    TcLin l; l.A0 = &TS.m_x2; l.W = &TS.proj; l.w_scale = TS.s_proj; l.bias = h->w.proj_b; l.C = h->att.as<float>(); l.ldc = E; l.Cmap = &h->mc_att;
+    l.M = rows; l.N = E; l.K = E;
+    return launch_tc(h, l, nullptr, s);
+}
+
 int copy_out(ffb_handle* h, const void* dev_src, void* dst, size_t bytes, int loc, cudaStream_t s) {
     CU(h, cudaMemcpyAsync(dst, dev_src, bytes, loc == FFB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
     if (loc == FFB_HOST) CU(h, cudaStreamSynchronize(s));
@@ -1440,6 +1519,14 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     h->L = cfg->num_lines + cfg->num_token; h->T = cfg->seq_len;
     h->Le = cfg->num_encoder_layers; h->Ld = cfg->num_decoder_layers;
     h->opt_prune = (cfg->mode == FFB_MODE_PARALLEL) ? 1 : 0;
+    {   // persistent decode kernel: the grid must be co-resident (grid-wide barriers), so it is sized from the occupancy of THIS device
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        if (coop && cudaFuncSetAttribute(pd::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pd::SMEM_BYTES) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pd::decode_persistent_kernel, pd::THREADS, (size_t)pd::SMEM_BYTES) == cudaSuccess)
+            h->pd_grid = std::min(per_sm, 1) * h->num_sms;
+        cudaGetLastError();
+    }
     for (auto& ev : h->ev) cudaEventCreate(&ev);
     *out = h;
     return FFB_OK;
@@ -1452,7 +1539,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0, &h->pd_sync, &h->pd_prof};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -1473,6 +1560,9 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
             h->opt_enc_prec = value; h->encoded = false; return FFB_OK;
         case FFB_OPT_HEAD_FP64: h->opt_head64 = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_L0_CACHE: h->opt_l0cache = value ? 1 : 0; h->encoded = false; return FFB_OK;
+        case FFB_OPT_PERSISTENT:
+            if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_PERSISTENT: 0 off, 1 auto, 2 wherever supported");
+            h->opt_persist = value; return FFB_OK;
         case FFB_OPT_SKINNY_GEMM: h->opt_skinny = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ATTN_LONG: h->opt_attn_long = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ENCODE_ONLY: h->opt_encode_only = value ? 1 : 0; h->encoded = false; return FFB_OK;
@@ -1650,6 +1740,13 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         }
         for (int i = 0; i < T; ++i) h->h_stop[i] = 0;
         h->steps_launched = 0;
+        h->used_persist = persist_applicable(h);
+        if (h->used_persist) {
+            // small batch: every step of the loop inside ONE cooperative kernel; the stop predicate never leaves the device
+            FFB_TRY(run_persistent(h, s));
+            if (!h->opt_prune) FFB_TRY(run_project_rows(h, s));       // seq2seq 'pointer' (model.py:216-217): project(decoder.norm(.)) of every position
+            h->steps_launched = T - 1;
+        } else
         for (int step = 0; step < T - 1; ++step) {
             bool stopped = false;
             for (int i = 0; i < step && !stopped; ++i) stopped = h->h_stop[i] != 0;
@@ -2026,6 +2123,8 @@ int ffb_overflowed(ffb_handle* h, int32_t* overflowed, void* stream) {
 }
 
 int ffb_steps_launched(const ffb_handle* h) { return h ? h->steps_launched : 0; }
+
+int ffb_used_persistent(const ffb_handle* h) { return (h && h->used_persist) ? 1 : 0; }
 
 int64_t ffb_kernel_launches(const ffb_handle* h) { return h ? h->launches : 0; }
 

@@ -358,6 +358,10 @@ class Engine:
     def steps_launched(self) -> int:
         return int(self._lib.ffb_steps_launched(self._h))
 
+    def used_persistent(self) -> bool:
+        """Did the last decode run inside the persistent cooperative kernel (FFB_OPT_PERSISTENT)?"""
+        return bool(self._lib.ffb_used_persistent(self._h))
+
     def kernel_launches(self) -> int:
         return int(self._lib.ffb_kernel_launches(self._h))
 

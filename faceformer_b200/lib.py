@@ -20,7 +20,7 @@ HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [os.path.join
 
 FFB_ABI_VERSION = 1
 FFB_HOST, FFB_DEVICE = 0, 1
-FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL, FFB_OPT_POINTER_BATCHED, FFB_OPT_BEAM, FFB_OPT_ENCODER_PRECISION, FFB_OPT_HEAD_FP64, FFB_OPT_FORCE_F, FFB_OPT_ENCODE_ONLY, FFB_OPT_ATTN_LONG, FFB_OPT_SKINNY_GEMM, FFB_OPT_L0_CACHE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22
+FFB_OPT_DEDUP_PAD, FFB_OPT_PRUNE_LAST, FFB_OPT_TIMING, FFB_OPT_PROFILE, FFB_OPT_TENSOR_CORE, FFB_OPT_ATTN_MMA, FFB_OPT_TC_FORMAT, FFB_OPT_STAGGER, FFB_OPT_TMA_EPILOGUE, FFB_OPT_ATTN_X, FFB_OPT_GEMM_VARIANT, FFB_OPT_ENCODER_TC, FFB_OPT_PDL, FFB_OPT_POINTER_BATCHED, FFB_OPT_BEAM, FFB_OPT_ENCODER_PRECISION, FFB_OPT_HEAD_FP64, FFB_OPT_FORCE_F, FFB_OPT_ENCODE_ONLY, FFB_OPT_ATTN_LONG, FFB_OPT_SKINNY_GEMM, FFB_OPT_L0_CACHE, FFB_OPT_PERSISTENT = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23
 PROFILE_CLASSES = ("linear", "layernorm", "attn_rows", "attn_tiled", "pointer", "other", "linear_tc")
 
 
@@ -63,6 +63,7 @@ SIGNATURES = {
     "ffb_get_beams": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ffb_overflowed": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
     "ffb_steps_launched": (C.c_int, [_P]),
+    "ffb_used_persistent": (C.c_int, [_P]),
     "ffb_phase_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "ffb_profile_read": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ffb_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

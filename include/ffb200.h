@@ -118,6 +118,13 @@ enum { FFB_OPT_SKINNY_GEMM = 21 };
  * only the new position is normalised and projected.  Greedy loop on the half pipeline only (not with beams, not for forced prefixes). */
 enum { FFB_OPT_L0_CACHE = 22 };
 
+/* The whole greedy loop as ONE persistent cooperative kernel (csrc/persist.cuh): all decode steps in a single launch, grid-wide barriers
+ * between the phases of a step, the stop predicate (model_para.py:232 / model.py:207-210) evaluated on the device.  0 = off; 1 (default) =
+ * auto: batches of at most 1024 decoder rows (sequences x (T - 1): one small wireframe per batch as in the reference's test loop,
+ * trainer.py:51, and seq2seq) while no option forces one of the multi-kernel pipelines; 2 = wherever it is supported (fp16x2 operand format,
+ * float64 head, beam width 1, no batch splitting, <= 64 wireframes).  Larger batches are tensor-bound and stay on the tcgen05 kernels. */
+enum { FFB_OPT_PERSISTENT = 23 };
+
 /* 1: ffb_encode computes the encoder memory only (embedding, encoder layers, final norm; ffb_get_memory reads it) -- no decode
  * workspaces are sized, the cross-attention K / V cache and the folded pointer head are skipped and ffb_decode_greedy is refused.
  * The encoder-only throughput workload of BASELINE.json configs[4] (2048-edge wireframes, batch 256). */
@@ -243,6 +250,9 @@ int ffb_overflowed(ffb_handle* h, int32_t* overflowed, void* stream);
  * stops launching once the early-stop predicate (model_para.py:232 / model.py:207-210) has fired; == executed steps + the few
  * steps that were already queued when the flag arrived. */
 int ffb_steps_launched(const ffb_handle* h);
+
+/* 1 if the last ffb_decode_greedy ran the whole loop inside the persistent cooperative kernel (FFB_OPT_PERSISTENT), else 0. */
+int ffb_used_persistent(const ffb_handle* h);
 
 /* Count of this library's kernels launched on the handle since creation (bench `gpu_launches`). */
 int64_t ffb_kernel_launches(const ffb_handle* h);

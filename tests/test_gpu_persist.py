@@ -1,0 +1,71 @@
+"""The persistent cooperative decode kernel (csrc/persist.cuh, FFB_OPT_PERSISTENT): the whole greedy loop in one launch.
+Same bar as every other pipeline: tokens exact against the reference goldens, executed steps equal (the stop predicate is evaluated on the
+device), last-step logits within the logit tolerance, seq2seq extras; and agreement with the multi-kernel path on fresh batches."""
+import numpy as np
+import pytest
+import torch
+
+from faceformer_b200 import synth
+from faceformer_b200.config import MODE_PARALLEL, MODE_SEQ2SEQ, OURS
+from faceformer_b200.engine import Engine
+from faceformer_b200.lib import FFB_OPT_PERSISTENT
+from util import LOGIT_TOL, load_case, logits_close
+
+pytestmark = pytest.mark.gpu
+
+
+def decode(g, batch, persist):
+    e = Engine(g["cfg"], g["mode"], 0)
+    e.load_state_dict(g["sd"])
+    e.set_option(FFB_OPT_PERSISTENT, persist)
+    coords = torch.from_numpy(batch["input"]).cuda().flatten(2)
+    mask, ni = torch.from_numpy(batch["input_mask"]).cuda(), torch.from_numpy(batch["num_input"]).cuda()
+    pred, steps = e.forward_eval(coords, mask, ni)
+    out = dict(pred=pred.cpu().numpy(), steps=steps, logits=e.get_last_logits().cpu().numpy(), used=e.used_persistent(), launches=e.kernel_launches())
+    if g["mode"] == MODE_SEQ2SEQ:
+        out["pointer"] = e.get_last_pointer().cpu().numpy()
+    e.close()
+    return out
+
+
+def test_seq2seq_single_wireframe_takes_the_persistent_kernel_by_default():
+    """BASELINE configs[0]: one 64-edge wireframe, 258 steps -- auto mode must choose the persistent kernel and match the reference."""
+    g = load_case("seq2seq_single64")
+    r = decode(g, g["batch"], 1)
+    assert r["used"]
+    assert r["steps"] == g["steps"]
+    assert np.array_equal(r["pred"], g["predict"]), f"{(r['pred'] != g['predict']).sum()} token mismatches"
+    ok, d = logits_close(r["logits"], g["last_logits"], b64=g.get("last_logits64"))
+    assert ok, f"last-step logits differ by {d}"
+    off = decode(g, g["batch"], 0)
+    assert not off["used"] and np.array_equal(off["pred"], g["predict"])
+    assert r["pointer"].shape == off["pointer"].shape
+    assert np.max(np.abs(r["pointer"] - off["pointer"])) <= LOGIT_TOL        # 'pointer' extra (model.py:216-217)
+    assert r["launches"] < off["launches"] / 50                               # one launch instead of ~72 per step
+
+
+@pytest.mark.parametrize("name", ["ours_parallel_small", "perspective_small", "ours_wide300", "mid_parallel_trained", "mid_parallel_trained_b"])
+def test_forced_persistent_kernel_matches_the_reference_goldens(name):
+    g = load_case(name)
+    r = decode(g, g["batch"], 2)
+    assert r["used"]
+    assert r["steps"] == g["steps"]
+    assert np.array_equal(r["pred"], g["predict"]), f"{(r['pred'] != g['predict']).sum()} token mismatches"
+    ok, d = logits_close(r["logits"], g["last_logits"], b64=g.get("last_logits64"))
+    assert ok, f"last-step logits differ by {d}"
+
+
+@pytest.mark.parametrize("mode,n,seed,lo,hi", [(MODE_PARALLEL, 1, 31, 24, 24), (MODE_PARALLEL, 1, 32, 7, 7), (MODE_PARALLEL, 5, 33, 3, 12),
+                                               (MODE_SEQ2SEQ, 3, 34, 5, 40)])
+def test_persistent_and_multi_kernel_paths_agree_on_fresh_batches(mode, n, seed, lo, hi):
+    """One wireframe per batch (the reference's test loop, trainer.py:51), a ragged small batch and a seq2seq batch: both pipelines are
+    fp32-class evaluations of the same function -- same tokens, same steps, logits within the tolerance."""
+    cfg = OURS if mode == MODE_PARALLEL else load_case("seq2seq_single64")["cfg"]
+    g = dict(cfg=cfg, mode=mode, sd=synth.synth_state_dict(cfg, mode, seed, "diverse"))
+    batch = synth.synth_batch(cfg, mode, n, seed, lo=lo, hi=hi)
+    a, b = decode(g, batch, 2), decode(g, batch, 0)
+    assert a["used"] and not b["used"]
+    assert a["steps"] == b["steps"]
+    assert np.array_equal(a["pred"], b["pred"]), f"{(a['pred'] != b['pred']).sum()} token mismatches"
+    ok, d = logits_close(a["logits"], b["logits"])
+    assert ok, d
