@@ -455,6 +455,9 @@ def run_small(args, name):
     if args.pdl >= 0:
         from faceformer_b200.lib import FFB_OPT_PDL
         eng.set_option(FFB_OPT_PDL, args.pdl)
+    if args.persistent >= 0:
+        from faceformer_b200.lib import FFB_OPT_PERSISTENT
+        eng.set_option(FFB_OPT_PERSISTENT, args.persistent)
     T = cfg.seq_len(mode)
 
     def step_device():
@@ -755,6 +758,7 @@ def main():
     ap.add_argument("--attn-x", type=int, default=-1, help="override FFB_OPT_ATTN_X (bit mask; -1 = library default)")
     ap.add_argument("--workload", default="ours32", choices=["ours32", "ours_n1", "seq2seq_n1_64", "split507", "beam4", "encoder2048"],
                     help="ours32 = BASELINE configs[1] (the headline, default); the others are the remaining BASELINE configs (faceformer_b200/workloads.py)")
+    ap.add_argument("--persistent", type=int, default=-1, help="override FFB_OPT_PERSISTENT (0 off, 1 auto, 2 wherever supported; -1 = library default)")
     ap.add_argument("--beam", type=int, default=4, help="beam width of --workload beam4")
     ap.add_argument("--split-size", type=int, default=507, help="wireframes of --workload split507")
     args = ap.parse_args()

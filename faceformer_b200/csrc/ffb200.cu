@@ -1427,7 +1427,10 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
         p.prof = h->pd_prof.as<long long>();
     }
     void* args[] = {(void*)&p};
-    CU(h, cudaLaunchCooperativeKernel((const void*)pd::decode_persistent_kernel, dim3(h->pd_grid), dim3(pd::THREADS), args, (size_t)pd::SMEM_BYTES, s));
+    prof_begin(h, PC_OTHER, 0.0, s);
+    const void* kern = (h->E <= 512) ? (const void*)pd::decode_persistent_kernel<4> : (const void*)pd::decode_persistent_kernel<8>;
+    CU(h, cudaLaunchCooperativeKernel(kern, dim3(h->pd_grid), dim3(pd::THREADS), args, (size_t)pd::SMEM_BYTES, s));
+    prof_end(h, s);
     h->launches++;
     h->last_P = 0;
     if (prof) {
@@ -1436,6 +1439,13 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
         CU(h, cudaStreamSynchronize(s));
         static const char* names[11] = {"ln1", "qkv", "self_attn", "sa_out", "ln2", "cross", "ca_out", "ln3", "ffn1", "ffn2", "head"};
         for (int i = 0; i < 11; ++i) fprintf(stderr, "[pd] %-9s work %10lld clk   barrier %10lld clk\n", names[i], v[i], v[16 + i]);
+        if (v[31] > 0) fprintf(stderr, "[pd] in-situ load latency (avg clk): activation via L2 %lld, parameter (read-only path) %lld, second activation %lld\n", v[24] / v[31], v[25] / v[31], v[23] / v[31]);
+        if (v[31] > 0)
+            fprintf(stderr, "[pd] LayerNorm row of CTA 0 warp 0 (avg clk over %lld rows): loads %lld, reductions %lld, format + store %lld\n", v[31], v[28] / v[31],
+                    v[29] / v[31], v[30] / v[31]);
+        if (v[27] > 0)
+            fprintf(stderr, "[pd] residual-projection item of CTA 0 (avg clk over %lld items): issue %lld, first pair landed %lld, mainloop %lld, hand-over %lld, epilogue %lld\n",
+                    v[27], v[11] / v[27], v[12] / v[27], v[13] / v[27], v[14] / v[27], v[15] / v[27]);
     }
     return FFB_OK;
 }
@@ -1522,8 +1532,9 @@ int ffb_create(const ffb_config* cfg, ffb_handle** out) {
     {   // persistent decode kernel: the grid must be co-resident (grid-wide barriers), so it is sized from the occupancy of THIS device
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
-        if (coop && cudaFuncSetAttribute(pd::decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pd::SMEM_BYTES) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pd::decode_persistent_kernel, pd::THREADS, (size_t)pd::SMEM_BYTES) == cudaSuccess)
+        if (coop && cudaFuncSetAttribute(pd::decode_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd::SMEM_BYTES) == cudaSuccess &&
+            cudaFuncSetAttribute(pd::decode_persistent_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd::SMEM_BYTES) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pd::decode_persistent_kernel<8>, pd::THREADS, (size_t)pd::SMEM_BYTES) == cudaSuccess)
             h->pd_grid = std::min(per_sm, 1) * h->num_sms;
         cudaGetLastError();
     }
