@@ -493,6 +493,7 @@ def run_small(args, name):
         steps_total += s
         bytes_total += s * wl.decoder_step_bytes(cfg, info["R"], info["B_eff"])
     eng.set_option(FFB_OPT_TIMING, 0)
+    persistent = bool(eng.used_persistent())                 # (of the last call; seq2seq_n1_64 has one call per step)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.kernel_launches()
@@ -524,7 +525,10 @@ def run_small(args, name):
         "e2e": {"value": edges * e2e_steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "decode step (all kernels of one greedy step; launch-latency bound at this size)",
+        "roofline": {"bound": "hbm", "kernel": ("pd::decode_persistent_kernel (the whole greedy loop in ONE cooperative launch; bound by ~61 grid-wide "
+                                                "barriers and dependent L2 round trips per decode step, not by bytes)" if persistent else
+                                                "decode step (all kernels of one greedy step; launch-latency bound at this size)"),
+                     "persistent_kernel": persistent,
                      "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                      "algorithmic_bytes_per_decode_step": bytes_total / steps_total, "launches_per_decode_step": launches / args.steps / steps_total,
                      "kernel_ms_by_class": {k: round(v["ms"], 3) for k, v in prof.items()},

@@ -1422,8 +1422,8 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
     p.bar = h->pd_sync.as<unsigned>(); p.counts = h->pd_sync.as<int>() + 1;
     const bool prof = getenv("FFB_PD_PROF") != nullptr;          // debugging aid: per-phase clock sums of CTA 0 on stderr
     if (prof) {
-        CU(h, h->pd_prof.ensure(32 * sizeof(long long)));
-        CU(h, cudaMemsetAsync(h->pd_prof.p, 0, 32 * sizeof(long long), s));
+        CU(h, h->pd_prof.ensure(64 * sizeof(long long)));
+        CU(h, cudaMemsetAsync(h->pd_prof.p, 0, 64 * sizeof(long long), s));
         p.prof = h->pd_prof.as<long long>();
     }
     void* args[] = {(void*)&p};
@@ -1434,7 +1434,7 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
     h->launches++;
     h->last_P = 0;
     if (prof) {
-        long long v[32];
+        long long v[64];
         CU(h, cudaMemcpyAsync(v, h->pd_prof.p, sizeof v, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         static const char* names[11] = {"ln1", "qkv", "self_attn", "sa_out", "ln2", "cross", "ca_out", "ln3", "ffn1", "ffn2", "head"};
@@ -1443,6 +1443,10 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
         if (v[31] > 0)
             fprintf(stderr, "[pd] LayerNorm row of CTA 0 warp 0 (avg clk over %lld rows): loads %lld, reductions %lld, format + store %lld\n", v[31], v[28] / v[31],
                     v[29] / v[31], v[30] / v[31]);
+        for (int o = 32; o <= 40; o += 8)
+            if (v[o + 5] > 0)
+                fprintf(stderr, "[pd] %s attention item, CTA 0 warp 0 (avg clk over %lld items): Q + first tile landed %lld, S + softmax %lld, P V (+ later tiles) %lld, partials + barrier %lld, merge + store %lld\n",
+                        o == 32 ? "self" : "cross", v[o + 5], v[o] / v[o + 5], v[o + 1] / v[o + 5], v[o + 2] / v[o + 5], v[o + 3] / v[o + 5], v[o + 4] / v[o + 5]);
         if (v[27] > 0)
             fprintf(stderr, "[pd] residual-projection item of CTA 0 (avg clk over %lld items): issue %lld, first pair landed %lld, mainloop %lld, hand-over %lld, epilogue %lld\n",
                     v[27], v[11] / v[27], v[12] / v[27], v[13] / v[27], v[14] / v[27], v[15] / v[27]);

@@ -206,9 +206,12 @@ static_assert(OFF_AMG + 8 * AMG_WARP <= OFF_RED, "attention buffers alias the op
 template <bool Q_SMEM>
 __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq, int nq, int nq_sub, const float* __restrict__ K,
                                           const float* __restrict__ V, int ldk, long long k0, int nk, int head, uint16_t* Os, long long os_stride,
-                                          int ldo, long long o0, int* ovf) {
+                                          int ldo, long long o0, int* ovf, long long* prof) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gq = lane >> 2, t = lane & 3;
     const int wps = 8 / nq_sub, sub = w / wps, kt_first = w % wps;
+    const bool probe = prof && blockIdx.x == 0 && tid == 0;
+    const long long a0 = probe ? clock64() : 0;
+    long long a1 = a0, a2 = a0, a3 = a0;
     float* Ks = reinterpret_cast<float*>(smem + OFF_AKV + w * AKV_WARP);     // [32][80]
     float* Vs = Ks + AK * AM_SQ;                                              // [32][68]
     float* mo = reinterpret_cast<float*>(smem + OFF_AMG + w * AMG_WARP);     // [16][64], then max[16], sum[16]
@@ -261,31 +264,40 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
             if (kt != kt_first * AK) { __syncwarp(); load_tile(kt); }     // (the first tile was requested before the Q fragments were loaded)
             cp_async_wait<0>();
             __syncwarp();
-            // ---- S = Q K^T: 16 rows x 32 keys ----
+            if (probe && kt == 0) a1 = clock64();
+            // ---- S = Q K^T: 16 rows x 32 keys.  Three independent accumulators per 8-key block (hi*hi, lo*hi, hi*lo: chains of 8 MMAs); a full
+            // tile runs without per-block branches so that the four blocks interleave ----
             float s[4][4];
+            auto s_block = [&](int j) {
+                float sm[4] = {0.f, 0.f, 0.f, 0.f}, sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float sm[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
-                if (j < nkb) {
+                for (int c = 0; c < 4; ++c) {
+                    const float4 kb = *reinterpret_cast<const float4*>(Ks + (8 * j + gq) * AM_SQ + 16 * c + 4 * t);
+                    uint32_t la[4], lb[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float4 kb = *reinterpret_cast<const float4*>(Ks + (8 * j + gq) * AM_SQ + 16 * c + 4 * t);
-                        uint32_t la[4], lb[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { la[e] = tf32_lo(__uint_as_float(qa[2 * c][e])); lb[e] = tf32_lo(__uint_as_float(qa[2 * c + 1][e])); }
-                        mma_tf32(sc, la, __float_as_uint(kb.x), __float_as_uint(kb.y));
-                        mma_tf32(sc, qa[2 * c], tf32_lo(kb.x), tf32_lo(kb.y));
-                        mma_tf32(sm, qa[2 * c], __float_as_uint(kb.x), __float_as_uint(kb.y));
-                        mma_tf32(sc, lb, __float_as_uint(kb.z), __float_as_uint(kb.w));
-                        mma_tf32(sc, qa[2 * c + 1], tf32_lo(kb.z), tf32_lo(kb.w));
-                        mma_tf32(sm, qa[2 * c + 1], __float_as_uint(kb.z), __float_as_uint(kb.w));
-                    }
+                    for (int e = 0; e < 4; ++e) { la[e] = tf32_lo(__uint_as_float(qa[2 * c][e])); lb[e] = tf32_lo(__uint_as_float(qa[2 * c + 1][e])); }
+                    mma_tf32(sa, la, __float_as_uint(kb.x), __float_as_uint(kb.y));
+                    mma_tf32(sb, qa[2 * c], tf32_lo(kb.x), tf32_lo(kb.y));
+                    mma_tf32(sm, qa[2 * c], __float_as_uint(kb.x), __float_as_uint(kb.y));
+                    mma_tf32(sa, lb, __float_as_uint(kb.z), __float_as_uint(kb.w));
+                    mma_tf32(sb, qa[2 * c + 1], tf32_lo(kb.z), tf32_lo(kb.w));
+                    mma_tf32(sm, qa[2 * c + 1], __float_as_uint(kb.z), __float_as_uint(kb.w));
                 }
                 const int key = kt + 8 * j + 2 * t;
-                s[j][0] = (key < nk) ? sm[0] + sc[0] : -INFINITY;
-                s[j][1] = (key + 1 < nk) ? sm[1] + sc[1] : -INFINITY;
-                s[j][2] = (key < nk) ? sm[2] + sc[2] : -INFINITY;
-                s[j][3] = (key + 1 < nk) ? sm[3] + sc[3] : -INFINITY;
+                s[j][0] = (key < nk) ? sm[0] + (sa[0] + sb[0]) : -INFINITY;
+                s[j][1] = (key + 1 < nk) ? sm[1] + (sa[1] + sb[1]) : -INFINITY;
+                s[j][2] = (key < nk) ? sm[2] + (sa[2] + sb[2]) : -INFINITY;
+                s[j][3] = (key + 1 < nk) ? sm[3] + (sa[3] + sb[3]) : -INFINITY;
+            };
+            if (nkb == 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_block(j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < nkb) s_block(j);
+                    else { s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY; }
+                }
             }
             // ---- online softmax (rows live in the 4 lanes of a quad) ----
             float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -306,15 +318,14 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
             ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
             l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;
             m0 = mn0; m1 = mn1;
+            if (probe && kt == 0) a2 = clock64();
             // ---- O_tile = P V from zero, then O = O * corr + O_tile (fp32, round to nearest); head dims [0, 32) and [32, 64) in turn ----
 #pragma unroll
             for (int uh = 0; uh < 2; ++uh) {
                 float om[4][4], oc[4][4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { om[u][0] = om[u][1] = om[u][2] = om[u][3] = 0.f; oc[u][0] = oc[u][1] = oc[u][2] = oc[u][3] = 0.f; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j >= nkb) continue;                       // all probabilities of the block are exactly 0
+                auto pv_block = [&](int j) {
                     uint32_t pa[4], pl[4];
                     pa[0] = __float_as_uint(s[j][0]); pa[1] = __float_as_uint(s[j][2]); pa[2] = __float_as_uint(s[j][1]); pa[3] = __float_as_uint(s[j][3]);
                     pl[0] = tf32_lo(s[j][0]); pl[1] = tf32_lo(s[j][2]); pl[2] = tf32_lo(s[j][1]); pl[3] = tf32_lo(s[j][3]);
@@ -328,6 +339,13 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
                         mma_tf32(oc[u], pa, tf32_lo(e0[u]), tf32_lo(e1[u]));
                         mma_tf32(om[u], pa, __float_as_uint(e0[u]), __float_as_uint(e1[u]));
                     }
+                };
+                if (nkb == 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pv_block(j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < nkb) pv_block(j);     // the probabilities of the other blocks are exactly 0
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -338,6 +356,7 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
             }
         }
     }
+    if (probe) a3 = clock64();
     // partial (max, sum, un-normalised O) of this warp; thread layout of the O fragments as in attn_mma.cuh
     if (sub_active) {
 #pragma unroll
@@ -352,6 +371,7 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
         if (t == 0) { mo[1024 + gq] = m0; mo[1024 + gq + 8] = m1; mo[1040 + gq] = l0; mo[1040 + gq + 8] = l1; }
     }
     __syncthreads();
+    const long long a4 = probe ? clock64() : 0;
     // merge in warp order, normalise, store as fp16x2: 4 consecutive head dims per thread and round
     for (int idx = tid; idx < nq_sub * 16 * 16; idx += THREADS) {
         const int row = idx >> 4, d4 = idx & 15, sb = row >> 4, lr = row & 15;
@@ -372,12 +392,17 @@ __device__ __forceinline__ void attn_item(uint8_t* smem, const float* Q, int ldq
         acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
         store_split4(Os + (size_t)(o0 + row) * ldo + head * 64 + d4 * 4, os_stride, acc, 2, ovf);
     }
+    if (probe) {
+        const long long a5 = clock64();
+        const int o = Q_SMEM ? 40 : 32;
+        prof[o] += a1 - a0; prof[o + 1] += a2 - a1; prof[o + 2] += a3 - a2; prof[o + 3] += a4 - a3; prof[o + 4] += a5 - a4; prof[o + 5] += 1;
+    }
 }
 
 // One 32 x TNT output tile (TNT = 64 or 32).  FUSE (TNT = 64): phase 5 -- the tile is the cross-attention query of (rows, head n0 / 64);
 // it is scaled, placed in the attention routine's Q buffer and consumed in place.
-template <bool FUSE, int TNT>
-__device__ __forceinline__ void gemm_item(const Params& p, const GemmDesc& d, uint8_t* smem, int row0, int nrows, int n0, int wf, int li) {
+template <bool FUSE, int TNT, int NV>
+__device__ __forceinline__ void gemm_item(const Params& p, const GemmDesc& d, uint8_t* smem, int P, int mt, int row0, int nrows, int n0, int wf, int li) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int kg = w >> 2, wm = (w >> 1) & 1, wn = w & 1;  // k group; warp tile: rows 16 wm .. +15, columns (TNT / 2) wn .. + TNT / 2 - 1
     constexpr int NJ = TNT / 16;                           // 8-column MMA tiles per warp
@@ -505,12 +530,12 @@ __device__ __forceinline__ void gemm_item(const Params& p, const GemmDesc& d, ui
         const size_t ldkv = (size_t)p.Ld * p.E;
         attn_item<true>(smem, Qs, AM_SQ, nrows, 2, p.Kc + (size_t)li * p.E, p.Vc + (size_t)li * p.E, (int)ldkv, reinterpret_cast<const int*>(smem + OFF_WFI)[(MAX_WF + 1) + wf],
                         reinterpret_cast<const int*>(smem + OFF_WFI)[2 * (MAX_WF + 1) + wf], n0 / 64,
-                        d.Cs, d.cs_split, d.ldcs, row0, p.state + 4);
+                        d.Cs, d.cs_split, d.ldcs, row0, p.state + 4, p.prof);
         return;
     }
 
-    if (kg != 0) return;
     const long long c4 = probe ? clock64() : 0;
+    if (kg == 0) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int col = n0 + wn * (TNT / 2) + j * 8 + 2 * t;
@@ -534,20 +559,21 @@ __device__ __forceinline__ void gemm_item(const Params& p, const GemmDesc& d, ui
             }
         }
     }
+    }
+    const long long c5 = probe ? clock64() : 0;
     if (probe) {
-        const long long c5 = clock64();
         p.prof[11] += c1 - c0; p.prof[12] += c2 - c1; p.prof[13] += c3 - c2; p.prof[14] += c4 - c3; p.prof[15] += c5 - c4; p.prof[27] += 1;
     }
 }
 
-template <bool FUSE, int TNT>
+template <bool FUSE, int TNT, int NV>
 __device__ __forceinline__ void gemm_phase(const Params& p, const GemmDesc& d, uint8_t* smem, const int* tile_first, int P, int li) {
     const int m_tiles = tile_first[p.N], n_tiles = d.N / TNT;
     for (int item = blockIdx.x; item < m_tiles * n_tiles; item += gridDim.x) {
         const int mt = item / n_tiles, nt = item - mt * n_tiles;
         int wf, row0, nrows;
         tile_rows(p, tile_first, mt, P, wf, row0, nrows);
-        gemm_item<FUSE, TNT>(p, d, smem, row0, nrows, nt * TNT, wf, li);
+        gemm_item<FUSE, TNT, NV>(p, d, smem, P, mt, row0, nrows, nt * TNT, wf, li);
     }
 }
 
@@ -563,7 +589,7 @@ __device__ __forceinline__ void self_attn_phase(const Params& p, uint8_t* smem, 
         const long long k0 = (long long)b * P, q0 = k0 + qt * 16 * nq_sub;
         __syncthreads();                                   // the previous item of this CTA is done with the shared buffers
         attn_item<false>(smem, p.qkv + (size_t)q0 * 3 * E + hd * 64, 3 * E, min(16 * nq_sub, P - qt * 16 * nq_sub), nq_sub, p.qkv + E, p.qkv + 2 * E, 3 * E,
-                         k0, P, hd, p.atts, p.ssE, E, q0, p.state + 4);
+                         k0, P, hd, p.atts, p.ssE, E, q0, p.state + 4, p.prof);
     }
 }
 
@@ -701,8 +727,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_persistent_kernel(const __g
                         d.R = p.x; d.ldr = E;
                         break;
                 }
-                if (ph == 5) gemm_phase<true, 64>(p, d, smem, tile_first, P, li);
-                else gemm_phase<false, 32>(p, d, smem, tile_first, P, li);
+                if (ph == 5) gemm_phase<true, 64, NV>(p, d, smem, tile_first, P, li);
+                else gemm_phase<false, 32, NV>(p, d, smem, tile_first, P, li);
             }
             const long long t1 = clock64();
             grid_sync(p.bar, target);
