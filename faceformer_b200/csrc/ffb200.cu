@@ -84,6 +84,8 @@ struct ffb_handle {
     int pd_grid = 0;                              // co-resident CTAs of decode_persistent_kernel on this device (0: cooperative launch unavailable)
     DevBuf pd_sync, pd_prof;                      // unsigned barrier counter + int[T] per-step counters; FFB_PD_PROF clock sums
     bool used_persist = false;                    // the last decode ran in the persistent kernel
+    const unsigned char* train_kmask = nullptr;   // non-null while ffb_forward_train runs its decoder pass: label padding mask [B * (T - 1)]
+    DevBuf d_label, d_label_mask, d_kmask;
     int opt_l0cache = 1;                          // decoder layer 0: q / k / v of earlier prefix positions are cached (exact), only the new position is projected
     DevBuf qkv0_cache, a_qkv0; CUtensorMap ms_qkv0; bool l0_ok = false;
     DevBuf e0pad, a_c; CUtensorMap ms_x2;         // W0 zero-padded to [E, 128]; coordinates as fp16x2 operand [2][cap][128]; split-store map of a_x2
@@ -337,11 +339,11 @@ int launch_attn_mma(ffb_handle* h, const float* Q, int ldq, const float* K, cons
 
 int launch_attn_rows(ffb_handle* h, const float* Q, int ldq, const float* K, const float* V, int ldk, float* O, int ldo,
                      int G, int nq, int nk, int q_stride, int q_off, int k_stride, int o_stride, const int* stop, cudaStream_t s,
-                     uint16_t* Os = nullptr, long long os_stride = 0) {
+                     uint16_t* Os = nullptr, long long os_stride = 0, const unsigned char* key_mask = nullptr, int causal = 0) {
     if (G <= 0 || nq <= 0) return FFB_OK;
     AttnGroups g{}; g.ragged = 0; g.nq = nq; g.nk = nk; g.q_stride = q_stride; g.q_off = q_off; g.k_stride = k_stride; g.o_stride = o_stride;
-    g.split_fmt = h->tc_fmt; g.overflow = ovf_ptr(h);
-    if (h->opt_attn_mma)
+    g.split_fmt = h->tc_fmt; g.overflow = ovf_ptr(h); g.key_mask = key_mask; g.causal = causal;
+    if (h->opt_attn_mma && !key_mask && !causal)       // (the masks of the teacher-forced pass exist in the SIMT kernel only)
         return launch_attn_mma(h, Q, ldq, K, V, ldk, O, ldo, g, G, nq, (double)G * nq * nk, PC_ATTN_ROWS, stop, s, Os, os_stride);
     dim3 grid(G, h->H, (nq + AR_BQ - 1) / AR_BQ);
     prof_begin(h, PC_ATTN_ROWS, 4.0 * 64 * (double)G * h->H * nq * nk, s);
@@ -1181,7 +1183,11 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
     uint16_t* ax2 = h->a_x2.as<uint16_t>(); uint16_t* ax2p = h->a_x2p.as<uint16_t>();
     uint16_t* aatt = h->a_att.as<uint16_t>(); uint16_t* ah = h->a_h.as<uint16_t>();
     uint16_t* aqkv = h->a_qkv.as<uint16_t>(); uint16_t* aqc = h->a_qc.as<uint16_t>();
-    const bool hp = h->half_pipe && h->tc_fmt == 2;      // q,k,v / cross-q produced and consumed as fp16x2 (no fp32 copy)
+    // teacher-forced pass (ffb_forward_train): causal + label-padding masks in the self-attention; they exist in the fp32 attention kernel
+    // only, so q,k,v stay fp32 (no half pipeline) while the GEMMs remain on the tensor path
+    const unsigned char* tmask = h->train_kmask;
+    const int causal = tmask ? 1 : 0;
+    const bool hp = h->half_pipe && h->tc_fmt == 2 && !tmask;      // q,k,v / cross-q produced and consumed as fp16x2 (no fp32 copy)
     const long long ssE = h->cap_rows * E, ssF = h->cap_rows * FF;     // elements between the operand splits
     for (int li = 0; li < Ld; ++li) {                    // TransformerDecoderLayer.forward_pre (transformer.py:235-256)
         const DecLayerW& Lw = w.dec[li];
@@ -1196,7 +1202,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
               l.pos = w.qpos; l.ldpos = E; l.pos_mod = P; l.pos_cols = 2 * E; l.M = M; l.N = 3 * E; l.K = E;
               FFB_TRY(launch_linear(h, l, stop, s)); }
             if (!last) {
-                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s));
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, nullptr, 0, tmask, causal));
                 { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, stop, s)); }
             } else {
@@ -1272,7 +1278,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
                     AttnGroups g{}; g.ragged = 0; g.nq = P; g.nk = P; g.q_stride = P; g.q_off = 0; g.k_stride = P; g.o_stride = P;
                     FFB_TRY(launch_attn_h(h, in, aatt, ssE, g, B, P, P, (double)B * P * P, PC_ATTN_ROWS, stop, s));
                 } else
-                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE));
+                FFB_TRY(launch_attn_rows(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, B, P, P, P, 0, P, P, stop, s, aatt, ssE, tmask, causal));
                 { TcLin l; l.A0 = &TS.m_att; l.W = &Tw.sa_out; l.w_scale = Tw.s_sa_out; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E; l.Cmap = &h->mc_x;
                   l.M = M; l.N = E; l.K = E; FFB_TRY(launch_tc(h, l, stop, s)); }
             } else {
@@ -1554,7 +1560,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0, &h->pd_sync, &h->pd_prof};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0, &h->pd_sync, &h->pd_prof, &h->d_label, &h->d_label_mask, &h->d_kmask};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -2042,6 +2048,69 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
     }
     h->decoded = false;
     return emit_logits(h, logits, loc, s);
+}
+
+int ffb_forward_train(ffb_handle* h, const float* coords, const uint8_t* pad_mask, const int64_t* num_input, int32_t N, const int64_t* label,
+                      const uint8_t* label_mask, int32_t label_rows, float* pointer, int32_t loc, void* stream) {
+    if (!h) return FFB_ERR_ARG;
+    if (h->cfg.mode != FFB_MODE_PARALLEL) return fail(h, FFB_ERR_UNSUPPORTED, "ffb_forward_train: the parallel model only (model_para.py:99-171)");
+    if (!label || !label_mask || !pointer) return fail(h, FFB_ERR_ARG, "label / label_mask / pointer is NULL");
+    if (h->xchg_on || h->opt_beam != 1) return fail(h, FFB_ERR_STATE, "ffb_forward_train needs beam width 1 and no batch splitting");
+    // every (wireframe, anchor slot) owns its label sequence: no de-duplication of padded anchors, no last-layer pruning (all positions are outputs)
+    const int dedup0 = h->opt_dedup, prune0 = h->opt_prune, force0 = h->opt_force_F;
+    h->opt_dedup = 0; h->opt_prune = 0;
+    int rc = ffb_encode(h, coords, pad_mask, num_input, N, loc, stream);
+    h->opt_dedup = dedup0; h->opt_force_F = force0;
+    if (rc != FFB_OK) { h->opt_prune = prune0; return rc; }
+    cudaStream_t s = (cudaStream_t)stream;
+    auto done = [&](int code) { h->opt_prune = prune0; h->train_kmask = nullptr; h->decoded = false; return code; };
+    if (label_rows < h->F) return done(fail(h, FFB_ERR_ARG, "label_rows (%d) < F = max(num_input) (%d)", label_rows, h->F));
+    const int T = h->T, P = T - 1, B = (int)h->B;
+    const size_t n_lab = (size_t)N * label_rows * T;
+    const long long* lab_dev = reinterpret_cast<const long long*>(label);
+    const unsigned char* lm_dev = label_mask;
+    std::vector<int64_t> hl(n_lab);
+    if (loc == FFB_HOST) {
+        if (h->d_label.ensure(n_lab * sizeof(int64_t)) != cudaSuccess || h->d_label_mask.ensure(n_lab) != cudaSuccess) return done(fail(h, FFB_ERR_CUDA, "out of device memory (labels)"));
+        if (cudaMemcpyAsync(h->d_label.p, label, n_lab * sizeof(int64_t), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(h->d_label_mask.p, label_mask, n_lab, cudaMemcpyHostToDevice, s) != cudaSuccess) return done(fail(h, FFB_ERR_CUDA, "label upload failed"));
+        lab_dev = h->d_label.as<long long>(); lm_dev = h->d_label_mask.as<unsigned char>();
+        memcpy(hl.data(), label, n_lab * sizeof(int64_t));
+    } else {
+        if (cudaMemcpyAsync(hl.data(), label, n_lab * sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+            return done(fail(h, FFB_ERR_CUDA, "label download failed"));
+    }
+    // every teacher token must address an un-masked memory row of its wireframe (the reference's torch.gather would read padding otherwise)
+    for (int wf = 0; wf < N; ++wf)
+        for (int f = 0; f < h->F; ++f)
+            for (int p = 0; p < P; ++p) {
+                const int64_t t = hl[((size_t)wf * label_rows + f) * T + p];
+                if (t < 0 || t >= h->h_vlen[wf]) return done(fail(h, FFB_ERR_ARG, "label[%d,%d,%d]=%lld is not an un-masked memory row", wf, f, p, (long long)t));
+            }
+    if (h->d_kmask.ensure((size_t)B * P) != cudaSuccess) return done(fail(h, FFB_ERR_CUDA, "out of device memory (key mask)"));
+    int* st = h->state.as<int>();
+    if (cudaMemsetAsync(st, 0, 5 * sizeof(int), s) != cudaSuccess) return done(fail(h, FFB_ERR_CUDA, "memset failed"));
+    h->tok_sel = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        load_labels_kernel<<<grid1d((long long)B * P), 256, 0, s>>>(lab_dev, lm_dev, label_rows, T, h->d_seq_wf.as<int>(), h->d_seq_off.as<int>(), h->tok.as<int>(),
+                                                                    h->d_kmask.as<unsigned char>(), B, P);
+        h->launches++;
+        h->train_kmask = h->d_kmask.as<unsigned char>();
+        rc = run_step(h, P, false, s);
+        h->train_kmask = nullptr;
+        if (rc != FFB_OK) return done(rc);
+        int ovf[2] = {0, 0};
+        if (cudaMemcpyAsync(ovf, st + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+            return done(fail(h, FFB_ERR_CUDA, "state download failed"));
+        if ((ovf[0] == 0 && !(h->half_pipe && ovf[1])) || h->tc_fmt != 2) break;
+        h->tc_fmt = 3; h->fp16_fallbacks++;                                   // an activation left the fp16 range: bf16x3 operands, once more
+        rc = prepare_tc(h, 3, s);
+        if (rc != FFB_OK) return done(rc);
+        cudaMemsetAsync(st, 0, 5 * sizeof(int), s);
+    }
+    // project(decoder(...)) of every position: rows ordered (sequence, position) = [N * F, T - 1, E] (model_para.py:161,166)
+    rc = copy_out(h, h->att.p, pointer, (size_t)B * P * h->E * sizeof(float), loc, s);
+    return done(rc);
 }
 
 int ffb_stop_exchange_export(ffb_handle* h, void* ipc_handle_out) {

@@ -534,6 +534,9 @@ struct AttnGroups {
     const int* q_begin; int q_mul; const int* k_begin; const int* k_len;
     // split output (operand of the tensor-core out-projection): format and overflow flag
     int split_fmt; int* overflow;
+    // teacher-forced pass (model_para.py:120,158-159; attn_rows_kernel only): causal mask (key position <= query position within the group)
+    // and tgt_key_padding_mask (one byte per key row, non-zero = masked)
+    int causal; const unsigned char* key_mask;
 };
 
 __device__ __forceinline__ void attn_group(const AttnGroups& g, int grp, long long& q0, int& nq,
@@ -598,11 +601,12 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict_
             *reinterpret_cast<float4*>(&Vs[r][d4 * 4]) = vv;
         }
         __syncthreads();
-        const bool kvalid = (kt + lane) < nk;
+        const bool kin = (kt + lane) < nk && !(g.key_mask != nullptr && g.key_mask[k0 + kt + lane] != 0);
 #pragma unroll
         for (int i = 0; i < AR_RPW; ++i) {
             const int r = w + 4 * i;
             if (r < nqt) {                                   // warp-uniform
+                const bool kvalid = kin && !(g.causal && (kt + lane) > (qt0 + r));      // generate_square_subsequent_mask (model_para.py:72-74)
                 float s = 0.f;
 #pragma unroll
                 for (int d4 = 0; d4 < 16; ++d4) {
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const float* __restrict_
                     s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
                 }
                 s = kvalid ? s * 0.125f : -INFINITY;          // q * sqrt(1/64): exact power of two
-                const float mn = fmaxf(m[i], warp_max(s));
+                const float mn = fmaxf(m[i], warp_max(s));   // finite from the first tile on (key 0 is never masked: the anchor / SOS position)
                 const float p = expf(s - mn);                 // masked lanes: exp(-inf) = 0
                 const float corr = expf(m[i] - mn);           // first tile: exp(-inf) = 0
                 l[i] = l[i] * corr + warp_sum(p);
@@ -1301,6 +1305,21 @@ __global__ void pack_memory_kernel(const float* __restrict__ in, const int* __re
 }
 
 // int64 prefix [P, B_full] -> int32 tok [P, B_eff] through seq -> first slot map
+// teacher forcing: tok[p*B + b] = label[wf, f, p], kmask[b*P + p] = label_mask[wf, f, p] for the P = T - 1 decoder input positions of sequence
+// b = (wireframe wf, anchor slot f) (model_para.py:84-86: tgt = label[..., :-1])
+__global__ void load_labels_kernel(const long long* __restrict__ label, const unsigned char* __restrict__ label_mask, int label_rows, int T,
+                                   const int* __restrict__ seq_wf, const int* __restrict__ seq_off, int* __restrict__ tok,
+                                   unsigned char* __restrict__ kmask, int B, int P) {
+    const long long total = (long long)B * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / P), p = (int)(i % P);
+        const int wf = seq_wf[b], f = b - seq_off[wf];
+        const size_t src = ((size_t)wf * label_rows + f) * T + p;
+        tok[(size_t)p * B + b] = (int)label[src];
+        kmask[i] = label_mask[src];
+    }
+}
+
 __global__ void load_prefix_kernel(const long long* __restrict__ prefix, const int* __restrict__ seq_slot,
                                    int* __restrict__ tok, int P, int B_full, int B) {
     const int total = P * B;

@@ -186,6 +186,29 @@ class Engine:
         self.encode(coords, pad_mask, num_input)
         return self.decode_greedy(want_steps, out)
 
+    def forward_train(self, coords, pad_mask, num_input, label, label_mask):
+        """Teacher-forced forward pass (SurfaceFormer_Parallel.forward_train, model_para.py:99-171, scheduled_sampling_ratio = 0; forward only):
+        label int64 / label_mask bool [N, rows >= F, T] -> pointer f32 [N * F, T - 1, E] on the inputs' side, F = max(num_input)."""
+        import torch
+        coords, pad_mask, num_input, n, loc = self._prep_inputs(coords, pad_mask, num_input)
+        if loc == FFB_DEVICE:
+            label = label.contiguous().to(torch.int64)
+            label_mask = label_mask.contiguous().to(torch.uint8)
+            f = int(num_input.max().item())
+        else:
+            label = np.ascontiguousarray(label, dtype=np.int64)
+            label_mask = np.ascontiguousarray(label_mask, dtype=np.uint8)
+            f = int(np.max(num_input))
+        T = self.cfg.seq_len(self.mode)
+        if label.ndim != 3 or label.shape[0] != n or label.shape[2] != T or tuple(label_mask.shape) != tuple(label.shape):
+            raise FFBError(f"label / label_mask must be [N={n}, rows, T={T}], got {tuple(label.shape)} / {tuple(label_mask.shape)}")
+        out = self._alloc((n * f, T - 1, self.cfg.num_model), torch.float32, loc)
+        self._keep = (coords, pad_mask, num_input, label, label_mask)
+        self._check(self._lib.ffb_forward_train(self._h, _ptr(coords), _ptr(pad_mask), _ptr(num_input), n, _ptr(label), _ptr(label_mask),
+                                                int(label.shape[1]), _ptr(out), loc, self._stream()))
+        self._loc, self._n = loc, n
+        return out
+
     # -- the step before the path (SURVEY.md 8f1) ------------------------------------------------
     def featurize(self, wireframes, device: bool = True):
         """wireframes: list (one per wireframe) of lists of edges, an edge = sequence of (x, y) points -- the `edges` entry of the

@@ -8,8 +8,9 @@ trainer.py:20), hold parameters under the reference's ``state_dict`` names (stri
 with ``inputs['predict']`` (int64 [N,F,T] or [N,T]) on the input's device.
 
 The modules below are parameter CONTAINERS only; no arithmetic of the path runs in PyTorch.
-``forward`` hands device pointers to libffb200.so through ``Engine``.  Training
-(``forward_train``, model_para.py:99-171) is out of scope and raises.
+``forward`` hands device pointers to libffb200.so through ``Engine``.  ``forward_train``
+(model_para.py:99-171) is the teacher-forced FORWARD pass only (loss / accuracy evaluation of a
+batch, trainer.py:61-79): the library has no backward pass, so gradients do not flow.
 """
 from __future__ import annotations
 
@@ -132,9 +133,30 @@ class _SurfaceFormerB200Base(nn.Module):
         return ent[0]
 
     # -- forward -----------------------------------------------------------------------------
-    def forward_train(self, inputs):
-        raise NotImplementedError("training is out of scope of faceformer_b200 (SURVEY.md section 8f4); "
-                                  "train with the reference classes and load the state_dict here")
+    def forward_train(self, inputs, scheduled_sampling_ratio=0):
+        """Teacher-forced forward pass of SurfaceFormer_Parallel.forward_train (model_para.py:99-171): sets the reference's outputs
+        `embedding` [N*F, L, E] (the encoder memory, replicated per anchor slot as model_para.py:116,164 do), `pointer` [N*F, T-1, E] and
+        `label` [N*F, T-1], which Trainer.compute_loss consumes (trainer.py:61-79).  FORWARD ONLY: the tensors carry no autograd graph
+        (there is no backward pass in libffb200), so this evaluates the training loss / token accuracy of a batch; optimisation steps
+        need the reference classes.  Scheduled sampling (model_para.py:125-142) draws torch random numbers and is not offered."""
+        if self.MODE != MODE_PARALLEL:
+            raise NotImplementedError("forward_train is implemented for SurfaceFormer_Parallel_B200 (model_para.py:99-171)")
+        if scheduled_sampling_ratio:
+            raise NotImplementedError("scheduled sampling is not offered by the forward-only teacher-forced pass")
+        coords = inputs["input"]
+        if not (torch.is_tensor(coords) and coords.is_cuda):
+            raise FFBError("faceformer_b200 has no CPU path: move the batch to a CUDA device")
+        eng = self.engine(coords.device.index if coords.device.index is not None else torch.cuda.current_device())
+        num_input = inputs["num_input"]
+        f = int(num_input.max().item())
+        label, label_mask = inputs["label"], inputs["label_mask"]
+        with torch.cuda.device(coords.device):
+            pointer = eng.forward_train(coords.flatten(2), inputs["input_mask"], num_input, label, label_mask)
+            memory = eng.get_memory()                                               # [N, L, E], zero rows at padded edges
+        inputs["embedding"] = memory.repeat_interleave(f, 0)
+        inputs["pointer"] = pointer
+        inputs["label"] = label[:, :f, 1:].flatten(0, 1)                              # patch_target + flatten (model_para.py:84-86,166)
+        return inputs
 
     def forward_eval(self, inputs):
         coords = inputs["input"]

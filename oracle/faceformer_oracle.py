@@ -144,13 +144,13 @@ def encoder(sd, cfg, src, key_padding_mask, pos):
     return layer_norm(out, sd["encoder.norm.weight"], sd["encoder.norm.bias"])
 
 
-def decoder_layer_pre(sd, p, H, tgt, memory, memory_key_padding_mask, pos, query_pos, tgt_mask=None):
+def decoder_layer_pre(sd, p, H, tgt, memory, memory_key_padding_mask, pos, query_pos, tgt_mask=None, tgt_key_padding_mask=None):
     """TransformerDecoderLayer.forward_pre (transformer.py:235-256)."""
     tgt2 = layer_norm(tgt, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"])
     q = k = tgt2 + query_pos
     tgt2 = multi_head_attention(q, k, tgt2, sd[p + ".self_attn.in_proj_weight"], sd[p + ".self_attn.in_proj_bias"],
                                 sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"], H,
-                                attn_mask=tgt_mask)
+                                attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)
     tgt = tgt + tgt2
     tgt2 = layer_norm(tgt, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"])
     tgt2 = multi_head_attention(tgt2 + query_pos, memory + pos, memory,
@@ -164,12 +164,12 @@ def decoder_layer_pre(sd, p, H, tgt, memory, memory_key_padding_mask, pos, query
     return (tgt + tgt2).astype(F32, copy=False)
 
 
-def decoder(sd, cfg, tgt, memory, memory_key_padding_mask, pos, query_pos, tgt_mask=None):
+def decoder(sd, cfg, tgt, memory, memory_key_padding_mask, pos, query_pos, tgt_mask=None, tgt_key_padding_mask=None):
     """TransformerDecoder.forward (transformer.py:95-124) incl. final norm (115-116)."""
     out = tgt
     for l in range(cfg["num_decoder_layers"]):
         out = decoder_layer_pre(sd, f"decoder.layers.{l}", cfg["num_head"], out, memory,
-                                memory_key_padding_mask, pos, query_pos, tgt_mask)
+                                memory_key_padding_mask, pos, query_pos, tgt_mask, tgt_key_padding_mask)
     return layer_norm(out, sd["decoder.norm.weight"], sd["decoder.norm.bias"])
 
 
@@ -286,3 +286,40 @@ def forced_prefix_logits(sd, cfg, mode, inputs, prefix):
         input_mask = np.repeat(input_mask, Fm, axis=0)
     _, logits, _ = decode_step(sd, cfg, memory, input_mask, pos, qpos, np.asarray(prefix, dtype=np.int64))
     return logits
+
+
+def forward_train(sd, cfg, inputs):
+    """SurfaceFormer_Parallel.forward_train (model_para.py:99-171) with scheduled_sampling_ratio = 0: the teacher-forced pass.
+
+    Returns the reference's outputs: embedding [N*F, L, E], pointer [N*F, T-1, E], label [N*F, T-1] (model_para.py:164-166)."""
+    F = int(np.max(inputs["num_input"]))                                        # model_para.py:103
+    label = np.asarray(inputs["label"])[:, :F, :]                              # :104
+    label_mask = np.asarray(inputs["label_mask"], bool)[:, :F, :]
+    tgt_kpm = label_mask[..., :-1]                                             # process_masks: "tgt is 1 shorter" (:68-69)
+    memory, input_mask, pos, qpos = encode(sd, cfg, MODE_PARALLEL, inputs)     # :107-116 (memory [L,N,E], qpos [T,1,E])
+    tgt = label.transpose(2, 0, 1)                                             # patch_target (:82-88): [T,N,F]
+    target, lab = tgt[:-1], tgt[1:]
+    qpos = qpos[:-1]
+    N = memory.shape[1]
+    T1 = target.shape[0]
+    memory = np.repeat(memory, F, axis=1)                                      # :116 repeat_interleave -> [L, N*F, E]
+    causal = np.triu(np.ones((T1, T1), bool), k=1)                             # generate_square_subsequent_mask (:72-74): True = ignore
+    tgt_emb = gather_rows(memory, target.reshape(T1, N * F))                   # :146-151
+    ptr = decoder(sd, cfg, tgt_emb, memory, np.repeat(input_mask, F, axis=0), pos, qpos, tgt_mask=causal,
+                  tgt_key_padding_mask=tgt_kpm.reshape(N * F, T1))             # :158-159
+    ptr = linear(ptr, sd["project.weight"], sd["project.bias"])               # :161
+    return dict(embedding=memory.transpose(1, 0, 2), pointer=ptr.transpose(1, 0, 2), label=lab.reshape(T1, N * F).T)
+
+
+def teacher_forced_loss(outputs, pad=0):
+    """Trainer.compute_loss (trainer.py:61-79): (mean cross-entropy over non-PAD labels, token accuracy, argmax predictions [N*F, T-1])."""
+    emb, ptr, labels = outputs["embedding"].astype(np.float64), outputs["pointer"].astype(np.float64), outputs["label"]
+    logits = np.matmul(emb, ptr.transpose(0, 2, 1))                            # [NF, L, T-1]
+    m = logits.max(axis=1, keepdims=True)
+    logp = logits - m - np.log(np.exp(logits - m).sum(axis=1, keepdims=True))
+    valid = labels != pad
+    picked = np.take_along_axis(logp, labels[:, None, :], axis=1)[:, 0, :]
+    loss = float(-(picked * valid).sum() / valid.sum())
+    pred = logits.argmax(axis=1)
+    acc = float((valid & (pred == labels)).sum() / (valid.sum() + 1e-10))
+    return loss, acc, pred
