@@ -39,60 +39,76 @@ struct GemmArgs {
     const int* stop;
 };
 
+// BM x BN output tile, TMR x TNR outputs per thread (256 threads = (BM / TMR) x (BN / TNR)).  <128, 64, 8, 4> is the throughput shape;
+// <32, 32, 2, 2> is for the few hundred memory rows of a single wireframe (one 128-row tile would leave all but N / 64 SMs idle and spend
+// ~100 us per launch at the FP64 rate of one SM).  Every output is one fma chain over k in ascending order in either shape: bit-identical.
+template <int BM, int BN, int TMR, int TNR>
 __global__ void __launch_bounds__(256, 2) dgemm_kernel(const GemmArgs a) {
+    static_assert((BM / TMR) * (BN / TNR) == 256 && BN / TNR == 16 && TMR % 2 == 0 && TNR % 2 == 0, "thread layout");
+    constexpr int EA = BM * GBK / 256, EW = BN * GBK / 256;       // consecutive k per thread of the A / W loaders
     if (a.stop != nullptr && *a.stop != 0) return;
-    __shared__ __align__(16) double As[GBK][GBM + 2];
-    __shared__ __align__(16) double Ws[GBK][GBN + 2];
+    __shared__ __align__(16) double As[GBK][BM + 2];
+    __shared__ __align__(16) double Ws[GBK][BN + 2];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
-    double acc[8][4];
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    double acc[TMR][TNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TMR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    // loaders: A tile 128 x 16 -> thread (row = tid / 2, 8 consecutive k); W tile 64 x 16 -> thread (row = tid / 4, 4 consecutive k)
-    const int ar = tid >> 1, ak = (tid & 1) * 8;
-    const int wr = tid >> 2, wk = (tid & 3) * 4;
+        for (int j = 0; j < TNR; ++j) acc[i][j] = 0.0;
+    // loaders: A tile BM x 16 -> thread (row = tid / (16 / EA), EA consecutive k); W tile BN x 16 likewise
+    const int ar = tid / (GBK / EA), ak = (tid % (GBK / EA)) * EA;
+    const int wr = tid / (GBK / EW), wk = (tid % (GBK / EW)) * EW;
     const int arow = m0 + ar;
     long long asrc = -1;
     if (arow < a.M) asrc = a.a_rows ? a.a_rows[arow] : arow;
     const int wrow = n0 + wr;
     // software pipeline: the global loads of k-tile t+1 are in flight while tile t is multiplied out of shared memory
-    double av[8], wv[4];
+    double av[EA], wv[EW];
     auto load_tile = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) av[i] = 0.0;
+        for (int i = 0; i < EA; ++i) av[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wv[i] = 0.0;
+        for (int i = 0; i < EW; ++i) wv[i] = 0.0;
         if (asrc >= 0) {
             if (a.a_f32) {
                 const float* p = reinterpret_cast<const float*>(a.A) + asrc * a.lda + k0 + ak;
-                if (k0 + ak + 8 <= a.K && (a.lda & 3) == 0 && ((uintptr_t)p & 15) == 0) {
+                if (EA == 8 && k0 + ak + 8 <= a.K && (a.lda & 3) == 0 && ((uintptr_t)p & 15) == 0) {
                     const float4 u = *reinterpret_cast<const float4*>(p), v = *reinterpret_cast<const float4*>(p + 4);
-                    av[0] = u.x; av[1] = u.y; av[2] = u.z; av[3] = u.w; av[4] = v.x; av[5] = v.y; av[6] = v.z; av[7] = v.w;
+                    const float t8[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < EA; ++i) av[i] = t8[i < 8 ? i : 0];
+                } else if (EA == 2 && k0 + ak + 2 <= a.K && (a.lda & 1) == 0 && ((uintptr_t)p & 7) == 0) {
+                    const float2 u = *reinterpret_cast<const float2*>(p);
+                    av[0] = u.x; av[EA - 1] = u.y;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (k0 + ak + i < a.K) av[i] = (double)p[i];
+                    for (int i = 0; i < EA; ++i) if (k0 + ak + i < a.K) av[i] = (double)p[i];
                 }
             } else {
                 const double* p = reinterpret_cast<const double*>(a.A) + asrc * a.lda + k0 + ak;
-                if (k0 + ak + 8 <= a.K && (a.lda & 1) == 0 && ((uintptr_t)p & 15) == 0) {
+                if (k0 + ak + EA <= a.K && (a.lda & 1) == 0 && ((uintptr_t)p & 15) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const double2 u = *reinterpret_cast<const double2*>(p + 2 * i); av[2 * i] = u.x; av[2 * i + 1] = u.y; }
+                    for (int i = 0; i < EA / 2; ++i) { const double2 u = *reinterpret_cast<const double2*>(p + 2 * i); av[2 * i] = u.x; av[2 * i + 1] = u.y; }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (k0 + ak + i < a.K) av[i] = p[i];
+                    for (int i = 0; i < EA; ++i) if (k0 + ak + i < a.K) av[i] = p[i];
                 }
             }
         }
         if (wrow < a.N) {
             const float* p = a.W + (size_t)wrow * a.ldw + k0 + wk;
-            if (k0 + wk + 4 <= a.K && (a.ldw & 3) == 0 && ((uintptr_t)p & 15) == 0) {
+            if (EW == 4 && k0 + wk + 4 <= a.K && (a.ldw & 3) == 0 && ((uintptr_t)p & 15) == 0) {
                 const float4 u = *reinterpret_cast<const float4*>(p);
-                wv[0] = u.x; wv[1] = u.y; wv[2] = u.z; wv[3] = u.w;
+                const float t4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < EW; ++i) wv[i] = t4[i < 4 ? i : 0];
+            } else if (EW == 2 && k0 + wk + 2 <= a.K && (a.ldw & 1) == 0 && ((uintptr_t)p & 7) == 0) {
+                const float2 u = *reinterpret_cast<const float2*>(p);
+                wv[0] = u.x; wv[EW - 1] = u.y;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (k0 + wk + i < a.K) wv[i] = (double)p[i];
+                for (int i = 0; i < EW; ++i) if (k0 + wk + i < a.K) wv[i] = (double)p[i];
             }
         }
     };
@@ -100,32 +116,32 @@ __global__ void __launch_bounds__(256, 2) dgemm_kernel(const GemmArgs a) {
     for (int k0 = 0; k0 < a.K; k0 += GBK) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) As[ak + i][ar] = av[i];
+        for (int i = 0; i < EA; ++i) As[ak + i][ar] = av[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) Ws[wk + i][wr] = wv[i];
+        for (int i = 0; i < EW; ++i) Ws[wk + i][wr] = wv[i];
         __syncthreads();
         if (k0 + GBK < a.K) load_tile(k0 + GBK);
 #pragma unroll
         for (int kk = 0; kk < GBK; ++kk) {
-            double am[8], wn[4];
+            double am[TMR], wn[TNR];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const double2 u = *reinterpret_cast<const double2*>(&As[kk][ty * 8 + 2 * i]); am[2 * i] = u.x; am[2 * i + 1] = u.y; }
+            for (int i = 0; i < TMR / 2; ++i) { const double2 u = *reinterpret_cast<const double2*>(&As[kk][ty * TMR + 2 * i]); am[2 * i] = u.x; am[2 * i + 1] = u.y; }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { const double2 u = *reinterpret_cast<const double2*>(&Ws[kk][tx * 4 + 2 * j]); wn[2 * j] = u.x; wn[2 * j + 1] = u.y; }
+            for (int j = 0; j < TNR / 2; ++j) { const double2 u = *reinterpret_cast<const double2*>(&Ws[kk][tx * TNR + 2 * j]); wn[2 * j] = u.x; wn[2 * j + 1] = u.y; }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TMR; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(am[i], wn[j], acc[i][j]);
+                for (int j = 0; j < TNR; ++j) acc[i][j] = fma(am[i], wn[j], acc[i][j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = m0 + ty * 8 + i;
+    for (int i = 0; i < TMR; ++i) {
+        const int r = m0 + ty * TMR + i;
         if (r >= a.M) continue;
         const long long cr = a.c_rows ? a.c_rows[r] : r;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + tx * 4 + j;
+        for (int j = 0; j < TNR; ++j) {
+            const int c = n0 + tx * TNR + j;
             if (c >= a.N) continue;
             double v = acc[i][j];
             if (a.bias) v += (double)a.bias[c];

@@ -134,7 +134,8 @@ __device__ __forceinline__ void ln_phase(const Params& p, int P, bool gather, co
         long long a3 = clock64();
         p.prof[24] += a1 - a0; p.prof[25] += a2 - a1; p.prof[23] += a3 - a2;
     }
-    for (int r = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); r < M; r += gridDim.x * (THREADS / 32)) {
+    // row r -> CTA r % grid, warp r / grid: a few hundred rows spread over all SMs (one or two warps each) instead of filling 8 warps of a few
+    for (int r = blockIdx.x + gridDim.x * (threadIdx.x >> 5); r < M; r += gridDim.x * (THREADS / 32)) {
         const long long c0 = probe ? clock64() : 0;
         const int pos = r % P;
         const float* xr;

@@ -163,5 +163,9 @@ def test_model_class_boundary():
     assert np.array_equal(out["predict"].cpu().numpy(), g["predict"])
     with pytest.raises(FFBError, match="no CPU path"):
         m({k: v.cpu() for k, v in batch.items()})
+    out = m.train()(batch)                 # teacher-forced forward pass (row f4; tests/test_gpu_train.py holds the parity checks)
+    F, T = int(g["batch"]["num_input"].max()), g["cfg"].seq_len(g["mode"])
+    assert tuple(out["pointer"].shape) == (len(g["batch"]["num_input"]) * F, T - 1, g["cfg"].num_model)
+    assert tuple(out["embedding"].shape)[0] == tuple(out["label"].shape)[0] == tuple(out["pointer"].shape)[0]
     with pytest.raises(NotImplementedError):
-        m.train()(batch)
+        m.forward_train(batch, scheduled_sampling_ratio=0.3)
