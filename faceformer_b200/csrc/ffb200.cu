@@ -1390,7 +1390,8 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
 
 
 // ---- the whole greedy loop in one persistent cooperative kernel (persist.cuh) ------------------------------------------------------
-constexpr long long PD_AUTO_ROWS = 1024;     // auto mode: batches with at most this many decoder rows (sequences x (T - 1)) in the last step
+constexpr long long PD_AUTO_ROWS = 896;      // auto mode: batches with at most this many decoder rows (sequences x (T - 1)) in the last step; measured crossover
+                                             // with the multi-kernel path at 860-1010 rows (profiles/probe_persist_threshold_r2.json)
 
 bool persist_applicable(const ffb_handle* h) {
     if (!h->opt_persist || h->pd_grid <= 0) return false;

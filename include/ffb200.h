@@ -130,7 +130,7 @@ enum { FFB_OPT_L0_CACHE = 22 };
 
 /* The whole greedy loop as ONE persistent cooperative kernel (csrc/persist.cuh): all decode steps in a single launch, grid-wide barriers
  * between the phases of a step, the stop predicate (model_para.py:232 / model.py:207-210) evaluated on the device.  0 = off; 1 (default) =
- * auto: batches of at most 1024 decoder rows (sequences x (T - 1): one small wireframe per batch as in the reference's test loop,
+ * auto: batches of at most 896 decoder rows (sequences x (T - 1): one small wireframe per batch as in the reference's test loop,
  * trainer.py:51, and seq2seq) while no option forces one of the multi-kernel pipelines; 2 = wherever it is supported (fp16x2 operand format,
  * float64 head, beam width 1, no batch splitting, <= 64 wireframes).  Larger batches are tensor-bound and stay on the tcgen05 kernels. */
 enum { FFB_OPT_PERSISTENT = 23 };

@@ -69,3 +69,13 @@ def test_persistent_and_multi_kernel_paths_agree_on_fresh_batches(mode, n, seed,
     assert np.array_equal(a["pred"], b["pred"]), f"{(a['pred'] != b['pred']).sum()} token mismatches"
     ok, d = logits_close(a["logits"], b["logits"])
     assert ok, d
+
+
+def test_auto_mode_takes_the_persistent_kernel_only_below_the_measured_crossover():
+    """FFB_OPT_PERSISTENT = 1 (default): sequences x (T - 1) <= 896 decoder rows (profiles/probe_persist_threshold_r2.json)."""
+    cfg = OURS
+    g = dict(cfg=cfg, mode=MODE_PARALLEL, sd=synth.synth_state_dict(cfg, MODE_PARALLEL, 5, "diverse"))
+    small = decode(g, synth.synth_batch(cfg, MODE_PARALLEL, 1, 35, lo=7, hi=7), 1)        # 7 x 36 = 252 rows
+    large = decode(g, synth.synth_batch(cfg, MODE_PARALLEL, 1, 36, lo=40, hi=40), 1)      # 40 x 36 = 1440 rows
+    assert small["used"] and not large["used"]
+    assert small["launches"] < large["launches"] / 10
