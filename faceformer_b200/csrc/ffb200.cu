@@ -85,7 +85,7 @@ struct ffb_handle {
     DevBuf pd_sync, pd_prof;                      // unsigned barrier counter + int[T] per-step counters; FFB_PD_PROF clock sums
     bool used_persist = false;                    // the last decode ran in the persistent kernel
     const unsigned char* train_kmask = nullptr;   // non-null while ffb_forward_train runs its decoder pass: label padding mask [B * (T - 1)]
-    DevBuf d_label, d_label_mask, d_kmask;
+    DevBuf d_label, d_label_mask, d_kmask, dn_q_begin, dn_edge_dst, dn_pos_idx;
     int opt_l0cache = 1;                          // decoder layer 0: q / k / v of earlier prefix positions are cached (exact), only the new position is projected
     DevBuf qkv0_cache, a_qkv0; CUtensorMap ms_qkv0; bool l0_ok = false;
     DevBuf e0pad, a_c; CUtensorMap ms_x2;         // W0 zero-padded to [E, 128]; coordinates as fp16x2 operand [2][cap][128]; split-store map of a_x2
@@ -1565,7 +1565,7 @@ int ffb_destroy(ffb_handle* h) {
     DevBuf* bufs[] = {&h->wblob, &h->wcross, &h->d_row_off, &h->d_vlen, &h->d_pos_idx, &h->d_edge_src, &h->d_edge_dst, &h->d_seq_wf,
                       &h->d_seq_first, &h->d_seq_off, &h->d_slot_seq, &h->d_seq_slot, &h->d_coords, &h->d_predict, &h->d_out_stage,
                       &h->d_mask_stage, &h->d_prefix, &h->mem, &h->Kc, &h->Vc, &h->tok, &h->logits, &h->state, &h->x, &h->x2, &h->qkv,
-                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0, &h->pd_sync, &h->pd_prof, &h->d_label, &h->d_label_mask, &h->d_kmask};
+                      &h->att, &h->hb, &h->xl, &h->tcs[0].wsplit, &h->tcs[1].wsplit, &h->a_x2, &h->a_x2p, &h->a_att, &h->a_h, &h->a_qkv, &h->a_qc, &h->kc_h, &h->vc_h, &h->a_ql, &h->beam_cum, &h->x64, &h->y64, &h->yp64, &h->qkv64, &h->att64, &h->h64, &h->projT, &h->memW, &h->hy32, &h->d_tile_off, &h->e0pad, &h->a_c, &h->qkv0_cache, &h->a_qkv0, &h->pd_sync, &h->pd_prof, &h->d_label, &h->d_label_mask, &h->d_kmask, &h->dn_q_begin, &h->dn_edge_dst, &h->dn_pos_idx};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
@@ -2055,10 +2055,59 @@ int ffb_forced_prefix_logits(ffb_handle* h, const int64_t* prefix, int32_t P, fl
     return emit_logits(h, logits, loc, s);
 }
 
+// ---- forward_train's `embedding` output: the encoder memory of ALL L rows of every wireframe, padded edges included ---------------------
+// The decode path packs the un-masked rows only (padded rows are never read there).  Trainer.compute_loss (trainer.py:61-66) however takes
+// the softmax over ALL L rows of outputs['embedding'], so the rows of padded edges -- queries that attend to the un-masked keys like every
+// other row, transformer.py:169-171 -- carry probability mass and must be the reference's values.  This is a second, dense fp32 encoder pass
+// (rows i * L + r; keys = the un-masked prefix of the wireframe) on the SIMT kernels; the encoder is ~1 % of a teacher-forced pass.
+int run_encoder_dense(ffb_handle* h, const float* coords_dev, float* out_dev, cudaStream_t s) {
+    const int E = h->E, FF = h->FF, N = h->N, L = h->L, nl = h->cfg.num_lines, nt = h->cfg.num_token;
+    const int R = N * L, Re = N * nl;
+    const Weights& w = h->w;
+    std::vector<int> q_begin(N + 1), edge_dst(Re), pos_idx(R);
+    for (int i = 0; i <= N; ++i) q_begin[i] = i * L;
+    for (int i = 0; i < N; ++i) {
+        for (int e = 0; e < nl; ++e) edge_dst[(size_t)i * nl + e] = i * L + nt + e;
+        for (int r = 0; r < L; ++r) pos_idx[(size_t)i * L + r] = r;
+    }
+    FFB_TRY(upload(h, h->dn_q_begin, q_begin, s));
+    FFB_TRY(upload(h, h->dn_edge_dst, edge_dst, s));
+    FFB_TRY(upload(h, h->dn_pos_idx, pos_idx, s));
+    CU(h, cudaStreamSynchronize(s));                       // the std::vectors are pageable
+    const size_t f4 = sizeof(float), rows = (size_t)std::max(R, Re);
+    CU(h, h->x.ensure(rows * E * f4)); CU(h, h->x2.ensure(rows * E * f4)); CU(h, h->qkv.ensure(rows * 3 * E * f4));
+    CU(h, h->att.ensure(rows * E * f4)); CU(h, h->hb.ensure(rows * std::max(FF, E) * f4));
+    float* x = h->x.as<float>(); float* x2 = h->x2.as<float>(); float* qkv = h->qkv.as<float>(); float* att = h->att.as<float>(); float* hb = h->hb.as<float>();
+    const int* qb = h->dn_q_begin.as<int>(); const int* pidx = h->dn_pos_idx.as<int>();
+    // VanillaEmedding (embedding.py:23-38): every edge row, zero-padded ones included
+    { Lin l; l.A = coords_dev; l.lda = h->cfg.in_dim; l.W = w.e0w; l.ldw = h->cfg.in_dim; l.bias = w.e0b; l.C = hb; l.ldc = E; l.M = Re; l.N = E; l.K = h->cfg.in_dim;
+      l.relu = 1; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    { Lin l; l.A = hb; l.lda = E; l.W = w.e2w; l.ldw = E; l.bias = w.e2b; l.C = x; l.ldc = E; l.c_rows = h->dn_edge_dst.as<int>(); l.M = Re; l.N = E; l.K = E;
+      FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    token_rows_kernel<<<grid1d((long long)N * nt * (E / 4)), 256, 0, s>>>(w.tok_table, qb, x, N, nt, E);
+    h->launches++; CU(h, cudaGetLastError());
+    AttnGroups g{}; g.ragged = 1; g.q_begin = qb; g.q_mul = 1; g.k_begin = qb; g.k_len = h->d_vlen.as<int>();
+    double qk = 0; for (int i = 0; i < N; ++i) qk += (double)L * h->h_vlen[i];
+    for (int li = 0; li < h->Le; ++li) {                                  // TransformerEncoderLayer.forward_pre (transformer.py:164-176)
+        const EncLayerW& Lw = w.enc[li];
+        FFB_TRY(launch_ln(h, x, Lw.n1w, Lw.n1b, x2, R, E, nullptr, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = Lw.sa.in_w; l.ldw = E; l.bias = Lw.sa.in_b; l.C = qkv; l.ldc = 3 * E;
+          l.pos = w.pos; l.ldpos = E; l.pos_idx = pidx; l.pos_cols = 2 * E; l.M = R; l.N = 3 * E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        FFB_TRY(launch_attn_tiled(h, qkv, 3 * E, qkv + E, qkv + 2 * E, 3 * E, att, E, g, N, L, qk, nullptr, s));
+        { Lin l; l.A = att; l.lda = E; l.W = Lw.sa.out_w; l.ldw = E; l.bias = Lw.sa.out_b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+          l.M = R; l.N = E; l.K = E; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        FFB_TRY(launch_ln(h, x, Lw.n2w, Lw.n2b, x2, R, E, nullptr, s));
+        { Lin l; l.A = x2; l.lda = E; l.W = Lw.l1w; l.ldw = E; l.bias = Lw.l1b; l.C = hb; l.ldc = FF; l.M = R; l.N = FF; l.K = E; l.relu = 1;
+          FFB_TRY(launch_linear(h, l, nullptr, s)); }
+        { Lin l; l.A = hb; l.lda = FF; l.W = Lw.l2w; l.ldw = FF; l.bias = Lw.l2b; l.C = x; l.ldc = E; l.R = x; l.ldr = E;
+          l.M = R; l.N = E; l.K = FF; FFB_TRY(launch_linear(h, l, nullptr, s)); }
+    }
+    return launch_ln(h, x, w.enc_nw, w.enc_nb, out_dev, R, E, nullptr, s);   // encoder.norm (transformer.py:80-81)
+}
+
 int ffb_forward_train(ffb_handle* h, const float* coords, const uint8_t* pad_mask, const int64_t* num_input, int32_t N, const int64_t* label,
-                      const uint8_t* label_mask, int32_t label_rows, float* pointer, int32_t loc, void* stream) {
+                      const uint8_t* label_mask, int32_t label_rows, float* pointer, float* embedding, int32_t loc, void* stream) {
     if (!h) return FFB_ERR_ARG;
-    if (h->cfg.mode != FFB_MODE_PARALLEL) return fail(h, FFB_ERR_UNSUPPORTED, "ffb_forward_train: the parallel model only (model_para.py:99-171)");
     if (!label || !label_mask || !pointer) return fail(h, FFB_ERR_ARG, "label / label_mask / pointer is NULL");
     if (h->xchg_on || h->opt_beam != 1) return fail(h, FFB_ERR_STATE, "ffb_forward_train needs beam width 1 and no batch splitting");
     // every (wireframe, anchor slot) owns its label sequence: no de-duplication of padded anchors, no last-layer pruning (all positions are outputs)
@@ -2115,6 +2164,15 @@ int ffb_forward_train(ffb_handle* h, const float* coords, const uint8_t* pad_mas
     }
     // project(decoder(...)) of every position: rows ordered (sequence, position) = [N * F, T - 1, E] (model_para.py:161,166)
     rc = copy_out(h, h->att.p, pointer, (size_t)B * P * h->E * sizeof(float), loc, s);
+    if (rc == FFB_OK && embedding != nullptr) {
+        // outputs['embedding'] before its replication per anchor slot: [N, L, E] with the rows of padded edges as the reference computes them
+        const size_t eb = (size_t)N * h->L * h->E * sizeof(float);
+        float* dst = embedding;
+        if (loc == FFB_HOST) { if (h->d_out_stage.ensure(eb) != cudaSuccess) return done(fail(h, FFB_ERR_CUDA, "out of device memory (embedding)")); dst = h->d_out_stage.as<float>(); }
+        const float* coords_dev = (loc == FFB_HOST) ? h->d_coords.as<float>() : coords;
+        rc = run_encoder_dense(h, coords_dev, dst, s);
+        if (rc == FFB_OK && loc == FFB_HOST) rc = copy_out(h, dst, embedding, eb, loc, s);
+    }
     return done(rc);
 }
 

@@ -186,28 +186,35 @@ class Engine:
         self.encode(coords, pad_mask, num_input)
         return self.decode_greedy(want_steps, out)
 
-    def forward_train(self, coords, pad_mask, num_input, label, label_mask):
-        """Teacher-forced forward pass (SurfaceFormer_Parallel.forward_train, model_para.py:99-171, scheduled_sampling_ratio = 0; forward only):
-        label int64 / label_mask bool [N, rows >= F, T] -> pointer f32 [N * F, T - 1, E] on the inputs' side, F = max(num_input)."""
+    def forward_train(self, coords, pad_mask, num_input, label, label_mask, want_embedding: bool = False):
+        """Teacher-forced forward pass (forward only).  want_embedding: also return the reference's `embedding` [N, L, E] (before its
+        replication per anchor slot) with the rows of padded edges computed as the reference does -- compute_loss's softmax runs over them.  Parallel model (model_para.py:99-171, scheduled_sampling_ratio = 0): label int64 /
+        label_mask bool [N, rows >= F, T] -> pointer f32 [N * F, T - 1, E], F = max(num_input).  Seq2seq model (model.py:98-157): label /
+        label_mask [N, T] -> pointer [N, T - 1, E].  The result lives on the inputs' side (CUDA tensor or numpy)."""
         import torch
         coords, pad_mask, num_input, n, loc = self._prep_inputs(coords, pad_mask, num_input)
         if loc == FFB_DEVICE:
             label = label.contiguous().to(torch.int64)
             label_mask = label_mask.contiguous().to(torch.uint8)
-            f = int(num_input.max().item())
         else:
             label = np.ascontiguousarray(label, dtype=np.int64)
             label_mask = np.ascontiguousarray(label_mask, dtype=np.uint8)
-            f = int(np.max(num_input))
         T = self.cfg.seq_len(self.mode)
-        if label.ndim != 3 or label.shape[0] != n or label.shape[2] != T or tuple(label_mask.shape) != tuple(label.shape):
-            raise FFBError(f"label / label_mask must be [N={n}, rows, T={T}], got {tuple(label.shape)} / {tuple(label_mask.shape)}")
+        if self.mode == MODE_PARALLEL:
+            f = int(num_input.max().item()) if loc == FFB_DEVICE else int(np.max(num_input))
+            want = 3
+        else:
+            f, want = 1, 2
+        if label.ndim != want or label.shape[0] != n or label.shape[-1] != T or tuple(label_mask.shape) != tuple(label.shape):
+            raise FFBError(f"label / label_mask must be [N={n}, {'rows, ' if want == 3 else ''}T={T}], got {tuple(label.shape)} / {tuple(label_mask.shape)}")
+        rows = int(label.shape[1]) if want == 3 else 1
         out = self._alloc((n * f, T - 1, self.cfg.num_model), torch.float32, loc)
+        emb = self._alloc((n, self.cfg.mem_len, self.cfg.num_model), torch.float32, loc) if want_embedding else None
         self._keep = (coords, pad_mask, num_input, label, label_mask)
         self._check(self._lib.ffb_forward_train(self._h, _ptr(coords), _ptr(pad_mask), _ptr(num_input), n, _ptr(label), _ptr(label_mask),
-                                                int(label.shape[1]), _ptr(out), loc, self._stream()))
+                                                rows, _ptr(out), _ptr(emb) if want_embedding else None, loc, self._stream()))
         self._loc, self._n = loc, n
-        return out
+        return (out, emb) if want_embedding else out
 
     # -- the step before the path (SURVEY.md 8f1) ------------------------------------------------
     def featurize(self, wireframes, device: bool = True):

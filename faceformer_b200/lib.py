@@ -64,7 +64,7 @@ SIGNATURES = {
     "ffb_overflowed": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
     "ffb_steps_launched": (C.c_int, [_P]),
     "ffb_used_persistent": (C.c_int, [_P]),
-    "ffb_forward_train": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P]),
+    "ffb_forward_train": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "ffb_phase_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32]),
     "ffb_profile_read": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ffb_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -134,28 +134,33 @@ class _SurfaceFormerB200Base(nn.Module):
 
     # -- forward -----------------------------------------------------------------------------
     def forward_train(self, inputs, scheduled_sampling_ratio=0):
-        """Teacher-forced forward pass of SurfaceFormer_Parallel.forward_train (model_para.py:99-171): sets the reference's outputs
-        `embedding` [N*F, L, E] (the encoder memory, replicated per anchor slot as model_para.py:116,164 do), `pointer` [N*F, T-1, E] and
-        `label` [N*F, T-1], which Trainer.compute_loss consumes (trainer.py:61-79).  FORWARD ONLY: the tensors carry no autograd graph
+        """Teacher-forced forward pass of forward_train (model_para.py:99-171 / model.py:98-157): sets the reference's outputs `embedding`
+        ([N*F, L, E]: the encoder memory, replicated per anchor slot as model_para.py:116,164 do; [N, L, E] for seq2seq), `pointer`
+        ([N*F, T-1, E] / [N, T-1, E]) and `label` ([N*F, T-1] / [N, T-1]), which Trainer.compute_loss consumes (trainer.py:61-79).  FORWARD ONLY: the tensors carry no autograd graph
         (there is no backward pass in libffb200), so this evaluates the training loss / token accuracy of a batch; optimisation steps
         need the reference classes.  Scheduled sampling (model_para.py:125-142) draws torch random numbers and is not offered."""
-        if self.MODE != MODE_PARALLEL:
-            raise NotImplementedError("forward_train is implemented for SurfaceFormer_Parallel_B200 (model_para.py:99-171)")
         if scheduled_sampling_ratio:
             raise NotImplementedError("scheduled sampling is not offered by the forward-only teacher-forced pass")
         coords = inputs["input"]
         if not (torch.is_tensor(coords) and coords.is_cuda):
             raise FFBError("faceformer_b200 has no CPU path: move the batch to a CUDA device")
         eng = self.engine(coords.device.index if coords.device.index is not None else torch.cuda.current_device())
-        num_input = inputs["num_input"]
-        f = int(num_input.max().item())
         label, label_mask = inputs["label"], inputs["label_mask"]
         with torch.cuda.device(coords.device):
-            pointer = eng.forward_train(coords.flatten(2), inputs["input_mask"], num_input, label, label_mask)
-            memory = eng.get_memory()                                               # [N, L, E], zero rows at padded edges
-        inputs["embedding"] = memory.repeat_interleave(f, 0)
+            if self.MODE == MODE_PARALLEL:
+                num_input = inputs["num_input"]
+                f = int(num_input.max().item())
+                pointer, memory = eng.forward_train(coords.flatten(2), inputs["input_mask"], num_input, label, label_mask, want_embedding=True)
+            else:
+                pointer, memory = eng.forward_train(coords.flatten(2), inputs["input_mask"], None, label, label_mask, want_embedding=True)
+            # memory [N, L, E] incl. the rows of padded edges (compute_loss's softmax runs over all L rows, trainer.py:64-69)
+        if self.MODE == MODE_PARALLEL:
+            inputs["embedding"] = memory.repeat_interleave(f, 0)                      # model_para.py:116,164
+            inputs["label"] = label[:, :f, 1:].flatten(0, 1)                          # patch_target + flatten (model_para.py:84-86,166)
+        else:
+            inputs["embedding"] = memory                                              # model.py:154
+            inputs["label"] = label[:, 1:]                                            # model.py:76-80,156
         inputs["pointer"] = pointer
-        inputs["label"] = label[:, :f, 1:].flatten(0, 1)                              # patch_target + flatten (model_para.py:84-86,166)
         return inputs
 
     def forward_eval(self, inputs):

@@ -246,6 +246,27 @@ def polygon_batch(cfg: ModelConfig, n: int, seed: int = 0, max_faces: int = 5):
 
 
 # --------------------------------------------------------------------------- checkpoint fixtures
+def seq2seq_labels(cfg: ModelConfig, batch: dict, seed: int = 0):
+    """Teacher sequences for a seq2seq batch (the layout of datasets/data.py: SOS, co-edge tokens with SEP between faces, EOS, then PAD):
+    adds `label` [N, T] int64 and `label_mask` [N, T] bool (True = PAD) to a copy of `batch`.  Tokens address un-masked memory rows only."""
+    rng = np.random.default_rng([seed, 15485863])
+    T = cfg.label_seq_length
+    n = batch["input"].shape[0]
+    label = np.zeros((n, T), np.int64)
+    nvalid = (~batch["input_mask"]).sum(1)
+    for i in range(n):
+        length = int(rng.integers(3, T - 1))
+        seq = rng.integers(cfg.num_token, cfg.num_token + max(1, int(nvalid[i])), size=length)
+        seq[rng.random(length) < 0.15] = 2                       # token.SEP
+        label[i, 0] = 1                                          # token.SOS
+        label[i, 1:1 + length] = seq
+        label[i, 1 + length] = 3                                 # token.EOS
+    out = dict(batch)
+    out["label"] = label
+    out["label_mask"] = label == 0
+    return out
+
+
 def quantize_state_dict(sd, bits: int = 8):
     """Snap every >= 2-d float tensor to a per-tensor symmetric integer grid (w = q * scale) so that a trained checkpoint
     can be committed as a small fixture.  Returns the npz payload: ``name`` (1-d / int tensors as they are) or

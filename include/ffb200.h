@@ -89,15 +89,19 @@ enum { FFB_OPT_BEAM = 15 };
  * FFB_OPT_HEAD_FP64: 1 (default) = decoder.norm + project + the pointer dot product of the last position in float64; 0 = fp32. */
 enum { FFB_OPT_ENCODER_PRECISION = 16, FFB_OPT_HEAD_FP64 = 17 };
 
-/* Teacher-forced FORWARD pass of SurfaceFormer_Parallel.forward_train (faceformer/models/model_para.py:99-171 with scheduled_sampling_ratio = 0):
+/* Teacher-forced FORWARD pass of SurfaceFormer_Parallel.forward_train (faceformer/models/model_para.py:99-171 with scheduled_sampling_ratio = 0;
+ * seq2seq handles: SurfaceFormer.forward_train, faceformer/models/model.py:98-157, with label / label_mask [N, T], i.e. label_rows = 1, F = 1):
  * encoder, then ONE decoder pass over the T - 1 input positions label[..., :-1] of every (wireframe, anchor slot) sequence with the causal mask
  * (model_para.py:72-74,120) and label_mask[..., :-1] as tgt_key_padding_mask (model_para.py:68-69,158-159), then project:
  * pointer [N * F, T - 1, E] fp32 with F = max(num_input) (the reference's outputs['pointer']).  label / label_mask: [N, label_rows, T] int64 / uint8
  * (non-zero = padding), label_rows >= F; only the first F rows of a wireframe are read (model_para.py:104).  Every teacher token must address an
  * un-masked memory row.  Forward only: there is no backward pass in this library -- this is the loss / accuracy evaluation of a teacher-forced
- * batch (faceformer/trainer.py:61-79), not a training step.  The batch stays encoded WITHOUT padded-anchor de-duplication (ffb_get_memory works). */
+ * batch (faceformer/trainer.py:61-79), not a training step.  embedding (optional, may be NULL): [N, L, E] fp32 = the reference's
+ * outputs['embedding'] before its replication per anchor slot (model_para.py:116,164) INCLUDING the rows of padded edges, which compute_loss's
+ * softmax runs over (trainer.py:64-69); they come from a second, dense fp32 encoder pass (ffb_get_memory returns zeros in those rows).
+ * The batch stays encoded WITHOUT padded-anchor de-duplication. */
 int ffb_forward_train(ffb_handle* h, const float* coords, const uint8_t* pad_mask, const int64_t* num_input, int32_t N, const int64_t* label,
-                      const uint8_t* label_mask, int32_t label_rows, float* pointer, int32_t loc, void* stream);
+                      const uint8_t* label_mask, int32_t label_rows, float* pointer, float* embedding, int32_t loc, void* stream);
 
 /* ---- one batch split over several GPUs (BASELINE.json configs[2]: "batch=128 sharded over 8xB200") -------------------------------
  * One process per GPU decodes a SHARE of the wireframes of one global batch.  forward_eval couples the wireframes of a batch in two

@@ -288,15 +288,21 @@ def forced_prefix_logits(sd, cfg, mode, inputs, prefix):
     return logits
 
 
-def forward_train(sd, cfg, inputs):
-    """SurfaceFormer_Parallel.forward_train (model_para.py:99-171) with scheduled_sampling_ratio = 0: the teacher-forced pass.
+def forward_train(sd, cfg, inputs, mode=MODE_PARALLEL):
+    """SurfaceFormer_Parallel.forward_train (model_para.py:99-171) / SurfaceFormer.forward_train (model.py:98-157) with
+    scheduled_sampling_ratio = 0: the teacher-forced pass.
 
-    Returns the reference's outputs: embedding [N*F, L, E], pointer [N*F, T-1, E], label [N*F, T-1] (model_para.py:164-166)."""
-    F = int(np.max(inputs["num_input"]))                                        # model_para.py:103
-    label = np.asarray(inputs["label"])[:, :F, :]                              # :104
-    label_mask = np.asarray(inputs["label_mask"], bool)[:, :F, :]
+    Returns the reference's outputs: embedding [B, L, E], pointer [B, T-1, E], label [B, T-1] with B = N*F (parallel, model_para.py:164-166)
+    or B = N (seq2seq, model.py:154-156)."""
+    label, label_mask = np.asarray(inputs["label"]), np.asarray(inputs["label_mask"], bool)
+    F = 1
+    if mode == MODE_PARALLEL:
+        F = int(np.max(inputs["num_input"]))                                    # model_para.py:103
+        label, label_mask = label[:, :F, :], label_mask[:, :F, :]              # :104
+    else:
+        label, label_mask = label[:, None, :], label_mask[:, None, :]          # one sequence per wireframe
     tgt_kpm = label_mask[..., :-1]                                             # process_masks: "tgt is 1 shorter" (:68-69)
-    memory, input_mask, pos, qpos = encode(sd, cfg, MODE_PARALLEL, inputs)     # :107-116 (memory [L,N,E], qpos [T,1,E])
+    memory, input_mask, pos, qpos = encode(sd, cfg, mode, inputs)              # :107-116 (memory [L,N,E], qpos [T,1,E])
     tgt = label.transpose(2, 0, 1)                                             # patch_target (:82-88): [T,N,F]
     target, lab = tgt[:-1], tgt[1:]
     qpos = qpos[:-1]

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from faceformer_b200 import synth
-from faceformer_b200.config import MODE_PARALLEL, ModelConfig
+from faceformer_b200.config import MODE_PARALLEL, MODE_SEQ2SEQ, ModelConfig
 from faceformer_b200.engine import Engine
 from faceformer_b200.lib import FFBError
 from oracle import faceformer_oracle as orc
@@ -23,32 +23,39 @@ def load(name):
         g = {k: z[k] for k in z.files}
     meta = json.loads(str(g.pop("meta")))
     cfg = ModelConfig(**meta["cfg"])
-    g.update(cfg=cfg, meta=meta, sd=synth.load_state_dict_npz(os.path.join(GOLDEN, meta["weights"])),
-             batch=synth.polygon_batch(cfg, meta["n"], seed=meta["seed"]))
+    mode = meta.get("mode", MODE_PARALLEL)
+    if mode == MODE_PARALLEL:
+        sd = synth.load_state_dict_npz(os.path.join(GOLDEN, meta["weights"]))
+        batch = synth.polygon_batch(cfg, meta["n"], seed=meta["seed"])
+    else:
+        sd = synth.synth_state_dict(cfg, mode, meta["weights"][1], "diverse")
+        batch = synth.seq2seq_labels(cfg, synth.synth_batch(cfg, mode, meta["n"], meta["seed"], lo=5, hi=min(60, cfg.num_lines)), meta["seed"])
+    g.update(cfg=cfg, mode=mode, meta=meta, sd=sd, batch=batch)
     return g
 
 
-@pytest.mark.parametrize("name", ["train_forward_tiny", "train_forward_mid"])
+@pytest.mark.parametrize("name", ["train_forward_tiny", "train_forward_mid", "train_forward_seq2seq_tiny", "train_forward_seq2seq"])
 @pytest.mark.parametrize("device_path", [True, False])
 def test_teacher_forced_pointer_loss_and_accuracy_match_the_reference(name, device_path):
     g = load(name)
-    b = g["batch"]
-    e = Engine(g["cfg"], MODE_PARALLEL, 0)
+    b, mode = g["batch"], g["mode"]
+    e = Engine(g["cfg"], mode, 0)
     e.load_state_dict(g["sd"])
     coords = b["input"].reshape(b["input"].shape[0], b["input"].shape[1], -1)
-    args = [coords, b["input_mask"], b["num_input"], b["label"], b["label_mask"]]
+    args = [coords, b["input_mask"], b["num_input"] if mode == MODE_PARALLEL else None, b["label"], b["label_mask"]]
     if device_path:
-        args = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in args]
-    ptr = e.forward_train(*args)
-    mem = e.get_memory()
+        args = [None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in args]
+    ptr, mem = e.forward_train(*args, want_embedding=True)
     if device_path:
         ptr, mem = ptr.cpu().numpy(), mem.cpu().numpy()
-    F = int(b["num_input"].max())
-    T = g["cfg"].seq_len(MODE_PARALLEL)
+    F = int(b["num_input"].max()) if mode == MODE_PARALLEL else 1
+    T = g["cfg"].seq_len(mode)
     assert ptr.shape == (len(b["num_input"]) * F, T - 1, g["cfg"].num_model)
-    st = g["meta"]["seq_step"]
-    ok, d = logits_close(ptr[::st], g["pointer"], b64=g["pointer64"])
+    st, ps = g["meta"]["seq_step"], g["meta"].get("pos_step", 1)
+    ok, d = logits_close(ptr[::st, ::ps], g["pointer"], b64=g["pointer64"])
     assert ok, f"pointer differs from the reference's by {d}"
+    assert mem.shape == g["memory"].shape                          # outputs['embedding'] per wireframe, rows of padded edges included
+    assert np.max(np.abs(mem - g["memory"])) <= LOGIT_TOL
     # what the trainer computes from it (trainer.py:61-79)
     out = dict(embedding=np.repeat(mem, F, axis=0), pointer=ptr, label=g["label"])
     loss, acc, pred = orc.teacher_forced_loss(out)

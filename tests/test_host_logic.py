@@ -65,14 +65,11 @@ def test_b200_model_classes_have_the_reference_state_dict_layout(mode, cfg):
         assert tuple(sd[n].shape) == tuple(shape)
         assert sd[n].dtype == (torch.int64 if dt == "i8" else torch.float32)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(cfg, mode, 1).items()}, strict=True)
-    if mode == MODE_PARALLEL:        # forward_train = the teacher-forced forward pass (row f4); like eval it has no CPU path
-        with pytest.raises(FFBError, match="no CPU path"):
-            m.train()({"input": torch.zeros(1, cfg.num_lines, 50, 2), "input_mask": torch.zeros(1, cfg.num_lines, dtype=torch.bool)})
-        with pytest.raises(NotImplementedError):
-            m.forward_train({}, scheduled_sampling_ratio=0.5)
-    else:
-        with pytest.raises(NotImplementedError):
-            m.train()({})
+    # forward_train = the teacher-forced forward pass (row f4); like eval it has no CPU path
+    with pytest.raises(FFBError, match="no CPU path"):
+        m.train()({"input": torch.zeros(1, cfg.num_lines, 50, 2), "input_mask": torch.zeros(1, cfg.num_lines, dtype=torch.bool)})
+    with pytest.raises(NotImplementedError):
+        m.forward_train({}, scheduled_sampling_ratio=0.5)
     with pytest.raises(FFBError, match="no CPU path"):
         m.eval()({"input": torch.zeros(1, cfg.num_lines, 50, 2), "input_mask": torch.zeros(1, cfg.num_lines, dtype=torch.bool)})
 
