@@ -1390,6 +1390,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
 
 
 // ---- the whole greedy loop in one persistent cooperative kernel (persist.cuh) ------------------------------------------------------
+constexpr int FFB_PD_UNAVAILABLE = 1;         // run_persistent: the cooperative launch was refused; the caller runs the per-step kernels instead
 constexpr long long PD_AUTO_ROWS = 896;      // auto mode: batches with at most this many decoder rows (sequences x (T - 1)) in the last step; measured crossover
                                              // with the multi-kernel path at 860-1010 rows (profiles/probe_persist_threshold_r2.json)
 
@@ -1440,8 +1441,15 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
     void* args[] = {(void*)&p};
     prof_begin(h, PC_OTHER, 0.0, s);
     const void* kern = (h->E <= 512) ? (const void*)pd::decode_persistent_kernel<4> : (const void*)pd::decode_persistent_kernel<8>;
-    CU(h, cudaLaunchCooperativeKernel(kern, dim3(h->pd_grid), dim3(pd::THREADS), args, (size_t)pd::SMEM_BYTES, s));
+    const cudaError_t le = cudaLaunchCooperativeKernel(kern, dim3(h->pd_grid), dim3(pd::THREADS), args, (size_t)pd::SMEM_BYTES, s);
     prof_end(h, s);
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+        // the grid cannot be co-resident right now (another context holds SM resources): this handle stays on the multi-kernel path
+        cudaGetLastError();
+        h->pd_grid = 0;
+        return FFB_PD_UNAVAILABLE;
+    }
+    CU(h, le);
     h->launches++;
     h->last_P = 0;
     if (prof) {
@@ -1769,7 +1777,11 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         h->used_persist = persist_applicable(h);
         if (h->used_persist) {
             // small batch: every step of the loop inside ONE cooperative kernel; the stop predicate never leaves the device
-            FFB_TRY(run_persistent(h, s));
+            const int prc = run_persistent(h, s);
+            if (prc == FFB_PD_UNAVAILABLE) h->used_persist = false;
+            else if (prc != FFB_OK) return prc;
+        }
+        if (h->used_persist) {
             if (!h->opt_prune) FFB_TRY(run_project_rows(h, s));       // seq2seq 'pointer' (model.py:216-217): project(decoder.norm(.)) of every position
             h->steps_launched = T - 1;
         } else
