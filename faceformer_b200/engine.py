@@ -223,7 +223,7 @@ class Engine:
         num_input [N] i64) as torch tensors on the engine's GPU (device=True) or numpy arrays computed through host buffers."""
         import torch
         pts, eoff, woff = self._ragged(wireframes)
-        n, nl, P = len(wireframes), self.cfg.num_lines, self.cfg.num_points_per_line
+        n, nl, P = len(woff) - 1, self.cfg.num_lines, self.cfg.num_points_per_line
         if device:
             dev = torch.device("cuda", self.device)
             t_pts, t_e, t_w = (torch.from_numpy(x).to(dev) for x in (pts, eoff, woff))
@@ -242,7 +242,16 @@ class Engine:
 
     # -- the step after the path --------------------------------------------------
     @staticmethod
+    def flatten_wireframes(wireframes):
+        """Nested `edges` lists -> the flat (points [n, 2] f64, edge offsets, wireframe offsets) arrays the C ABI takes.  This Python loop
+        costs as much as the reference's own per-edge numpy featurisation (profiles/probe_f1_f2_r2.json): do it ONCE per dataset (the JSON
+        is static) and hand the tuple to featurize / parse_faces instead of the nested lists."""
+        return Engine._ragged(wireframes)
+
+    @staticmethod
     def _ragged(wireframes):
+        if isinstance(wireframes, tuple) and len(wireframes) == 3 and all(isinstance(a, np.ndarray) for a in wireframes):
+            return wireframes                                  # already flat (flatten_wireframes)
         pts, eoff, woff = [], [0], [0]
         for edges in wireframes:
             for e in edges:
