@@ -6,8 +6,9 @@
 //
 // Why: with one wireframe per batch (the reference's own test loop, trainer.py:51; BASELINE configs[0]) a decode step is 65 MB of weights
 // against a few hundred activation rows.  As ~72 dependent kernel launches it costs 0.7-0.9 ms; the work itself is a few microseconds per
-// phase.  This kernel runs ALL steps of the loop in one launch: the grid (2 CTAs per SM, co-resident through a cooperative launch) walks
-// the phases of a step and meets at a grid-wide barrier between them; the stop predicate is evaluated on the device after every step.
+// phase.  This kernel runs ALL steps of the loop in one launch: the grid (one CTA of 256 threads per SM, co-resident through a cooperative
+// launch) walks the phases of a step and meets at a grid-wide barrier between them; the stop predicate is evaluated on the device after
+// every step.
 //
 // Phases per decoder layer (10) + the head (1):
 //   0  xs, xps = split(LN1(x)), split(LN1(x) + qpos)            layer 0: x = memory[tokens] is gathered here (model_para.py:217-219)
@@ -22,12 +23,18 @@
 //   9  x      += h W_2^T + b
 //   head       float64 LayerNorm of the last position, folded pointer dot (memW, ffb200.cu run_head_fold), first-max argmax, append, counters
 //
-// GEMM items are 32 x 64 output tiles on 256 threads: two groups of four warps split K (even / odd 64-wide chunks) and are summed in a fixed
-// order; mma.sync m16n8k16 on fp16x2 split operands (hi*hi + lo*hi + hi*lo), fp32 accumulation, register accumulators drained with
-// round-to-nearest adds every 128 k of a group -- the precision class of gemm_tc.cuh.  Every GEMM operand lives in global memory (L2 at
-// these sizes) already split, so a chunk goes cp.async -> ldmatrix -> MMA with no conversion; up to 192 KB (a whole K = 512 item) is in
-// flight per CTA.  Weights are the pre-scaled fp16x2 arrays of the tensor-core path.  The attention core is attn_mma.cuh's 3xTF32 tile
-// routine, two independent work items per CTA (128 threads each, named barriers).
+// GEMM items are 32 x 32 output tiles (32 x 64 for the fused phase 5) on 256 threads: two groups of four warps split K (even / odd 64-wide
+// chunks) and are summed in a fixed order; mma.sync m16n8k16 on fp16x2 split operands (hi*hi + lo*hi + hi*lo), fp32 accumulation, register
+// accumulators drained with round-to-nearest adds every 128 k of a group -- the precision class of gemm_tc.cuh.  Every GEMM operand lives in
+// global memory (L2 at these sizes) already split, so a chunk goes cp.async -> ldmatrix -> MMA with no conversion; up to 192 KB (a whole
+// K = 512 item) is in flight per CTA; bias / residual are prefetched before the mainloop.  Weights are the pre-scaled fp16x2 arrays of the
+// tensor-core path.  Attention items use all 8 warps (attn_item below): the arithmetic of attn_mma.cuh (3xTF32 mma.sync, online softmax), keys
+// split over the warps, partials merged in a fixed order.
+//
+// Performance notes (profiles/persist_phase_clocks_r2.md).  One L2 access costs ~1.1 k clk in situ and the per-barrier acquire fence drops
+// L1, so every phase is a chain of L2 round trips and every spilled register is one more: the kernel is built to stay spill-free in its hot
+// loops at 255 registers (one call site per routine, arrays sized by the NV template parameter).  It is sensitive to that: two later
+// experiments that added a third GEMM instantiation or a LayerNorm tail to the GEMM items lost 5-30 % through re-allocation alone.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
