@@ -6,9 +6,10 @@ import pytest
 import torch
 
 from faceformer_b200 import synth
-from faceformer_b200.config import MODE_PARALLEL, MODE_SEQ2SEQ, OURS
+from faceformer_b200.config import MODE_PARALLEL, MODE_SEQ2SEQ, OURS, SEQ2SEQ
 from faceformer_b200.engine import Engine
 from faceformer_b200.lib import FFB_OPT_PERSISTENT
+from oracle import faceformer_oracle as orc
 from util import LOGIT_TOL, load_case, logits_close
 
 pytestmark = pytest.mark.gpu
@@ -79,3 +80,24 @@ def test_auto_mode_takes_the_persistent_kernel_only_below_the_measured_crossover
     large = decode(g, synth.synth_batch(cfg, MODE_PARALLEL, 1, 36, lo=40, hi=40), 1)      # 40 x 36 = 1440 rows
     assert small["used"] and not large["used"]
     assert small["launches"] < large["launches"] / 10
+
+
+@pytest.mark.parametrize("cfg,mode,n,seed,lo,hi,steps", [(SEQ2SEQ, MODE_SEQ2SEQ, 2, 68, 6, 14, 4),      # cumulative EOS count reaches N at step 4 (model.py:207-210)
+                                                         (SEQ2SEQ, MODE_SEQ2SEQ, 2, 62, 6, 14, 2),
+                                                         (OURS, MODE_PARALLEL, 1, 108, 5, 9, 5),        # all sequences emit a special token at step 5 (model_para.py:232)
+                                                         (OURS, MODE_PARALLEL, 1, 100, 5, 9, 1)])
+def test_early_stop_is_decided_on_the_device_like_the_reference_does(cfg, mode, n, seed, lo, hi, steps):
+    """The persistent kernel evaluates the stop predicate itself after every step and leaves the loop: executed steps, tokens up to the stop
+    and the zero padding behind it must equal the numpy oracle's (= the reference's loop), on full-size (E = 512) models."""
+    sd = synth.synth_state_dict(cfg, mode, seed, "diverse")
+    batch = synth.synth_batch(cfg, mode, n, seed, lo=lo, hi=hi)
+    want = orc.forward_eval(sd, cfg.to_dict(), mode, batch, return_trace=True, max_steps=steps + 3)
+    assert want["steps"] == steps
+    g = dict(cfg=cfg, mode=mode, sd=sd)
+    a, b = decode(g, batch, 1), decode(g, batch, 0)
+    assert a["used"] and not b["used"]
+    for r in (a, b):
+        assert r["steps"] == steps
+        assert np.array_equal(r["pred"], want["predict"]), f"{(r['pred'] != want['predict']).sum()} token mismatches"
+    ok, d = logits_close(a["logits"], want["logits"][-1])
+    assert ok, d
