@@ -169,3 +169,29 @@ def test_model_class_boundary():
     assert tuple(out["embedding"].shape)[0] == tuple(out["label"].shape)[0] == tuple(out["pointer"].shape)[0]
     with pytest.raises(NotImplementedError):
         m.forward_train(batch, scheduled_sampling_ratio=0.3)
+
+
+def test_strict_logit_bar_report():
+    """north_star's bar read literally: |logit - reference fp32 logit| <= 1e-4 (x max|logit| / 32 above 32), WITHOUT the noise-floor clause of
+    util.logits_close.  Default path, every full-size golden.  The bar holds everywhere except where the reference's own fp32 run is >= 0.8e-4 from
+    its float64 evaluation (two correct fp32 evaluations cannot be asked to agree more closely than either agrees with the exact result); those
+    fixtures are pinned here BY NAME with their measured distance, so a regression of the decoder stack shows up as a failure, not as drift
+    inside a widened tolerance.  Distances to the float64 evaluation are asserted to stay below the reference's own."""
+    known_over = {"ours_wide300": 1.5e-4}            # measured 1.26e-4 (fp16x2 pipeline); reference fp32 vs float64 there: 0.86e-4
+    report = {}
+    for name in ["ours_parallel_small", "seq2seq_single64", "perspective_small", "ours_wide300", "mid_parallel_trained", "mid_parallel_trained_b"]:
+        g = load_case(name)
+        e = make_engine(g)
+        run(e, g["batch"], True)
+        lg = e.get_last_logits().cpu().numpy()
+        e.close()
+        ref, ref64 = g["last_logits"], g["last_logits64"]
+        m = ref != np.finfo(np.float32).min
+        scale = max(1.0, float(np.max(np.abs(ref[m]))) / 32.0)
+        d32 = float(np.max(np.abs(lg[m] - ref[m]))) / scale
+        d64 = float(np.max(np.abs(lg[m].astype(np.float64) - ref64[m])))
+        n64 = float(np.max(np.abs(ref[m].astype(np.float64) - ref64[m])))
+        report[name] = (d32, d64, n64)
+        assert d32 <= known_over.get(name, LOGIT_TOL), f"{name}: {d32:.3e} from the reference's fp32 logits (scaled), bar {known_over.get(name, LOGIT_TOL):.1e}"
+        assert d64 <= n64, f"{name}: {d64:.3e} from the float64 evaluation, the reference's own fp32 run is {n64:.3e} from it"
+    print("strict logit report (scaled |ours - ref32|, |ours - ref64|, |ref32 - ref64|):", {k: tuple(f"{x:.2e}" for x in v) for k, v in report.items()})
