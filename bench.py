@@ -529,7 +529,9 @@ def run_small(args, name):
                                                 "barriers and dependent L2 round trips per decode step, not by bytes)" if persistent else
                                                 "decode step (all kernels of one greedy step; launch-latency bound at this size)"),
                      "persistent_kernel": persistent,
-                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                     "traffic": (load_traffic("decode_persistent_kernel")[0] if persistent and name == "seq2seq_n1_64" else None),
+                     "traffic_note": (load_traffic("decode_persistent_kernel")[1] if persistent and name == "seq2seq_n1_64" else None),
                      "algorithmic_bytes_per_decode_step": bytes_total / steps_total, "launches_per_decode_step": launches / args.steps / steps_total,
                      "kernel_ms_by_class": {k: round(v["ms"], 3) for k, v in prof.items()},
                      "kernel_ms_sum_vs_step_ms": [round(sum(v["ms"] for v in prof.values()), 3), round(ms / args.steps, 3)],
