@@ -41,9 +41,10 @@ __device__ __forceinline__ uint32_t tf32_lo(float x) {
     return r;
 }
 
-// One work item = (group, head, tile of <= 64 query rows) on 128 threads; `smem` = AM_SMEM_BYTES of shared memory.  Callable from a
-// persistent kernel (persist.cuh): global reads go through L2 (__ldcg: q / k / v may have been written by other CTAs of the SAME launch),
-// and with q_staged the caller has already placed the pre-scaled Q tile in smem[0, 64 * 80) and synchronised the CTA.
+// One work item = (group, head, tile of <= 64 query rows) on 128 threads; `smem` = AM_SMEM_BYTES of shared memory.  Written as a device routine
+// so that a multi-phase kernel can run it on any 128-thread group: global reads go through L2 (__ldcg: q / k / v may have been written by other
+// CTAs of the SAME launch), the 128 threads meet at named barrier `bar_id`, and with q_staged the caller has already placed the pre-scaled Q tile in
+// smem[0, 64 * 80).  (persist.cuh started from this routine and now carries its own warp-level variant of the same arithmetic, attn_item.)
 __device__ __forceinline__ void attn_mma_tile(float* smem, bool q_staged, const float* __restrict__ Q, int ldq,
                                               const float* __restrict__ K, const float* __restrict__ V, int ldk,
                                               float* __restrict__ O, int ldo, uint16_t* __restrict__ Os, long long os_stride,
