@@ -83,7 +83,8 @@ struct ffb_handle {
     int opt_persist = 1;                          // whole greedy loop as one persistent cooperative kernel (persist.cuh): 0 off, 1 auto (small batches), 2 wherever supported
     int pd_grid = 0;                              // co-resident CTAs of decode_persistent_kernel on this device (0: cooperative launch unavailable)
     DevBuf pd_sync, pd_prof;                      // unsigned barrier counter + int[T] per-step counters; FFB_PD_PROF clock sums
-    bool used_persist = false;                    // the last decode ran in the persistent kernel
+    bool used_persist = false;                    // the last decode ran (at least its first steps) in the persistent kernel
+    bool l0_suspend = false;                      // ... and the per-step kernels behind it must not read the layer-0 cache
     const unsigned char* train_kmask = nullptr;   // non-null while ffb_forward_train runs its decoder pass: label padding mask [B * (T - 1)]
     DevBuf d_label, d_label_mask, d_kmask, dn_q_begin, dn_edge_dst, dn_pos_idx;
     int opt_l0cache = 1;                          // decoder layer 0: q / k / v of earlier prefix positions are cached (exact), only the new position is projected
@@ -1239,7 +1240,7 @@ int run_step(ffb_handle* h, int P, bool append, cudaStream_t s) {
             const ffb_handle::DecTcW& Tw = TS.layers[li];
             // layer 0 inside the greedy loop: q / k / v of the positions that existed in the previous step are unchanged (exact): project the
             // NEW position only (B rows instead of B * P) and assemble the (sequence, position)-ordered operand from the cache
-            const bool l0 = (li == 0) && append && hp && h->l0_ok && !last;
+            const bool l0 = (li == 0) && append && hp && h->l0_ok && !h->l0_suspend && !last;
             if (l0) {
                 launch_k(h, copy_rows_kernel, dim3(grid1d((long long)B * (E / 4))), dim3(256), 0, s, (const float*)x, xl, B, P, P - 1, E, stop);
                 h->launches++; CU(h, cudaGetLastError());
@@ -1394,19 +1395,24 @@ constexpr int FFB_PD_UNAVAILABLE = 1;         // run_persistent: the cooperative
 constexpr long long PD_AUTO_ROWS = 896;      // auto mode: batches with at most this many decoder rows (sequences x (T - 1)) in the last step; measured crossover
                                              // with the multi-kernel path at 860-1010 rows (profiles/probe_persist_threshold_r2.json)
 
-bool persist_applicable(const ffb_handle* h) {
-    if (!h->opt_persist || h->pd_grid <= 0) return false;
-    if (h->tc_fmt != 2 || !h->tc_ok || !h->opt_tc) return false;
+// Decode steps the persistent kernel takes for the encoded batch (0 = none).  Hybrid mode (3): the steps whose row count (sequences x prefix
+// length) stays in the latency-bound regime; the rest of the loop runs on the per-step kernels (the two share tok / state, so the hand-over is
+// free -- but the layer-0 q / k / v cache is lost for the rest of that decode).
+int persist_steps(const ffb_handle* h) {
+    if (!h->opt_persist || h->pd_grid <= 0) return 0;
+    if (h->tc_fmt != 2 || !h->tc_ok || !h->opt_tc) return 0;
     const ffb_handle::TcSet& TS = h->tcs[0];
-    if (!TS.ready || (int)TS.layers.size() != h->Ld) return false;
-    if (!h->opt_head64 || h->W != 1 || h->xchg_on || h->encode_only) return false;
-    if (h->N > pd::MAX_WF || h->Ld > pd::MAX_LAYERS || h->E % 128 != 0 || h->E > 1024 || h->FF % pd::TK != 0 || h->H * 64 != h->E) return false;
-    if (h->opt_persist == 2) return true;
-    // auto: the launch-bound regime only, and never when a test forces one of the multi-kernel pipelines
-    return h->opt_tc == 1 && h->B * (long long)(h->T - 1) <= PD_AUTO_ROWS;
+    if (!TS.ready || (int)TS.layers.size() != h->Ld) return 0;
+    if (!h->opt_head64 || h->W != 1 || h->xchg_on || h->encode_only) return 0;
+    if (h->N > pd::MAX_WF || h->Ld > pd::MAX_LAYERS || h->E % 128 != 0 || h->E > 1024 || h->FF % pd::TK != 0 || h->H * 64 != h->E) return 0;
+    if (h->opt_persist == 2) return h->T - 1;
+    // auto / hybrid: never when a test forces one of the multi-kernel pipelines
+    if (h->opt_tc != 1 || h->B <= 0) return 0;
+    if (h->opt_persist == 3) return (int)std::min<long long>(h->T - 1, PD_AUTO_ROWS / h->B);     // hybrid: the first steps only
+    return (h->B * (long long)(h->T - 1) <= PD_AUTO_ROWS) ? h->T - 1 : 0;                         // auto: whole decodes that stay below the crossover
 }
 
-int run_persistent(ffb_handle* h, cudaStream_t s) {
+int run_persistent(ffb_handle* h, int max_steps, cudaStream_t s) {
     const ffb_handle::TcSet& TS = h->tcs[0];
     pd::Params p{};
     for (int li = 0; li < h->Ld; ++li) {
@@ -1420,7 +1426,7 @@ int run_persistent(ffb_handle* h, cudaStream_t s) {
         L.n1w = Lw.n1w; L.n1b = Lw.n1b; L.n2w = Lw.n2w; L.n2b = Lw.n2b; L.n3w = Lw.n3w; L.n3b = Lw.n3b;
     }
     p.Ld = h->Ld; p.E = h->E; p.FF = h->FF; p.H = h->H; p.B = (int)h->B; p.T = h->T; p.N = h->N; p.Lrows = h->L; p.mode = h->cfg.mode;
-    p.num_token = h->cfg.num_token;
+    p.num_token = h->cfg.num_token; p.max_steps = max_steps;
     p.x = h->x.as<float>(); p.qkv = h->qkv.as<float>();
     p.xs = h->a_x2.as<uint16_t>(); p.xps = h->a_x2p.as<uint16_t>(); p.atts = h->a_att.as<uint16_t>(); p.hs = h->a_h.as<uint16_t>();
     p.ssE = h->cap_rows * h->E; p.ssF = h->cap_rows * h->FF;
@@ -1595,7 +1601,7 @@ int ffb_set_option(ffb_handle* h, int option, int value) {
         case FFB_OPT_HEAD_FP64: h->opt_head64 = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_L0_CACHE: h->opt_l0cache = value ? 1 : 0; h->encoded = false; return FFB_OK;
         case FFB_OPT_PERSISTENT:
-            if (value < 0 || value > 2) return fail(h, FFB_ERR_ARG, "FFB_OPT_PERSISTENT: 0 off, 1 auto, 2 wherever supported");
+            if (value < 0 || value > 3) return fail(h, FFB_ERR_ARG, "FFB_OPT_PERSISTENT: 0 off, 1 auto, 2 wherever supported, 3 hybrid");
             h->opt_persist = value; return FFB_OK;
         case FFB_OPT_SKINNY_GEMM: h->opt_skinny = value ? 1 : 0; return FFB_OK;
         case FFB_OPT_ATTN_LONG: h->opt_attn_long = value ? 1 : 0; return FFB_OK;
@@ -1774,18 +1780,22 @@ int ffb_decode_greedy(ffb_handle* h, int64_t* predict, int loc, int32_t* steps_r
         }
         for (int i = 0; i < T; ++i) h->h_stop[i] = 0;
         h->steps_launched = 0;
-        h->used_persist = persist_applicable(h);
+        int pd_steps = persist_steps(h);
+        h->used_persist = pd_steps > 0;
         if (h->used_persist) {
-            // small batch: every step of the loop inside ONE cooperative kernel; the stop predicate never leaves the device
-            const int prc = run_persistent(h, s);
-            if (prc == FFB_PD_UNAVAILABLE) h->used_persist = false;
+            // small batch: the loop (or its first steps, while sequences x prefix length stays in the latency-bound regime) inside ONE
+            // cooperative kernel; the stop predicate never leaves the device
+            const int prc = run_persistent(h, pd_steps, s);
+            if (prc == FFB_PD_UNAVAILABLE) { h->used_persist = false; pd_steps = 0; }
             else if (prc != FFB_OK) return prc;
         }
         if (h->used_persist) {
             if (!h->opt_prune) FFB_TRY(run_project_rows(h, s));       // seq2seq 'pointer' (model.py:216-217): project(decoder.norm(.)) of every position
-            h->steps_launched = T - 1;
-        } else
-        for (int step = 0; step < T - 1; ++step) {
+            h->steps_launched = pd_steps;
+            if (pd_steps < T - 1) CU(h, cudaMemcpyAsync((void*)(h->h_stop + pd_steps - 1), st, sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        h->l0_suspend = h->used_persist;              // the layer-0 q / k / v cache holds nothing for the positions the persistent kernel decoded
+        for (int step = pd_steps; step < T - 1; ++step) {
             bool stopped = false;
             for (int i = 0; i < step && !stopped; ++i) stopped = h->h_stop[i] != 0;
             if (stopped) break;

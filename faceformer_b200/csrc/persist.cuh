@@ -70,6 +70,8 @@ struct LayerP {
 struct Params {
     LayerP L[MAX_LAYERS];
     int Ld, E, FF, H, B, T, N, Lrows, mode, num_token;
+    int max_steps;                                 // decode steps this launch may run (<= T - 1): the host continues with the per-step kernels
+                                                   // behind it when the batch outgrows the latency-bound regime (rows = sequences x prefix length)
     float *x, *qkv;                                // fp32: residual stream [M, E]; q,k,v [M, 3E]; rows ordered (sequence, position)
     uint16_t *xs, *xps, *atts, *hs;                // fp16x2 GEMM operands [2][cap][E or FF]: LN(x), LN(x) + qpos, attention output, FFN hidden
     long long ssE, ssF;                            // elements between the two halves of a split array
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_persistent_kernel(const __g
     unsigned target = 0;
     const int E = p.E, FF = p.FF;
     int steps = 0, eos_total = 0, stopped = 0;
-    for (int step = 0; step < p.T - 1; ++step) {
+    for (int step = 0; step < p.max_steps; ++step) {
         const int P = step + 1;
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -136,7 +136,10 @@ enum { FFB_OPT_L0_CACHE = 22 };
  * between the phases of a step, the stop predicate (model_para.py:232 / model.py:207-210) evaluated on the device.  0 = off; 1 (default) =
  * auto: batches of at most 896 decoder rows (sequences x (T - 1): one small wireframe per batch as in the reference's test loop,
  * trainer.py:51, and seq2seq) while no option forces one of the multi-kernel pipelines; 2 = wherever it is supported (fp16x2 operand format,
- * float64 head, beam width 1, no batch splitting, <= 64 wireframes).  Larger batches are tensor-bound and stay on the tcgen05 kernels. */
+ * float64 head, beam width 1, no batch splitting, <= 64 wireframes); 3 = hybrid: the first steps of ANY supported batch, while sequences x prefix
+ * length <= 896, then the per-step kernels take over from the same token / state buffers (meant for checkpoints whose decodes stop after a few
+ * steps; on the synthetic batch-1 loop, where no decode stops early, it measured 2 % slower than mode 1 because the layer-0 cache is lost for the
+ * rest of the decode).  Larger batches are tensor-bound and stay on the tcgen05 kernels. */
 enum { FFB_OPT_PERSISTENT = 23 };
 
 /* 1: ffb_encode computes the encoder memory only (embedding, encoder layers, final norm; ffb_get_memory reads it) -- no decode

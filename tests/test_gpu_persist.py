@@ -82,6 +82,27 @@ def test_auto_mode_takes_the_persistent_kernel_only_below_the_measured_crossover
     assert small["launches"] < large["launches"] / 10
 
 
+def test_hybrid_mode_hands_over_to_the_per_step_kernels_at_the_measured_crossover():
+    """FFB_OPT_PERSISTENT = 3: the persistent kernel runs the steps whose row count (sequences x prefix length) is <= 896
+    (profiles/probe_persist_threshold_r2.json) and the per-step kernels continue from the same token / state buffers: a 7-edge wireframe is
+    decoded entirely inside it (7 x 36 = 252 rows), a 40-edge one for its first 22 steps, a 120-edge one for 7 -- all token-identical to the
+    multi-kernel decode."""
+    cfg = OURS
+    g = dict(cfg=cfg, mode=MODE_PARALLEL, sd=synth.synth_state_dict(cfg, MODE_PARALLEL, 5, "diverse"))
+    prev = None
+    for seed, n in ((35, 7), (36, 40), (37, 120)):
+        batch = synth.synth_batch(cfg, MODE_PARALLEL, 1, seed, lo=n, hi=n)
+        a, b = decode(g, batch, 3), decode(g, batch, 0)
+        assert a["used"] and not b["used"]
+        assert a["steps"] == b["steps"] and np.array_equal(a["pred"], b["pred"]), f"{n} edges: {(a['pred'] != b['pred']).sum()} token mismatches"
+        ok, d = logits_close(a["logits"], b["logits"])
+        assert ok, d
+        assert a["launches"] < b["launches"]
+        if prev is not None:
+            assert a["launches"] > prev                     # fewer steps inside the persistent kernel as the wireframe grows
+        prev = a["launches"]
+
+
 @pytest.mark.parametrize("cfg,mode,n,seed,lo,hi,steps", [(SEQ2SEQ, MODE_SEQ2SEQ, 2, 68, 6, 14, 4),      # cumulative EOS count reaches N at step 4 (model.py:207-210)
                                                          (SEQ2SEQ, MODE_SEQ2SEQ, 2, 62, 6, 14, 2),
                                                          (OURS, MODE_PARALLEL, 1, 108, 5, 9, 5),        # all sequences emit a special token at step 5 (model_para.py:232)
@@ -100,4 +121,19 @@ def test_early_stop_is_decided_on_the_device_like_the_reference_does(cfg, mode, 
         assert r["steps"] == steps
         assert np.array_equal(r["pred"], want["predict"]), f"{(r['pred'] != want['predict']).sum()} token mismatches"
     ok, d = logits_close(a["logits"], want["logits"][-1])
+    assert ok, d
+
+
+def test_hybrid_mode_early_stop_inside_the_persistent_part():
+    """30 edges: the persistent kernel may run 29 of the 36 steps (mode 3); the batch stops at step 2 inside it, so the 7 steps that were
+    launched behind it on the per-step kernels must all exit on the device-side stop flag -- tokens, steps and padding as the oracle's loop."""
+    cfg, seed = OURS, 216
+    sd = synth.synth_state_dict(cfg, MODE_PARALLEL, seed, "diverse")
+    batch = synth.synth_batch(cfg, MODE_PARALLEL, 1, seed, lo=30, hi=30)
+    want = orc.forward_eval(sd, cfg.to_dict(), MODE_PARALLEL, batch, return_trace=True, max_steps=5)
+    assert want["steps"] == 2
+    r = decode(dict(cfg=cfg, mode=MODE_PARALLEL, sd=sd), batch, 3)
+    assert r["used"] and r["steps"] == 2
+    assert np.array_equal(r["pred"], want["predict"])
+    ok, d = logits_close(r["logits"], want["logits"][-1])
     assert ok, d
