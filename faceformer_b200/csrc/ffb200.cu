@@ -1472,6 +1472,9 @@ int run_persistent(ffb_handle* h, int max_steps, cudaStream_t s) {
             if (v[o + 5] > 0)
                 fprintf(stderr, "[pd] %s attention item, CTA 0 warp 0 (avg clk over %lld items): Q + first tile landed %lld, S + softmax %lld, P V (+ later tiles) %lld, partials + barrier %lld, merge + store %lld\n",
                         o == 32 ? "self" : "cross", v[o + 5], v[o] / v[o + 5], v[o + 1] / v[o + 5], v[o + 2] / v[o + 5], v[o + 3] / v[o + 5], v[o + 4] / v[o + 5]);
+        if (v[52] > 0)
+            fprintf(stderr, "[pd] head of CTA 0 (avg clk over %lld sequences): row -> smem %lld, float64 LayerNorm %lld, memory-row scan %lld, merge + append %lld\n", v[52],
+                    v[48] / v[52], v[49] / v[52], v[50] / v[52], v[51] / v[52]);
         if (v[27] > 0)
             fprintf(stderr, "[pd] residual-projection item of CTA 0 (avg clk over %lld items): issue %lld, first pair landed %lld, mainloop %lld, hand-over %lld, epilogue %lld\n",
                     v[27], v[11] / v[27], v[12] / v[27], v[13] / v[27], v[14] / v[27], v[15] / v[27]);

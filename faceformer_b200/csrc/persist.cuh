@@ -610,31 +610,59 @@ __device__ __forceinline__ void head_phase(const Params& p, uint8_t* smem, int P
     float* hy = reinterpret_cast<float*>(smem);                        // [E]
     float* bestv = reinterpret_cast<float*>(smem + OFF_MISC);
     int* besti = reinterpret_cast<int*>(smem + OFF_MISC + 32);
+    const bool probe = p.prof && blockIdx.x == 0 && tid == 0;
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
+        const long long h0 = probe ? clock64() : 0;
         {   // the row goes to shared memory first: three short float64 passes over it, nothing held in registers
             const float* xr = p.x + ((size_t)b * P + (P - 1)) * E;
             for (int c = tid; c < E; c += THREADS) hy[c] = __ldcg(xr + c);
         }
         __syncthreads();
-        if (w == 0) {
+        const long long h1 = probe ? clock64() : 0;
+        {   // all 8 warps: thread t owns elements t, t + 256, ... (E <= 1024: at most 4); two block-wide float64 reductions through shared memory
+            double* red64 = reinterpret_cast<double*>(smem + 8192);          // [8] partials (the staged row uses the first E * 4 <= 4096 bytes)
+            float xv[4]; float gw[4], gb[4];
+            int ne = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = tid + k * THREADS;
+                if (c < E) { xv[k] = hy[c]; gw[k] = __ldg(p.dec_nw + c); gb[k] = __ldg(p.dec_nb + c); ne = k + 1; }
+            }
             double s = 0.0;
-            for (int c = lane; c < E; c += 32) s += (double)hy[c];
-            const double mean = e64::warp_sum_d(s) / E;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < ne) s += (double)xv[k];
+            s = e64::warp_sum_d(s);
+            if (lane == 0) red64[w] = s;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < THREADS / 32; ++k) tot += red64[k];
+            const double mean = tot / E;
             double q = 0.0;
-            for (int c = lane; c < E; c += 32) { const double dd = (double)hy[c] - mean; q = fma(dd, dd, q); }
-            const double rstd = 1.0 / sqrt(e64::warp_sum_d(q) / E + 1e-5);
-            for (int c = lane; c < E; c += 32) hy[c] = (float)(((double)hy[c] - mean) * rstd * (double)__ldg(p.dec_nw + c) + (double)__ldg(p.dec_nb + c));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < ne) { const double dd = (double)xv[k] - mean; q = fma(dd, dd, q); }
+            q = e64::warp_sum_d(q);
+            __syncthreads();
+            if (lane == 0) red64[w] = q;
+            __syncthreads();
+            double qt = 0.0;
+#pragma unroll
+            for (int k = 0; k < THREADS / 32; ++k) qt += red64[k];
+            const double rstd = 1.0 / sqrt(qt / E + 1e-5);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < ne) hy[tid + k * THREADS] = (float)(((double)xv[k] - mean) * rstd * (double)gw[k] + (double)gb[k]);
         }
         __syncthreads();
+        const long long h2 = probe ? clock64() : 0;
         const int wf = p.seq_wf[b];
         const int r0 = reinterpret_cast<const int*>(smem + OFF_WFI)[(MAX_WF + 1) + wf], vl = reinterpret_cast<const int*>(smem + OFF_WFI)[2 * (MAX_WF + 1) + wf];
         const int ldm = E + 4;
         float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int j0 = w; j0 < vl; j0 += 4 * (THREADS / 32)) {          // four rows in flight per warp (same per-row arithmetic and row order)
-            float4 mv[4][NV]; float mb[4];
+        for (int j0 = w; j0 < vl; j0 += 2 * (THREADS / 32)) {          // two rows in flight per warp (same per-row arithmetic and row order)
+            float4 mv[2][NV]; float mb[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int j = j0 + u * (THREADS / 32);
                 if (j < vl) {
                     const float* mr = p.memW + (size_t)(r0 + j) * ldm;
@@ -644,7 +672,7 @@ __device__ __forceinline__ void head_phase(const Params& p, uint8_t* smem, int P
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int j = j0 + u * (THREADS / 32);
                 if (j >= vl) continue;
                 float sd = 0.f;
@@ -661,6 +689,7 @@ __device__ __forceinline__ void head_phase(const Params& p, uint8_t* smem, int P
             }
         }
         for (int j = vl + tid; j < p.Lrows; j += THREADS) p.logits[(size_t)b * p.Lrows + j] = -FLT_MAX;   // finfo.min
+        const long long h3 = probe ? clock64() : 0;
         if (lane == 0) { bestv[w] = bv; besti[w] = bi; }
         __syncthreads();
         if (tid == 0) {
@@ -673,6 +702,7 @@ __device__ __forceinline__ void head_phase(const Params& p, uint8_t* smem, int P
             p.tok[(size_t)P * p.B + b] = idx;
             // parallel (model_para.py:232): sequences that did NOT emit a special token; seq2seq (model.py:207-210): EOS tokens (config.py:44)
             if (p.mode == 0 ? (idx >= p.num_token) : (idx == 3)) atomicAdd(p.counts + step, 1);
+            if (probe) { const long long h4 = clock64(); p.prof[48] += h1 - h0; p.prof[49] += h2 - h1; p.prof[50] += h3 - h2; p.prof[51] += h4 - h3; p.prof[52] += 1; }
         }
     }
 }
